@@ -1,0 +1,93 @@
+"""The front-end oracle against the committed golden vectors (made by running the
+reference's File_Processor, oracle/make_golden.py) and, in the build container, against
+the reference itself run through the third-party shims."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import frontend_oracle as fo
+from tests import helpers as H
+
+
+@pytest.mark.parametrize("case", H.FRONTEND_CASES, ids=[c[0] for c in H.FRONTEND_CASES])
+def test_oracle_matches_golden(case):
+    gold = H.load("frontend.npz")
+    name, _, _, kw = case
+    pcm = H.frontend_pcm(case, gold)
+    r = fo.process(pcm, fo.derive_params(**kw))
+    assert len(r.tiles) == int(gold[name + "/n_tiles"])
+    assert r.spectrogram_length == int(gold[name + "/spectrogram_length"])
+    p = r.params
+    assert [p.w_pix, p.hop_spectro, p.n_fft, p.hop, p.low_idx, p.high_idx] == gold[name + "/consts"].tolist()
+    np.testing.assert_array_equal(
+        np.array([p.freq_accuracy, p.dt, p.low_freq, p.high_freq]), gold[name + "/fconsts"])
+    tiles = np.stack(r.tiles)
+    np.testing.assert_array_equal(tiles[:, ::H.ROW_STRIDE, ::H.COL_STRIDE].astype(np.float32), gold[name + "/sample"])
+    np.testing.assert_array_equal(tiles[:, :, -1].astype(np.float32), gold[name + "/last_col"])
+    np.testing.assert_allclose(tiles.sum(axis=(1, 2)), gold[name + "/tile_sum"], rtol=0, atol=1e-9)
+    assert tiles.min() == 0.0 and tiles.max() == 1.0
+
+
+def test_frame_and_tile_counts():
+    p = fo.derive_params()
+    # SURVEY.md section 8 table
+    for n, T, tiles in [(441000, 3341, 4), (1323000, 10023, 12), (2646000, 20046, 25),
+                        (26460000, 200455, 245), (149984100, 1136244, 1388)]:
+        assert fo.n_frames(n, p) == T
+        assert fo.n_tiles(T, p) == tiles
+
+
+def test_reflect_padding_is_exact_copy():
+    p = fo.derive_params()
+    for secs, seed in [(0.5, 12), (2.0, 11)]:
+        from birdsoundclassif_b200 import synth
+        r = fo.process(synth.synth_pcm(secs, seed), p)
+        w = r.spectrogram_length
+        t = r.tiles[-1]
+        for j in range(w, p.w_pix, 37):
+            np.testing.assert_array_equal(t[:, j], t[:, fo.reflect_index(j, w)])
+
+
+def test_tile_plan_seam_quirk():
+    p = fo.derive_params()
+    # one chunk: plain windows
+    plan = fo.tile_plan([3000], p)
+    assert plan[0] == [(0, 0, 1024)] and plan[-1][0][0] == 0
+    # two chunks: a window crossing the seam concatenates both sides...
+    plan = fo.tile_plan([1500, 1500], p)
+    assert plan[1] == [(0, 819, 1500), (1, 0, 819 + 1024 - 1500)]
+    # ...but a window starting in chunk 0 and ending past the end of the FILE keeps chunk 0 only
+    plan = fo.tile_plan([1000, 100], p)
+    assert plan[-1] == [(0, 819, 1000)]
+
+
+@pytest.mark.reference
+def test_oracle_equals_reference_bit_for_bit(tmp_path):
+    from birdsoundclassif_b200 import synth
+    from oracle import ref_shims
+    pd = ref_shims.ref("nbm_model.nbm_datasets.prepare_dataset")
+    for secs, seed, kw in [(3.7, 21, {}), (0.9, 22, {}), (1.2, 23, dict(freq_accuracy=20.0, dt=0.002, overlap_spectro=0.5, w_pix=256))]:
+        pcm = synth.synth_pcm(secs, seed)
+        path = synth.write_wav(str(tmp_path / f"s{seed}.wav"), pcm)
+        fp = pd.File_Processor(path)
+        ref_tiles, _ = fp.process_file(**kw)
+        r = fo.process_file(path, **kw)
+        assert len(ref_tiles) == len(r.tiles) and fp.spectrogram_length == r.spectrogram_length
+        for a, b in zip(ref_tiles, r.tiles):
+            assert a.dtype == np.float64
+            np.testing.assert_array_equal(np.asarray(a), b)
+
+
+@pytest.mark.reference
+def test_shim_stft_agrees_with_torch_stft():
+    """Independent cross-check of the librosa restatement (float64 torch.stft, centre, zero pad,
+    periodic Hann): agreement to complex64 rounding."""
+    import torch
+    from birdsoundclassif_b200 import synth
+    y = fo.to_float(synth.synth_pcm(1.5, 31))
+    z = fo.stft(y, 1324, 132)
+    t = torch.stft(torch.from_numpy(y).double(), 1324, 132, window=torch.hann_window(1324, periodic=True, dtype=torch.float64),
+                   center=True, pad_mode="constant", return_complex=True).numpy()
+    assert z.shape == t.shape
+    assert np.abs(z - t).max() <= 2e-6 * np.abs(t).max()
