@@ -1,0 +1,575 @@
+// Front-end kernels: PCM -> dB band spectrogram (+ per-file min/max) -> normalised detector tiles.
+//
+// Replaces File_Processor.spectrogram / split_power_spec of the reference
+// (nbm_model/nbm_datasets/prepare_dataset.py:228-294) and librosa.stft as called at :237.
+//
+// Algorithm (exact DFT bins of an n_fft that need not be a power of two; 1324 = 4*331 here):
+//   R_t[k]  = sum_n x[t*hop - n_fft/2 + n] w^(kn),  w = exp(-2 pi i / n_fft)   (rectangular window)
+//   X_t[k]  = R_t[k]/2 - (R_t[k-1] + R_t[k+1])/4                               (periodic Hann, exact)
+//   R_{t+1} = w^(-hop k) (R_t + D_t),  D_t[k] = sum_{m<hop} (x[s_t+n_fft+m] - x[s_t+m]) w^(km)
+// Frames overlap by 1 - hop/n_fft (90 %), so instead of one n_fft-point transform per frame each
+// group of 64 frames computes ONE direct anchor DFT (middle frame) and slides it 32 frames forward
+// and 32 backward with hop-point difference DFTs.  Both the anchor and the hop-point sums are
+// folded about their centre (cos part uses x[c+u]+x[c-u], sin part x[c+u]-x[c-u]) which halves the
+// multiply-adds.  Thread = frequency bin, so the per-frame recurrence is register-resident; the
+// Hann combination uses warp shuffles (each warp computes 32 bins, emits the inner 30).
+#include <mutex>
+#include <vector>
+#include <cmath>
+
+#include "common.cuh"
+
+namespace nbm {
+
+constexpr int GF = 64;      // frames per group (one anchor per group)
+constexpr int PASS = 32;    // frames slid per direction
+constexpr int BINS_PER_WARP = 30;
+constexpr int STAGE_LD = PASS + 1;
+constexpr int TILE_ROWS = 15;   // spectrogram rows per block in the tiling kernel
+
+struct SegDesc {
+    long long pcm_start;   // per-channel sample index of the segment's first sample
+    long long n_samples;   // samples in this STFT chunk (prepare_dataset.py:236-237)
+    long long spec_off;    // float offset of S[0][first column of this segment]
+    int n_frames;
+    int row_stride;
+    int file;
+    int group0;            // index of the segment's first 64-frame group
+};
+
+struct FileDesc {
+    long long spec_off;    // float offset of the file's S[0][0]
+    long long tile0;       // index of the file's first tile in d_tiles
+    int row_stride;
+    int n_tiles;
+    int total_frames;
+    int last_width;        // valid columns of the last tile (rest is reflect padding)
+};
+
+struct KParams {
+    int N, hop, low_idx, n_bins, w_pix, hop_spectro;
+    int npN, npH;          // folded pair counts, ceil(N/2), ceil(hop/2)
+    int buf_len;           // N + (GF-1)*hop
+    float min_level_sq;
+    const float2 *tw;      // [2N] (cos, sin)(pi q / N)
+};
+
+__device__ __forceinline__ float load_sample(const void *pcm, int dtype, int channels, long long idx) {
+    float s = 0.f;
+    if (dtype == NBM_PCM_INT16) {
+        const short *p = reinterpret_cast<const short *>(pcm) + idx * channels;
+        for (int c = 0; c < channels; ++c) s += (float)__ldg(p + c) * (1.0f / 32768.0f);
+    } else {
+        const float *p = reinterpret_cast<const float *>(pcm) + idx * channels;
+        for (int c = 0; c < channels; ++c) s += __ldg(p + c);
+    }
+    return channels == 1 ? s : s / (float)channels;
+}
+
+// pair j of a length-L fold: 2u = 2j + (L even), hi = (L-1+2u)/2, lo = (L-1-2u)/2
+__device__ __forceinline__ void fold_idx(int L, int j, int &hi, int &lo) {
+    int u2 = 2 * j + ((L & 1) ? 0 : 1);
+    hi = (L - 1 + u2) >> 1;
+    lo = (L - 1 - u2) >> 1;
+}
+
+__global__ void __launch_bounds__(512, 1)
+stft_db_kernel(KParams P, const SegDesc *__restrict__ segs, int n_segs, const void *__restrict__ pcm,
+               int dtype, int channels, float *__restrict__ spec, unsigned int *__restrict__ minmax_enc) {
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
+
+    // ---- which segment / group -------------------------------------------------------------
+    int lo_s = 0, hi_s = n_segs - 1;
+    while (lo_s < hi_s) {
+        int mid = (lo_s + hi_s + 1) >> 1;
+        if (segs[mid].group0 <= (int)blockIdx.x) lo_s = mid; else hi_s = mid - 1;
+    }
+    const SegDesc sd = segs[lo_s];
+    const int t0 = ((int)blockIdx.x - sd.group0) * GF;
+    const int nf = min(GF, sd.n_frames - t0);
+    const int a = nf >> 1;                       // anchor frame (local)
+    const int N = P.N, hop = P.hop, N2 = 2 * P.N;
+
+    const int buf_pad = (P.buf_len + 3) & ~3;
+    float *buf = smem;
+    float2 *F = reinterpret_cast<float2 *>(buf + buf_pad);
+    float2 *E = F + ((P.npN + 1) & ~1);
+    float *stage = reinterpret_cast<float *>(E + P.npH * PASS);
+
+    // ---- samples of the group (zero outside the segment: centre padding, pad_mode='constant') --
+    const long long s0 = (long long)t0 * hop - N / 2;
+    const int need = N + (nf - 1) * hop;
+    for (int i = tid; i < need; i += nthr) {
+        long long s = s0 + i;
+        buf[i] = (s >= 0 && s < sd.n_samples) ? load_sample(pcm, dtype, channels, sd.pcm_start + s) : 0.f;
+    }
+    __syncthreads();
+
+    // ---- anchor: folded pairs of frame a -------------------------------------------------------
+    const float *xa = buf + a * hop;
+    for (int j = tid; j < P.npN; j += nthr) {
+        int hi, lo;
+        fold_idx(N, j, hi, lo);
+        F[j] = (hi == lo) ? make_float2(xa[hi], 0.f) : make_float2(xa[hi] + xa[lo], xa[hi] - xa[lo]);
+    }
+    __syncthreads();
+
+    const int k = P.low_idx - 1 + warp * BINS_PER_WARP + lane;      // this thread's DFT bin
+    const int kk = k % N2;
+    const int step = (2 * kk) % N2;
+    float Rr, Ri;
+    {
+        int q = (N & 1) ? 0 : kk;
+        double dr = 0.0, di = 0.0;
+        for (int j0 = 0; j0 < P.npN; j0 += 32) {
+            float ar = 0.f, ai = 0.f;
+            const int j1 = min(j0 + 32, P.npN);
+            for (int j = j0; j < j1; ++j) {
+                const float2 f = F[j];
+                const float2 w = __ldg(P.tw + q);
+                ar = fmaf(f.x, w.x, ar);
+                ai = fmaf(f.y, w.y, ai);
+                q += step;
+                if (q >= N2) q -= N2;
+            }
+            dr += (double)ar;
+            di += (double)ai;
+        }
+        // R_a = exp(-i theta (N-1)/2) (A - iB)
+        const float2 c0 = __ldg(P.tw + (int)(((long long)kk * (N - 1)) % N2));
+        Rr = (float)((double)c0.x * dr - (double)c0.y * di);
+        Ri = (float)(-((double)c0.x * di + (double)c0.y * dr));
+    }
+    const float2 cf = __ldg(P.tw + (int)(((long long)kk * 2 * hop) % N2));     // e^{+i theta hop}
+    const float2 gf = __ldg(P.tw + (int)(((long long)kk * (hop + 1)) % N2));   // e^{+i theta (hop+1)/2}
+    const float2 gb = __ldg(P.tw + (int)(((long long)kk * (hop - 1)) % N2));   // e^{-i theta (hop-1)/2} = (c,-s)
+    const float Ra_r = Rr, Ra_i = Ri;
+
+    const int out_bin = warp * BINS_PER_WARP + lane - 1;
+    const bool emit = lane >= 1 && lane <= BINS_PER_WARP && out_bin < P.n_bins;
+    float vmin = INFINITY, vmax = -INFINITY;
+    float *spec_seg = spec + sd.spec_off;
+    const int n_warps = nthr >> 5;
+
+    auto emit_frame = [&](float r, float im, int col) {
+        const float lr = __shfl_up_sync(0xffffffffu, r, 1), li = __shfl_up_sync(0xffffffffu, im, 1);
+        const float rr = __shfl_down_sync(0xffffffffu, r, 1), ri = __shfl_down_sync(0xffffffffu, im, 1);
+        const float xr = 0.5f * r - 0.25f * (lr + rr);
+        const float xi = 0.5f * im - 0.25f * (li + ri);
+        const float p = fmaxf(fmaf(xr, xr, xi * xi), P.min_level_sq);
+        const float db = 3.0102999566398120f * __log2f(p);     // 10 log10(p)
+        if (emit) {
+            stage[out_bin * STAGE_LD + col] = db;
+            vmin = fminf(vmin, db);
+            vmax = fmaxf(vmax, db);
+        }
+    };
+
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool fwd = pass == 0;
+        const int cnt = fwd ? (nf - 1 - a) : a;          // hop-DFTs needed in this direction
+        // ---- folded hop-point differences, E[j][i] for the pass's frames ---------------------
+        for (int idx = tid; idx < P.npH * PASS; idx += nthr) {
+            const int j = idx / PASS, i = idx - j * PASS;
+            float2 e = make_float2(0.f, 0.f);
+            if (i < cnt) {
+                const int t = fwd ? (a + i) : (a - 1 - i);
+                const float *x = buf + t * hop;
+                int hi, lo;
+                fold_idx(hop, j, hi, lo);
+                const float dh = x[N + hi] - x[hi];
+                if (hi == lo) e = make_float2(dh, 0.f);
+                else { const float dl = x[N + lo] - x[lo]; e = make_float2(dh + dl, dh - dl); }
+            }
+            E[idx] = e;
+        }
+        __syncthreads();
+        // ---- G_t[k] = sum_j E+ cos - i sum_j E- sin, 32 frames in registers -------------------
+        float gr[PASS], gi[PASS];
+#pragma unroll
+        for (int i = 0; i < PASS; ++i) { gr[i] = 0.f; gi[i] = 0.f; }
+        if (cnt > 0) {
+            int q = (hop & 1) ? 0 : kk;
+            const float4 *E4 = reinterpret_cast<const float4 *>(E);
+            for (int j = 0; j < P.npH; ++j) {
+                const float2 w = __ldg(P.tw + q);
+#pragma unroll
+                for (int i2 = 0; i2 < PASS / 2; ++i2) {
+                    const float4 e = E4[j * (PASS / 2) + i2];
+                    gr[2 * i2] = fmaf(e.x, w.x, gr[2 * i2]);
+                    gi[2 * i2] = fmaf(e.y, w.y, gi[2 * i2]);
+                    gr[2 * i2 + 1] = fmaf(e.z, w.x, gr[2 * i2 + 1]);
+                    gi[2 * i2 + 1] = fmaf(e.w, w.y, gi[2 * i2 + 1]);
+                }
+                q += step;
+                if (q >= N2) q -= N2;
+            }
+        }
+        // ---- slide, Hann (shuffles), dB, stage -------------------------------------------------
+        Rr = Ra_r; Ri = Ra_i;
+        if (fwd) {
+            emit_frame(Rr, Ri, 0);
+#pragma unroll
+            for (int i = 0; i < PASS; ++i) {
+                if (i < cnt) {       // block-uniform
+                    const float Gr = gr[i], Gi = -gi[i];
+                    const float nr = cf.x * Rr - cf.y * Ri + gf.x * Gr - gf.y * Gi;
+                    const float ni = cf.x * Ri + cf.y * Rr + gf.x * Gi + gf.y * Gr;
+                    Rr = nr; Ri = ni;
+                    emit_frame(Rr, Ri, i + 1);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < PASS; ++i) {
+                if (i < cnt) {
+                    const float Gr = gr[i], Gi = -gi[i];
+                    // R_t = conj(cf) R_{t+1} - (gb.x - i gb.y) G_t
+                    const float nr = cf.x * Rr + cf.y * Ri - (gb.x * Gr + gb.y * Gi);
+                    const float ni = cf.x * Ri - cf.y * Rr - (gb.x * Gi - gb.y * Gr);
+                    Rr = nr; Ri = ni;
+                    emit_frame(Rr, Ri, a - 1 - i);
+                }
+            }
+        }
+        __syncthreads();
+        // ---- coalesced rows out -----------------------------------------------------------------
+        const int ncols = fwd ? (cnt + 1) : cnt;
+        const int col0 = t0 + (fwd ? a : 0);
+        for (int b = warp; b < P.n_bins; b += n_warps) {
+            if (lane < ncols) spec_seg[(long long)b * sd.row_stride + col0 + lane] = stage[b * STAGE_LD + lane];
+            if (lane + 32 < ncols) spec_seg[(long long)b * sd.row_stride + col0 + lane + 32] = stage[b * STAGE_LD + lane + 32];
+        }
+        __syncthreads();
+    }
+
+    // ---- per-file min / max ---------------------------------------------------------------------
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    }
+    float *red = stage;
+    if (lane == 0) { red[warp] = vmin; red[32 + warp] = vmax; }
+    __syncthreads();
+    if (warp == 0) {
+        vmin = lane < n_warps ? red[lane] : INFINITY;
+        vmax = lane < n_warps ? red[32 + lane] : -INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+            vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        }
+        if (lane == 0) {
+            atomicMin(minmax_enc + 2 * sd.file, float_to_ordered(vmin));
+            atomicMax(minmax_enc + 2 * sd.file + 1, float_to_ordered(vmax));
+        }
+    }
+}
+
+__global__ void init_minmax_kernel(unsigned int *enc, int n_files) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_files) { enc[2 * i] = 0xffffffffu; enc[2 * i + 1] = 0u; }
+}
+
+__global__ void finalize_minmax_kernel(const unsigned int *enc, float *out, int n_files) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_files) { out[2 * i] = ordered_to_float(enc[2 * i]); out[2 * i + 1] = ordered_to_float(enc[2 * i + 1]); }
+}
+
+// Normalise by the file's min/max and cut detector windows (prepare_dataset.py:248-250, 255-294);
+// columns past the file's end mirror numpy's iterated 'reflect' pad of the partial window.
+__global__ void __launch_bounds__(256)
+tile_kernel(KParams P, const FileDesc *__restrict__ files, int n_files, const float *__restrict__ spec,
+            const float *__restrict__ minmax, float *__restrict__ tiles) {
+    const long long tile = blockIdx.x;
+    int lo_f = 0, hi_f = n_files - 1;
+    while (lo_f < hi_f) {
+        int mid = (lo_f + hi_f + 1) >> 1;
+        if (files[mid].tile0 <= tile) lo_f = mid; else hi_f = mid - 1;
+    }
+    const FileDesc fd = files[lo_f];
+    const int kt = (int)(tile - fd.tile0);
+    const int start = kt * P.hop_spectro;
+    const int width = (kt == fd.n_tiles - 1) ? fd.last_width : P.w_pix;
+    const float smin = minmax[2 * lo_f], smax = minmax[2 * lo_f + 1];
+    const float range = smax - smin;
+    const int r0 = blockIdx.y * TILE_ROWS;
+    const int r1 = min(r0 + TILE_ROWS, P.n_bins);
+    const int period = 2 * (width - 1);
+    for (int c = threadIdx.x; c < P.w_pix; c += blockDim.x) {
+        int src = c;
+        if (c >= width) {
+            if (width == 1) src = 0;
+            else { int r = c % period; src = r < width ? r : period - r; }
+        }
+        const float *sp = spec + fd.spec_off + start + src;
+        float *tp = tiles + (tile * P.n_bins) * P.w_pix + c;
+        for (int r = r0; r < r1; ++r)
+            tp[(long long)r * P.w_pix] = __fdiv_rn(sp[(long long)r * fd.row_stride] - smin, range);
+    }
+}
+
+}  // namespace nbm
+
+// ------------------------------------------------------------------------------ host side ------
+using namespace nbm;
+
+struct nbm_frontend_plan {
+    nbm_frontend_params prm;
+    KParams kp;
+    float2 *d_tw = nullptr;
+    int device = 0;
+    int n_threads = 0;
+    size_t smem_bytes = 0;
+    // pinned staging for descriptor uploads
+    std::mutex mu;
+    void *h_stage = nullptr;
+    size_t h_stage_bytes = 0;
+    cudaEvent_t staged = nullptr;
+};
+
+namespace {
+
+struct FileLayout {
+    int64_t n_frames = 0, n_tiles = 0;
+    int last_width = 0;
+    int64_t row_stride = 0;
+    std::vector<int64_t> seg_samples, seg_frames;
+};
+
+FileLayout layout_of(const nbm_frontend_params &p, int64_t n) {
+    FileLayout L;
+    const int64_t n_chunks = n / p.stft_chunk + 1;          // range(int(len/max_l)+1), :236
+    for (int64_t c = 0; c < n_chunks; ++c) {
+        int64_t len = std::max<int64_t>(0, std::min<int64_t>(n, (c + 1) * p.stft_chunk) - c * p.stft_chunk);
+        L.seg_samples.push_back(len);
+        L.seg_frames.push_back(1 + len / p.hop);
+        L.n_frames += 1 + len / p.hop;
+    }
+    const int64_t T = L.n_frames;
+    // max(1, int(1 + ceil((T - w_pix) / hop_spectro)))  :266
+    int64_t nt = 1;
+    if (T > p.w_pix) nt = 1 + (T - p.w_pix + p.hop_spectro - 1) / p.hop_spectro;
+    L.n_tiles = std::max<int64_t>(1, nt);
+    // valid width of the last window, including the reference's seam quirk (:268-278): a window
+    // that starts in chunk c and runs past the end of the file keeps chunk c's columns only.
+    const int64_t start = (L.n_tiles - 1) * (int64_t)p.hop_spectro;
+    const int64_t end = start + p.w_pix;
+    if (end <= T) {
+        L.last_width = p.w_pix;
+    } else {
+        int64_t edge = 0;
+        size_t c = 0;
+        for (; c < L.seg_frames.size(); ++c) {
+            if (start < edge + L.seg_frames[c]) break;
+            edge += L.seg_frames[c];
+        }
+        L.last_width = (int)(edge + L.seg_frames[c] - start);
+    }
+    L.row_stride = (int64_t)align_up((size_t)T, 32);
+    return L;
+}
+
+size_t desc_bytes(size_t n_segs, size_t n_files) {
+    return align_up(n_segs * sizeof(SegDesc), 256) + align_up(n_files * sizeof(FileDesc), 256) +
+           align_up(n_files * 2 * sizeof(unsigned int), 256);
+}
+
+}  // namespace
+
+extern "C" int nbm_frontend_plan_create(const nbm_frontend_params *p, nbm_frontend_plan **out) {
+    NBM_REQUIRE(p && out, "null argument");
+    NBM_REQUIRE(p->n_fft >= 8 && p->hop >= 1 && p->hop <= p->n_fft, "need 1 <= hop <= n_fft, n_fft >= 8");
+    NBM_REQUIRE(p->low_idx >= 1 && p->n_bins >= 1 && p->low_idx + p->n_bins <= p->n_fft / 2 + 1,
+                "band [low_idx, low_idx+n_bins) must lie in [1, n_fft/2]");
+    NBM_REQUIRE(p->w_pix >= 1 && p->hop_spectro >= 1 && p->stft_chunk >= p->n_fft, "bad tiling parameters");
+    if (p->pad_mode != 0) {
+        set_error("pad_mode %d not supported (only 0 = 'constant', the librosa>=0.10 default)", p->pad_mode);
+        return NBM_ERR_UNSUPPORTED;
+    }
+    const int n_warps = (p->n_bins + BINS_PER_WARP - 1) / BINS_PER_WARP;
+    NBM_REQUIRE(n_warps <= 16, "n_bins too large for one block (max 480)");
+    auto *pl = new nbm_frontend_plan();
+    pl->prm = *p;
+    KParams &k = pl->kp;
+    k.N = p->n_fft; k.hop = p->hop; k.low_idx = p->low_idx; k.n_bins = p->n_bins;
+    k.w_pix = p->w_pix; k.hop_spectro = p->hop_spectro;
+    k.npN = (p->n_fft + 1) / 2; k.npH = (p->hop + 1) / 2;
+    k.buf_len = p->n_fft + (GF - 1) * p->hop;
+    k.min_level_sq = (float)(p->min_level * p->min_level);
+    pl->n_threads = 32 * n_warps;
+    pl->smem_bytes = (size_t)((k.buf_len + 3) & ~3) * 4 + (size_t)((k.npN + 1) & ~1) * 8 +
+                     (size_t)k.npH * PASS * 8 + (size_t)std::max(p->n_bins * STAGE_LD, 64) * 4;
+    cudaError_t e = cudaGetDevice(&pl->device);
+    if (e != cudaSuccess) { delete pl; return cuda_fail(e, "cudaGetDevice"); }
+    int max_smem = 0;
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, pl->device);
+    if ((size_t)max_smem < pl->smem_bytes) {
+        set_error("front-end needs %zu B of shared memory per block, device offers %d", pl->smem_bytes, max_smem);
+        delete pl;
+        return NBM_ERR_UNSUPPORTED;
+    }
+    const int N2 = 2 * p->n_fft;
+    std::vector<float2> tw(N2);
+    for (int q = 0; q < N2; ++q) {
+        const double ang = M_PI * (double)q / (double)p->n_fft;
+        tw[q] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+    if ((e = cudaMalloc(&pl->d_tw, N2 * sizeof(float2))) != cudaSuccess ||
+        (e = cudaMemcpy(pl->d_tw, tw.data(), N2 * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&pl->staged, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(stft_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)pl->smem_bytes)) != cudaSuccess) {
+        int rc = cuda_fail(e, "plan_create");
+        nbm_frontend_plan_destroy(pl);
+        return rc;
+    }
+    k.tw = pl->d_tw;
+    *out = pl;
+    return NBM_OK;
+}
+
+extern "C" int nbm_frontend_plan_destroy(nbm_frontend_plan *pl) {
+    if (!pl) return NBM_OK;
+    if (pl->d_tw) cudaFree(pl->d_tw);
+    if (pl->h_stage) cudaFreeHost(pl->h_stage);
+    if (pl->staged) cudaEventDestroy(pl->staged);
+    delete pl;
+    return NBM_OK;
+}
+
+extern "C" int nbm_frontend_query_batch(const nbm_frontend_plan *pl, const int64_t *n_samples, int32_t n_files,
+                                        int64_t *n_frames, int64_t *tile_offsets, size_t *workspace_bytes) {
+    NBM_REQUIRE(pl && n_samples && n_files >= 1, "bad argument");
+    size_t n_segs = 0, spec_floats = 0;
+    int64_t tiles = 0;
+    for (int f = 0; f < n_files; ++f) {
+        NBM_REQUIRE(n_samples[f] >= 0, "negative sample count");
+        FileLayout L = layout_of(pl->prm, n_samples[f]);
+        n_segs += L.seg_frames.size();
+        spec_floats += (size_t)L.row_stride * pl->prm.n_bins;
+        if (n_frames) n_frames[f] = L.n_frames;
+        if (tile_offsets) tile_offsets[f] = tiles;
+        tiles += L.n_tiles;
+    }
+    if (tile_offsets) tile_offsets[n_files] = tiles;
+    if (workspace_bytes) *workspace_bytes = desc_bytes(n_segs, n_files) + spec_floats * sizeof(float);
+    return NBM_OK;
+}
+
+extern "C" int nbm_frontend_query(const nbm_frontend_plan *pl, int64_t n_samples, int64_t *n_frames,
+                                  int64_t *n_tiles, size_t *workspace_bytes) {
+    int64_t off[2] = {0, 0};
+    int rc = nbm_frontend_query_batch(pl, &n_samples, 1, n_frames, off, workspace_bytes);
+    if (rc == NBM_OK && n_tiles) *n_tiles = off[1];
+    return rc;
+}
+
+extern "C" int nbm_frontend_spectrogram_view(const nbm_frontend_plan *pl, const int64_t *n_samples, int32_t n_files,
+                                             int32_t file_index, size_t *offset_bytes, int64_t *row_stride) {
+    NBM_REQUIRE(pl && n_samples && file_index >= 0 && file_index < n_files, "bad argument");
+    size_t n_segs = 0, spec_floats = 0, mine = 0;
+    for (int f = 0; f < n_files; ++f) {
+        FileLayout L = layout_of(pl->prm, n_samples[f]);
+        n_segs += L.seg_frames.size();
+        if (f == file_index) { mine = spec_floats; if (row_stride) *row_stride = L.row_stride; }
+        spec_floats += (size_t)L.row_stride * pl->prm.n_bins;
+    }
+    if (offset_bytes) *offset_bytes = desc_bytes(n_segs, n_files) + mine * sizeof(float);
+    return NBM_OK;
+}
+
+extern "C" int nbm_frontend_run_batch(const nbm_frontend_plan *cpl, const void *d_pcm, int32_t pcm_dtype,
+                                      int32_t channels, const int64_t *sample_offsets, int32_t n_files,
+                                      float *d_tiles, float *d_minmax, void *d_workspace, size_t workspace_bytes,
+                                      void *stream_) {
+    auto *pl = const_cast<nbm_frontend_plan *>(cpl);
+    NBM_REQUIRE(pl && d_pcm && sample_offsets && d_tiles && d_minmax && d_workspace, "null argument");
+    NBM_REQUIRE(n_files >= 1 && channels >= 1, "need n_files >= 1, channels >= 1");
+    NBM_REQUIRE(pcm_dtype == NBM_PCM_INT16 || pcm_dtype == NBM_PCM_FLOAT32, "unknown pcm_dtype %d", pcm_dtype);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const nbm_frontend_params &p = pl->prm;
+
+    std::vector<SegDesc> segs;
+    std::vector<FileDesc> files(n_files);
+    size_t spec_floats = 0;
+    long long tiles = 0;
+    int groups = 0;
+    for (int f = 0; f < n_files; ++f) {
+        const int64_t n = sample_offsets[f + 1] - sample_offsets[f];
+        NBM_REQUIRE(n >= 0, "sample_offsets must be non-decreasing");
+        FileLayout L = layout_of(p, n);
+        NBM_REQUIRE(L.row_stride < (1ll << 31), "file too long");
+        FileDesc &fd = files[f];
+        fd.spec_off = (long long)spec_floats;
+        fd.tile0 = tiles;
+        fd.row_stride = (int)L.row_stride;
+        fd.n_tiles = (int)L.n_tiles;
+        fd.total_frames = (int)L.n_frames;
+        fd.last_width = L.last_width;
+        long long col = 0, s = sample_offsets[f];
+        for (size_t c = 0; c < L.seg_frames.size(); ++c) {
+            SegDesc sd;
+            sd.pcm_start = s;
+            sd.n_samples = L.seg_samples[c];
+            sd.spec_off = fd.spec_off + col;
+            sd.n_frames = (int)L.seg_frames[c];
+            sd.row_stride = fd.row_stride;
+            sd.file = f;
+            sd.group0 = groups;
+            segs.push_back(sd);
+            groups += (int)((L.seg_frames[c] + GF - 1) / GF);
+            col += L.seg_frames[c];
+            s += L.seg_samples[c];
+        }
+        spec_floats += (size_t)L.row_stride * p.n_bins;
+        tiles += L.n_tiles;
+    }
+    const size_t seg_b = align_up(segs.size() * sizeof(SegDesc), 256);
+    const size_t file_b = align_up(files.size() * sizeof(FileDesc), 256);
+    const size_t mm_b = align_up((size_t)n_files * 2 * sizeof(unsigned int), 256);
+    const size_t need = seg_b + file_b + mm_b + spec_floats * sizeof(float);
+    if (workspace_bytes < need) {
+        set_error("workspace too small: %zu < %zu", workspace_bytes, need);
+        return NBM_ERR_WORKSPACE;
+    }
+    char *ws = reinterpret_cast<char *>(d_workspace);
+    SegDesc *d_segs = reinterpret_cast<SegDesc *>(ws);
+    FileDesc *d_files = reinterpret_cast<FileDesc *>(ws + seg_b);
+    unsigned int *d_enc = reinterpret_cast<unsigned int *>(ws + seg_b + file_b);
+    float *d_spec = reinterpret_cast<float *>(ws + seg_b + file_b + mm_b);
+
+    {
+        std::lock_guard<std::mutex> lock(pl->mu);
+        const size_t up = seg_b + file_b;
+        if (pl->h_stage_bytes < up) {
+            if (pl->h_stage) { NBM_CUDA(cudaEventSynchronize(pl->staged)); cudaFreeHost(pl->h_stage); pl->h_stage = nullptr; }
+            NBM_CUDA(cudaMallocHost(&pl->h_stage, up));
+            pl->h_stage_bytes = up;
+        } else {
+            NBM_CUDA(cudaEventSynchronize(pl->staged));     // previous upload has left the staging buffer
+        }
+        memcpy(pl->h_stage, segs.data(), segs.size() * sizeof(SegDesc));
+        memcpy((char *)pl->h_stage + seg_b, files.data(), files.size() * sizeof(FileDesc));
+        NBM_CUDA(cudaMemcpyAsync(ws, pl->h_stage, up, cudaMemcpyHostToDevice, stream));
+        NBM_CUDA(cudaEventRecord(pl->staged, stream));
+    }
+    init_minmax_kernel<<<(n_files + 255) / 256, 256, 0, stream>>>(d_enc, n_files);
+    stft_db_kernel<<<groups, pl->n_threads, pl->smem_bytes, stream>>>(pl->kp, d_segs, (int)segs.size(), d_pcm,
+                                                                      pcm_dtype, channels, d_spec, d_enc);
+    finalize_minmax_kernel<<<(n_files + 255) / 256, 256, 0, stream>>>(d_enc, d_minmax, n_files);
+    dim3 grid((unsigned)tiles, (unsigned)((p.n_bins + TILE_ROWS - 1) / TILE_ROWS));
+    tile_kernel<<<grid, 256, 0, stream>>>(pl->kp, d_files, n_files, d_spec, d_minmax, d_tiles);
+    NBM_CUDA(cudaGetLastError());
+    return NBM_OK;
+}
+
+extern "C" int nbm_frontend_run(const nbm_frontend_plan *pl, const void *d_pcm, int32_t pcm_dtype, int32_t channels,
+                                int64_t n_samples, float *d_tiles, float *d_minmax, void *d_workspace,
+                                size_t workspace_bytes, void *stream) {
+    int64_t off[2] = {0, n_samples};
+    return nbm_frontend_run_batch(pl, d_pcm, pcm_dtype, channels, off, 1, d_tiles, d_minmax, d_workspace,
+                                  workspace_bytes, stream);
+}

@@ -1,0 +1,580 @@
+// Detector post-processing kernels: anchor/RoI delta decode, clamp, min-size and score filters,
+// and the reference's in-order greedy NMS as a bitmask kernel pair.
+//
+// Replaces nbm_model/nets/util/nets_utils.py:35-59,169-245, ProposalLayer.forward
+// (nbm_model/nets/layers.py:226-303), the FastRCNN inference tail (layers.py:688-778) and
+// merge_images (nbm_model/run_detection.py:163-249).
+//
+// Bit-exactness: boxes are integer-valued float32; every IoU operation is a single IEEE
+// round-to-nearest op in the reference's order (no FMA contraction), the comparison is
+// `iou >= (float)thresh`, NaN never suppresses, and the greedy order is the INPUT order.
+#include <cub/cub.cuh>
+#include <vector>
+#include <climits>
+
+#include "common.cuh"
+
+namespace nbm {
+
+// ------------------------------------------------------------------------------ decode ------
+__device__ __forceinline__ float4 decode_one(float4 d, float4 a) {
+    // bbox_reg_to_coord, nets_utils.py:171-186; eager PyTorch = one rounding per op
+    const float wa = __fadd_rn(__fsub_rn(a.z, a.x), 1.0f);
+    const float ha = __fadd_rn(__fsub_rn(a.w, a.y), 1.0f);
+    const float xa = __fadd_rn(a.x, __fmul_rn(0.5f, wa));
+    const float ya = __fadd_rn(a.y, __fmul_rn(0.5f, ha));
+    const float x = __fadd_rn(__fmul_rn(d.x, wa), xa);
+    const float y = __fadd_rn(__fmul_rn(d.y, ha), ya);
+    const float w = __fmul_rn(expf(d.z), wa);
+    const float h = __fmul_rn(expf(d.w), ha);
+    const float hw = __fmul_rn(0.5f, w), hh = __fmul_rn(0.5f, h);
+    return make_float4(rintf(__fsub_rn(x, hw)), rintf(__fsub_rn(y, hh)),
+                       rintf(__fadd_rn(x, hw)), rintf(__fadd_rn(y, hh)));     // half-to-even == torch.round
+}
+
+__device__ __forceinline__ float4 clamp_box(float4 b, float clip_w, float clip_h) {
+    if (clip_w > 0.f) { b.x = fminf(fmaxf(b.x, 0.f), clip_w - 1.f); b.z = fminf(fmaxf(b.z, 0.f), clip_w - 1.f); }
+    if (clip_h > 0.f) { b.y = fminf(fmaxf(b.y, 0.f), clip_h - 1.f); b.w = fminf(fmaxf(b.w, 0.f), clip_h - 1.f); }
+    return b;
+}
+
+__device__ __forceinline__ bool big_enough(float4 b, float min_size) {
+    return (__fadd_rn(__fsub_rn(b.z, b.x), 1.0f) >= min_size) && (__fadd_rn(__fsub_rn(b.w, b.y), 1.0f) >= min_size);
+}
+
+__global__ void decode_kernel(const float4 *__restrict__ deltas, const float4 *__restrict__ anchors, int B, int N,
+                              int per_image, float clip_w, float clip_h, float min_size,
+                              float4 *__restrict__ boxes, uint8_t *__restrict__ valid) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * N) return;
+    const float4 a = per_image ? anchors[i] : anchors[i % N];
+    const float4 b = clamp_box(decode_one(deltas[i], a), clip_w, clip_h);
+    boxes[i] = b;
+    if (valid) valid[i] = big_enough(b, min_size) ? 1 : 0;
+}
+
+// --------------------------------------------------------------------------------- NMS -------
+__device__ __forceinline__ bool iou_ge(float4 a, float4 b, float area_a, float area_b, float thresh) {
+    // batch_self_overlap, nets_utils.py:193-205
+    const float xi = fmaxf(__fadd_rn(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 1.0f), 0.0f);
+    const float yi = fmaxf(__fadd_rn(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 1.0f), 0.0f);
+    const float inter = __fmul_rn(xi, yi);
+    const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+    return __fdiv_rn(inter, uni) >= thresh;       // NaN -> false
+}
+
+__device__ __forceinline__ float box_area(float4 b) {
+    return __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.0f), __fadd_rn(__fsub_rn(b.w, b.y), 1.0f));
+}
+
+// mask[b][i][w] bit j' set  <=>  j = 64 w + j' > i, j < n, IoU(i, j) >= thresh.   Upper triangle only.
+__global__ void __launch_bounds__(64)
+nms_mask_kernel(const float4 *__restrict__ boxes, const int *__restrict__ n_valid, const int *__restrict__ n_cap,
+                int N, float thresh, unsigned long long *__restrict__ mask, int words) {
+    const int b = blockIdx.z, rb = blockIdx.y, cb = blockIdx.x;
+    if (cb < rb) return;
+    int n = n_valid ? n_valid[b] : N;
+    if (n_cap) n = min(n, *n_cap);
+    n = min(n, N);
+    if (rb * 64 >= n || cb * 64 >= n) return;
+    __shared__ float4 cbox[64];
+    __shared__ float carea[64];
+    const float4 *bx = boxes + (long long)b * N;
+    const int t = threadIdx.x;
+    const int j0 = cb * 64;
+    if (j0 + t < n) { cbox[t] = bx[j0 + t]; carea[t] = box_area(cbox[t]); }
+    __syncthreads();
+    const int i = rb * 64 + t;
+    if (i >= n) return;
+    const float4 me = bx[i];
+    const float ma = box_area(me);
+    unsigned long long bits = 0;
+    const int lim = min(64, n - j0);
+    for (int jj = (cb == rb ? t + 1 : 0); jj < lim; ++jj)
+        if (iou_ge(cbox[jj], me, carea[jj], ma, thresh)) bits |= 1ull << jj;
+    mask[((long long)b * N + i) * words + cb] = bits;
+}
+
+// Sequential greedy resolution, one block per image, 64 boxes per step.
+__global__ void __launch_bounds__(256)
+nms_scan_kernel(const unsigned long long *__restrict__ mask, const int *__restrict__ n_valid,
+                const int *__restrict__ n_cap, int N, int words, int *__restrict__ keep_idx,
+                int *__restrict__ keep_cnt) {
+    extern __shared__ unsigned long long sm[];
+    unsigned long long *removed = sm;            // [words]
+    unsigned long long *kept = sm + words;       // [words]
+    __shared__ unsigned long long diag[64];
+    __shared__ unsigned long long keepbits;
+    __shared__ int total;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    int n = n_valid ? n_valid[b] : N;
+    if (n_cap) n = min(n, *n_cap);
+    n = min(n, N);
+    const unsigned long long *m = mask + (long long)b * N * words;
+    const int chunks = (n + 63) / 64;
+    for (int w = tid; w < words; w += blockDim.x) { removed[w] = 0; kept[w] = 0; }
+    __syncthreads();
+    for (int c = 0; c < chunks; ++c) {
+        if (tid < 64) {
+            const int i = c * 64 + tid;
+            diag[tid] = i < n ? m[(long long)i * words + c] : 0ull;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long cur = removed[c], kb = 0;
+            const int lim = min(64, n - c * 64);
+            for (int t = 0; t < lim; ++t)
+                if (!((cur >> t) & 1ull)) { kb |= 1ull << t; cur |= diag[t]; }
+            keepbits = kb;
+            kept[c] = kb;
+        }
+        __syncthreads();
+        const unsigned long long kb = keepbits;
+        for (int w = c + 1 + tid; w < chunks; w += blockDim.x) {
+            unsigned long long acc = 0, bits = kb;
+            while (bits) {
+                const int t = __ffsll((long long)bits) - 1;
+                bits &= bits - 1;
+                acc |= m[(long long)(c * 64 + t) * words + w];
+            }
+            removed[w] |= acc;
+        }
+        __syncthreads();
+    }
+    // compaction: ascending kept indices
+    if (tid == 0) {
+        int off = 0;
+        for (int c = 0; c < chunks; ++c) { const int pc = __popcll(kept[c]); removed[c] = (unsigned long long)off; off += pc; }
+        total = off;
+        keep_cnt[b] = off;
+    }
+    __syncthreads();
+    for (int c = tid; c < chunks; c += blockDim.x) {
+        unsigned long long bits = kept[c];
+        int off = (int)removed[c];
+        while (bits) {
+            const int t = __ffsll((long long)bits) - 1;
+            bits &= bits - 1;
+            keep_idx[(long long)b * N + off++] = c * 64 + t;
+        }
+    }
+    for (int i = total + tid; i < N; i += blockDim.x) keep_idx[(long long)b * N + i] = -1;
+}
+
+static inline int nms_words(int N) { return (N + 63) / 64; }
+
+static int launch_nms(const float *d_boxes, const int *d_n, const int *d_cap, int B, int N, float thresh,
+                      int *d_keep_idx, int *d_keep_cnt, void *ws, size_t ws_bytes, cudaStream_t s) {
+    const int words = nms_words(N);
+    const size_t need = (size_t)B * N * words * sizeof(unsigned long long);
+    if (ws_bytes < need) { set_error("nms workspace too small: %zu < %zu", ws_bytes, need); return NBM_ERR_WORKSPACE; }
+    const size_t smem = (size_t)2 * words * sizeof(unsigned long long);
+    NBM_REQUIRE(smem <= 200 * 1024, "N too large for the NMS scan kernel");
+    if (smem > 48 * 1024)
+        NBM_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(words, words, B);
+    nms_mask_kernel<<<grid, 64, 0, s>>>(reinterpret_cast<const float4 *>(d_boxes), d_n, d_cap, N, thresh,
+                                        reinterpret_cast<unsigned long long *>(ws), words);
+    nms_scan_kernel<<<B, 256, smem, s>>>(reinterpret_cast<const unsigned long long *>(ws), d_n, d_cap, N, words,
+                                         d_keep_idx, d_keep_cnt);
+    NBM_CUDA(cudaGetLastError());
+    return NBM_OK;
+}
+
+// --------------------------------------------------------------------------- proposals -------
+// scores/deltas from the RPN's [B, C, H, W] layout (layers.py:264-267), decode + clamp + min-size.
+__global__ void rpn_decode_kernel(const float *__restrict__ cls, const float *__restrict__ reg,
+                                  const float4 *__restrict__ anchors, int B, int A, int H, int W, float clip_w,
+                                  float clip_h, float min_size, float4 *__restrict__ boxes, float *__restrict__ keys,
+                                  int *__restrict__ idx, int *__restrict__ n_valid) {
+    const int N = A * H * W;
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)B * N) return;
+    const int b = (int)(g / N), n = (int)(g % N);
+    const int a = n % A, cell = n / A;           // cell = y*W + x
+    const long long hw = (long long)H * W;
+    const float *rb = reg + ((long long)b * 4 * A + 4 * a) * hw + cell;
+    const float4 d = make_float4(rb[0], rb[hw], rb[2 * hw], rb[3 * hw]);
+    const float score = cls[((long long)b * 2 * A + 2 * a + 1) * hw + cell];
+    const float4 bx = clamp_box(decode_one(d, anchors[n]), clip_w, clip_h);
+    boxes[g] = bx;
+    const bool ok = big_enough(bx, min_size);
+    keys[g] = ok ? score : -INFINITY;            // invalid boxes sort last (scores are probabilities)
+    idx[g] = n;
+    if (ok) atomicAdd(n_valid + b, 1);
+}
+
+__global__ void fill_offsets_kernel(int *seg, int n, int stride) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) seg[i] = i * stride;
+}
+
+__global__ void proposal_pre_kernel(const int *n_valid, int B, int pre_topN, int rcnn_bs, int *pre, int *status) {
+    int m = INT_MAX;
+    for (int b = 0; b < B; ++b) m = min(m, n_valid[b]);
+    m = min(m, pre_topN);
+    *pre = m;
+    *status = (m < rcnn_bs) ? -1 : 0;
+}
+
+__global__ void gather_sorted_kernel(const float4 *__restrict__ boxes, const float *__restrict__ keys_sorted,
+                                     const int *__restrict__ idx_sorted, const int *__restrict__ pre, int N, int cap,
+                                     float4 *__restrict__ out_boxes, float *__restrict__ out_scores) {
+    const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= min(*pre, cap)) return;
+    out_boxes[(long long)b * cap + i] = boxes[(long long)b * N + idx_sorted[(long long)b * N + i]];
+    out_scores[(long long)b * cap + i] = keys_sorted[(long long)b * N + i];
+}
+
+__global__ void proposal_out_kernel(const float4 *__restrict__ boxes, const float *__restrict__ scores,
+                                    const int *__restrict__ keep_idx, const int *__restrict__ keep_cnt, int B, int cap,
+                                    int post_topN, const int *__restrict__ status, float4 *__restrict__ rois,
+                                    float *__restrict__ out_scores, int *__restrict__ M_out) {
+    int m = INT_MAX;
+    for (int b = 0; b < B; ++b) m = min(m, keep_cnt[b]);
+    m = min(m, post_topN);                         // nets_utils.py:236
+    if (*status < 0) m = -1;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *M_out = m;
+    const int b = blockIdx.x;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const int k = keep_idx[(long long)b * cap + i];
+        rois[(long long)b * post_topN + i] = boxes[(long long)b * cap + k];
+        out_scores[(long long)b * post_topN + i] = scores[(long long)b * cap + k];
+    }
+}
+
+// ------------------------------------------------------------------------- final tail --------
+// One block per image, thread per RoI (R <= 256).  layers.py:688-766.
+constexpr int TAIL_MAX_R = 256;
+__global__ void __launch_bounds__(TAIL_MAX_R)
+final_detections_kernel(const float *__restrict__ bbox_reg, const float *__restrict__ probs,
+                        const float4 *__restrict__ rois, int R, int C, float img_w, float img_h, float nms_thresh,
+                        float min_score, float4 *__restrict__ det_boxes, float *__restrict__ det_scores,
+                        int *__restrict__ det_class, int *__restrict__ det_count) {
+    __shared__ float s_score[TAIL_MAX_R];
+    __shared__ int s_cls[TAIL_MAX_R];
+    __shared__ float4 s_box[TAIL_MAX_R];
+    __shared__ float4 o_box[TAIL_MAX_R];      // score-descending, class 0 removed
+    __shared__ float o_score[TAIL_MAX_R];
+    __shared__ int o_cls[TAIL_MAX_R];
+    __shared__ unsigned char o_dead[TAIL_MAX_R];
+    __shared__ int s_pos[TAIL_MAX_R];
+    __shared__ int n_fg;
+    const int b = blockIdx.x, r = threadIdx.x;
+    const int C1 = C + 1;
+    if (r < R) {
+        const float *p = probs + ((long long)b * R + r) * C1;
+        float best = p[0];
+        int arg = 0;
+        for (int c = 1; c < C1; ++c) { const float v = p[c]; if (v > best) { best = v; arg = c; } }   // first max
+        const float *d = bbox_reg + ((long long)b * R + r) * 4 * C1 + 4 * arg;
+        const float4 box = clamp_box(decode_one(make_float4(d[0], d[1], d[2], d[3]), rois[(long long)b * R + r]),
+                                     img_w, img_h);
+        s_score[r] = best; s_cls[r] = arg; s_box[r] = box;
+    }
+    __syncthreads();
+    if (r < R) {
+        // rank in the stable descending order (ties: lower index first)
+        const float me = s_score[r];
+        int rank = 0;
+        for (int j = 0; j < R; ++j) { const float v = s_score[j]; rank += (v > me) || (v == me && j < r); }
+        s_pos[rank] = r;
+    }
+    __syncthreads();
+    if (r == 0) {
+        int n = 0;
+        for (int i = 0; i < R; ++i) {
+            const int src = s_pos[i];
+            if (s_cls[src] > 0) { o_box[n] = s_box[src]; o_score[n] = s_score[src]; o_cls[n] = s_cls[src]; o_dead[n] = 0; ++n; }
+        }
+        n_fg = n;
+    }
+    __syncthreads();
+    const int n = n_fg;
+    // greedy NMS over n <= R boxes: step i, all threads j > i test against box i if it is alive
+    for (int i = 0; i < n; ++i) {
+        if (!o_dead[i] && r > i && r < n && !o_dead[r]) {
+            if (iou_ge(o_box[r], o_box[i], box_area(o_box[r]), box_area(o_box[i]), nms_thresh)) o_dead[r] = 1;
+        }
+        __syncthreads();
+    }
+    if (r == 0) {
+        int m = 0;
+        for (int i = 0; i < n; ++i) {
+            if (!o_dead[i] && o_score[i] > min_score) {
+                det_boxes[(long long)b * R + m] = o_box[i];
+                det_scores[(long long)b * R + m] = o_score[i];
+                det_class[(long long)b * R + m] = o_cls[i];
+                ++m;
+            }
+        }
+        det_count[b] = m;
+    }
+}
+
+// ------------------------------------------------------------------------------ merge ---------
+// run_detection.py:180-230: border filter, x offset, end-of-file filter; key = class (dropped -> INT_MAX)
+__global__ void merge_filter_kernel(const float4 *__restrict__ boxes, const int *__restrict__ cls,
+                                    const int *__restrict__ tile, int n, int n_tiles, float w_pix, float hop_spectro,
+                                    float spec_len, float min_border, float4 *__restrict__ shifted,
+                                    int *__restrict__ keys, int *__restrict__ idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 b = boxes[i];
+    const int t = tile[i];
+    const float width = __fsub_rn(b.z, b.x);
+    const bool right = b.z >= w_pix - 5.f, left = b.x <= 4.f;
+    const bool edge = (t == 0) ? right : ((t == n_tiles - 1) ? left : (left || right));
+    bool drop = edge && (width < min_border);
+    const float off = __fmul_rn(hop_spectro, (float)t);
+    b.x = __fadd_rn(b.x, off);
+    b.z = __fadd_rn(b.z, off);
+    drop = drop || (b.z >= spec_len);
+    shifted[i] = b;
+    keys[i] = drop ? INT_MAX : cls[i];
+    idx[i] = i;
+}
+
+__global__ void merge_gather_kernel(const float4 *__restrict__ shifted, const int *__restrict__ keys_sorted,
+                                    const int *__restrict__ idx_sorted, int n, float4 *__restrict__ cand,
+                                    int *__restrict__ n_cand) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool ok = keys_sorted[i] != INT_MAX;
+    if (ok) cand[i] = shifted[idx_sorted[i]];
+    if (ok && (i == n - 1 || keys_sorted[i + 1] == INT_MAX)) *n_cand = i + 1;
+    if (i == 0 && !ok) *n_cand = 0;
+}
+
+__global__ void merge_out_kernel(const float4 *__restrict__ cand, const float *__restrict__ scores,
+                                 const int *__restrict__ keys_sorted, const int *__restrict__ idx_sorted,
+                                 const int *__restrict__ keep_idx, const int *__restrict__ keep_cnt,
+                                 float4 *__restrict__ out_boxes, float *__restrict__ out_scores,
+                                 int *__restrict__ out_class, int *__restrict__ out_count) {
+    const int m = *keep_cnt;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *out_count = m;
+    if (i >= m) return;
+    const int k = keep_idx[i];
+    out_boxes[i] = cand[k];
+    out_scores[i] = scores[idx_sorted[k]];
+    out_class[i] = keys_sorted[k];
+}
+
+}  // namespace nbm
+
+using namespace nbm;
+
+// --------------------------------------------------------------------------- C entry points --
+extern "C" int nbm_make_anchors(int32_t base_size, const double *ratios, int32_t n_ratios, const int64_t *scales,
+                                int32_t n_scales, int32_t width, int32_t height, int32_t stride, float *out) {
+    NBM_REQUIRE(ratios && scales && out && n_ratios > 0 && n_scales > 0 && width > 0 && height > 0, "bad argument");
+    const int A = n_ratios * n_scales;
+    std::vector<long long> base((size_t)A * 4);
+    const double side = sqrt((double)base_size * (double)base_size);
+    const long long centre = (long long)(base_size / 2);        // int(base_size / 2)
+    for (int s = 0; s < n_scales; ++s)
+        for (int r = 0; r < n_ratios; ++r) {
+            const double w = sqrt(ratios[r]) * side * (double)scales[s];
+            const double h = (1.0 / sqrt(ratios[r])) * side * (double)scales[s];
+            long long *a = &base[(size_t)(s * n_ratios + r) * 4];
+            // numpy .astype(int) truncates toward zero
+            a[0] = (long long)(-w / 2 + (double)centre);
+            a[1] = (long long)(-h / 2 + (double)centre);
+            a[2] = (long long)(w / 2 + (double)centre);
+            a[3] = (long long)(h / 2 + (double)centre);
+        }
+    for (int y = 0; y < height; ++y)
+        for (int x = 0; x < width; ++x)
+            for (int a = 0; a < A; ++a) {
+                float *o = out + (((size_t)y * width + x) * A + a) * 4;
+                o[0] = (float)(base[a * 4 + 0] + (long long)x * stride);
+                o[1] = (float)(base[a * 4 + 1] + (long long)y * stride);
+                o[2] = (float)(base[a * 4 + 2] + (long long)x * stride);
+                o[3] = (float)(base[a * 4 + 3] + (long long)y * stride);
+            }
+    return NBM_OK;
+}
+
+extern "C" int nbm_decode_boxes(const float *d_deltas, const float *d_anchors, int32_t B, int32_t N,
+                                int32_t anchors_per_image, float clip_w, float clip_h, float min_size,
+                                float *d_boxes, uint8_t *d_valid, void *stream) {
+    NBM_REQUIRE(d_deltas && d_anchors && d_boxes && B >= 0 && N >= 0, "bad argument");
+    const long long total = (long long)B * N;
+    if (total == 0) return NBM_OK;
+    decode_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4 *>(d_deltas), reinterpret_cast<const float4 *>(d_anchors), B, N,
+        anchors_per_image, clip_w, clip_h, min_size, reinterpret_cast<float4 *>(d_boxes), d_valid);
+    NBM_CUDA(cudaGetLastError());
+    return NBM_OK;
+}
+
+extern "C" size_t nbm_nms_workspace_bytes(int32_t B, int32_t N) {
+    return (size_t)std::max(B, 0) * std::max(N, 0) * nms_words(std::max(N, 1)) * sizeof(unsigned long long);
+}
+
+extern "C" int nbm_nms_greedy(const float *d_boxes, const int32_t *d_n, int32_t B, int32_t N, float thresh,
+                              int32_t *d_keep_idx, int32_t *d_keep_cnt, void *ws, size_t ws_bytes, void *stream) {
+    NBM_REQUIRE(d_keep_cnt && B >= 0 && N >= 0, "bad argument");
+    if (B == 0) return NBM_OK;
+    if (N == 0) { NBM_CUDA(cudaMemsetAsync(d_keep_cnt, 0, sizeof(int) * B, (cudaStream_t)stream)); return NBM_OK; }
+    NBM_REQUIRE(d_boxes && d_keep_idx && ws, "null argument");
+    return launch_nms(d_boxes, d_n, nullptr, B, N, thresh, d_keep_idx, d_keep_cnt, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+namespace {
+struct ProposalWs {
+    size_t boxes, keys, keys_sorted, idx, idx_sorted, seg, n_valid, pre, status, M, top_boxes, top_scores,
+        keep_idx, keep_cnt, nms, cub, total, cub_bytes;
+};
+ProposalWs proposal_ws(const nbm_proposal_params &p, int B) {
+    ProposalWs w{};
+    const size_t N = (size_t)p.A * p.H * p.W, cap = (size_t)p.pre_nms_topN;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 256); return at; };
+    w.boxes = take(B * N * 16); w.keys = take(B * N * 4); w.keys_sorted = take(B * N * 4);
+    w.idx = take(B * N * 4); w.idx_sorted = take(B * N * 4); w.seg = take((B + 1) * 4);
+    w.n_valid = take(B * 4); w.pre = take(4); w.status = take(4); w.M = take(4);
+    w.top_boxes = take(B * cap * 16); w.top_scores = take(B * cap * 4);
+    w.keep_idx = take(B * cap * 4); w.keep_cnt = take(B * 4);
+    w.nms = take(nbm_nms_workspace_bytes(B, (int)cap));
+    size_t cub_bytes = 0;
+    cub::DeviceSegmentedRadixSort::SortPairsDescending(nullptr, cub_bytes, (const float *)nullptr, (float *)nullptr,
+                                                       (const int *)nullptr, (int *)nullptr, (int)(B * N), B,
+                                                       (const int *)nullptr, (const int *)nullptr);
+    w.cub_bytes = cub_bytes;
+    w.cub = take(cub_bytes);
+    w.total = o;
+    return w;
+}
+}  // namespace
+
+extern "C" size_t nbm_proposals_workspace_bytes(const nbm_proposal_params *p, int32_t B) {
+    if (!p || B <= 0) return 0;
+    return proposal_ws(*p, B).total;
+}
+
+extern "C" int nbm_proposals(const nbm_proposal_params *p, const float *d_cls, const float *d_reg,
+                             const float *d_anchors, int32_t B, float *d_rois, float *d_scores, int32_t *h_M,
+                             void *ws_, size_t ws_bytes, void *stream_) {
+    NBM_REQUIRE(p && d_cls && d_reg && d_anchors && d_rois && d_scores && h_M && ws_ && B >= 1, "bad argument");
+    NBM_REQUIRE(p->pre_nms_topN >= 1 && p->post_nms_topN >= 1, "topN must be positive");
+    cudaStream_t s = (cudaStream_t)stream_;
+    const ProposalWs w = proposal_ws(*p, B);
+    if (ws_bytes < w.total) { set_error("proposal workspace too small: %zu < %zu", ws_bytes, w.total); return NBM_ERR_WORKSPACE; }
+    char *ws = reinterpret_cast<char *>(ws_);
+    const int N = p->A * p->H * p->W, cap = p->pre_nms_topN;
+    auto *boxes = reinterpret_cast<float4 *>(ws + w.boxes);
+    auto *keys = reinterpret_cast<float *>(ws + w.keys);
+    auto *keys_sorted = reinterpret_cast<float *>(ws + w.keys_sorted);
+    auto *idx = reinterpret_cast<int *>(ws + w.idx);
+    auto *idx_sorted = reinterpret_cast<int *>(ws + w.idx_sorted);
+    auto *seg = reinterpret_cast<int *>(ws + w.seg);
+    auto *n_valid = reinterpret_cast<int *>(ws + w.n_valid);
+    auto *pre = reinterpret_cast<int *>(ws + w.pre);
+    auto *status = reinterpret_cast<int *>(ws + w.status);
+    auto *M = reinterpret_cast<int *>(ws + w.M);
+    auto *top_boxes = reinterpret_cast<float4 *>(ws + w.top_boxes);
+    auto *top_scores = reinterpret_cast<float *>(ws + w.top_scores);
+    auto *keep_idx = reinterpret_cast<int *>(ws + w.keep_idx);
+    auto *keep_cnt = reinterpret_cast<int *>(ws + w.keep_cnt);
+
+    fill_offsets_kernel<<<(B + 1 + 127) / 128, 128, 0, s>>>(seg, B + 1, N);
+    NBM_CUDA(cudaMemsetAsync(n_valid, 0, sizeof(int) * B, s));
+    const long long total = (long long)B * N;
+    rpn_decode_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+        d_cls, d_reg, reinterpret_cast<const float4 *>(d_anchors), B, p->A, p->H, p->W, p->img_width, p->img_height,
+        p->min_size, boxes, keys, idx, n_valid);
+    proposal_pre_kernel<<<1, 1, 0, s>>>(n_valid, B, p->pre_nms_topN, p->rcnn_batch_size, pre, status);
+    size_t cub_bytes = w.cub_bytes;
+    NBM_CUDA(cub::DeviceSegmentedRadixSort::SortPairsDescending(ws + w.cub, cub_bytes, keys, keys_sorted, idx,
+                                                                idx_sorted, (int)total, B, seg, seg + 1, 0, 32, s));
+    dim3 gg((cap + 127) / 128, B);
+    gather_sorted_kernel<<<gg, 128, 0, s>>>(boxes, keys_sorted, idx_sorted, pre, N, cap, top_boxes, top_scores);
+    int rc = launch_nms(reinterpret_cast<const float *>(top_boxes), nullptr, pre, B, cap, p->nms_thresh, keep_idx,
+                        keep_cnt, ws + w.nms, nbm_nms_workspace_bytes(B, cap), s);
+    if (rc != NBM_OK) return rc;
+    proposal_out_kernel<<<B, 128, 0, s>>>(top_boxes, top_scores, keep_idx, keep_cnt, B, cap, p->post_nms_topN, status,
+                                          reinterpret_cast<float4 *>(d_rois), d_scores, M);
+    NBM_CUDA(cudaMemcpyAsync(h_M, M, sizeof(int), cudaMemcpyDeviceToHost, s));
+    NBM_CUDA(cudaStreamSynchronize(s));
+    NBM_CUDA(cudaGetLastError());
+    return NBM_OK;
+}
+
+extern "C" int nbm_final_detections(const float *d_bbox_reg, const float *d_probs, const float *d_rois, int32_t B,
+                                    int32_t R, int32_t num_classes, float img_width, float img_height,
+                                    float nms_thresh, float min_score, float *d_det_boxes, float *d_det_scores,
+                                    int32_t *d_det_class, int32_t *d_det_count, void *stream) {
+    NBM_REQUIRE(d_bbox_reg && d_probs && d_rois && d_det_boxes && d_det_scores && d_det_class && d_det_count,
+                "null argument");
+    NBM_REQUIRE(B >= 1 && R >= 1 && num_classes >= 1, "bad sizes");
+    if (R > TAIL_MAX_R) { set_error("R=%d exceeds the fused tail limit %d", R, TAIL_MAX_R); return NBM_ERR_UNSUPPORTED; }
+    final_detections_kernel<<<B, TAIL_MAX_R, 0, (cudaStream_t)stream>>>(
+        d_bbox_reg, d_probs, reinterpret_cast<const float4 *>(d_rois), R, num_classes, img_width, img_height,
+        nms_thresh, min_score, reinterpret_cast<float4 *>(d_det_boxes), d_det_scores, d_det_class, d_det_count);
+    NBM_CUDA(cudaGetLastError());
+    return NBM_OK;
+}
+
+namespace {
+struct MergeWs { size_t shifted, keys, keys_sorted, idx, idx_sorted, cand, n_cand, keep_idx, keep_cnt, nms, cub, total, cub_bytes; };
+MergeWs merge_ws(int n) {
+    MergeWs w{};
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 256); return at; };
+    const size_t N = (size_t)std::max(n, 1);
+    w.shifted = take(N * 16); w.keys = take(N * 4); w.keys_sorted = take(N * 4); w.idx = take(N * 4);
+    w.idx_sorted = take(N * 4); w.cand = take(N * 16); w.n_cand = take(4); w.keep_idx = take(N * 4);
+    w.keep_cnt = take(4); w.nms = take(nbm_nms_workspace_bytes(1, (int)N));
+    size_t cb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cb, (const int *)nullptr, (int *)nullptr, (const int *)nullptr,
+                                    (int *)nullptr, (int)N);
+    w.cub_bytes = cb;
+    w.cub = take(cb);
+    w.total = o;
+    return w;
+}
+}  // namespace
+
+extern "C" size_t nbm_merge_workspace_bytes(int32_t n) { return merge_ws(n).total; }
+
+extern "C" int nbm_merge_detections(const float *d_boxes, const float *d_scores, const int32_t *d_class,
+                                    const int32_t *d_tile, int32_t n, int32_t n_tiles, int32_t w_pix,
+                                    int32_t hop_spectro, int64_t spectrogram_length, float nms_thresh,
+                                    float *d_out_boxes, float *d_out_scores, int32_t *d_out_class,
+                                    int32_t *d_out_count, void *ws_, size_t ws_bytes, void *stream_) {
+    NBM_REQUIRE(d_out_count && n >= 0 && n_tiles >= 1, "bad argument");
+    cudaStream_t s = (cudaStream_t)stream_;
+    if (n == 0) { NBM_CUDA(cudaMemsetAsync(d_out_count, 0, sizeof(int), s)); return NBM_OK; }
+    NBM_REQUIRE(d_boxes && d_scores && d_class && d_tile && d_out_boxes && d_out_scores && d_out_class && ws_,
+                "null argument");
+    const MergeWs w = merge_ws(n);
+    if (ws_bytes < w.total) { set_error("merge workspace too small: %zu < %zu", ws_bytes, w.total); return NBM_ERR_WORKSPACE; }
+    char *ws = reinterpret_cast<char *>(ws_);
+    auto *shifted = reinterpret_cast<float4 *>(ws + w.shifted);
+    auto *keys = reinterpret_cast<int *>(ws + w.keys);
+    auto *keys_sorted = reinterpret_cast<int *>(ws + w.keys_sorted);
+    auto *idx = reinterpret_cast<int *>(ws + w.idx);
+    auto *idx_sorted = reinterpret_cast<int *>(ws + w.idx_sorted);
+    auto *cand = reinterpret_cast<float4 *>(ws + w.cand);
+    auto *n_cand = reinterpret_cast<int *>(ws + w.n_cand);
+    auto *keep_idx = reinterpret_cast<int *>(ws + w.keep_idx);
+    auto *keep_cnt = reinterpret_cast<int *>(ws + w.keep_cnt);
+    const float min_border = (float)(0.9 * (double)(w_pix - hop_spectro));      // run_detection.py:165
+    const int blocks = (n + 255) / 256;
+    merge_filter_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const float4 *>(d_boxes), d_class, d_tile, n, n_tiles,
+                                               (float)w_pix, (float)hop_spectro, (float)spectrogram_length, min_border,
+                                               shifted, keys, idx);
+    size_t cb = w.cub_bytes;
+    NBM_CUDA(cub::DeviceRadixSort::SortPairs(ws + w.cub, cb, keys, keys_sorted, idx, idx_sorted, n, 0, 32, s));
+    merge_gather_kernel<<<blocks, 256, 0, s>>>(shifted, keys_sorted, idx_sorted, n, cand, n_cand);
+    int rc = launch_nms(reinterpret_cast<const float *>(cand), n_cand, nullptr, 1, n, nms_thresh, keep_idx, keep_cnt,
+                        ws + w.nms, nbm_nms_workspace_bytes(1, n), s);
+    if (rc != NBM_OK) return rc;
+    merge_out_kernel<<<blocks, 256, 0, s>>>(cand, d_scores, keys_sorted, idx_sorted, keep_idx, keep_cnt,
+                                            reinterpret_cast<float4 *>(d_out_boxes), d_out_scores, d_out_class,
+                                            d_out_count);
+    NBM_CUDA(cudaGetLastError());
+    return NBM_OK;
+}

@@ -1,0 +1,223 @@
+"""GPU front-end behind the reference's ``File_Processor`` interface.
+
+Mirrors ``nbm_model/nbm_datasets/prepare_dataset.py`` ``File_Processor`` (:92-294) for the
+inference path: same constructor, same ``process_file`` keyword defaults, same attributes
+set on the object (``W_PIX, HOP_SPECTRO, WIN_LENGTH, HOP_LENGTH, FREQ_ACCURACY, DT, LOW_IDX,
+HIGH_IDX, LOW_FREQ, HIGH_FREQ, spectrogram_length``) and the same ``(None, None)`` failure
+convention.  The arithmetic runs in libnbm_b200.so on the current CUDA device; the returned
+``img_db`` is a float32 CUDA tensor ``[n_tiles, H_PIX, W_PIX]`` (``len()``-able and
+indexable like the reference's list of arrays), already laid out as the detector batch
+``run_detection.py:53-55`` builds, so no host round trip happens.
+
+PyTorch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from .synth import read_wav_pcm16
+
+STFT_CHUNK = int(5e7)                                   # prepare_dataset.py:234
+LONG_FILE_SAMPLES = int(15e7) - int(15e7) % 44100       # prepare_dataset.py:194
+
+
+def derive_constants(freq_accuracy=33.3, dt=0.003, overlap_spectro=0.2, w_pix=1024,
+                     sample_rate=44100, h_pix=375, low_freq=500) -> dict:
+    """The scalar derivations of process_file (prepare_dataset.py:114-138), same float/int
+    arithmetic, as a dict keyed by the reference's attribute names."""
+    W_PIX = w_pix
+    HOP_SPECTRO = int((1 - overlap_spectro) * W_PIX)
+    WIN_LENGTH = int(sample_rate / freq_accuracy)
+    HOP_LENGTH = int(sample_rate * dt)
+    overlap_fft = float(np.round(1 - HOP_LENGTH / WIN_LENGTH, 3))
+    FREQ_ACCURACY = sample_rate / WIN_LENGTH
+    DT = int((1 - overlap_fft) * WIN_LENGTH) / sample_rate
+    LOW_IDX = 1 + int(low_freq / FREQ_ACCURACY)
+    HIGH_IDX = LOW_IDX + h_pix
+    return dict(W_PIX=W_PIX, HOP_SPECTRO=HOP_SPECTRO, WIN_LENGTH=WIN_LENGTH, HOP_LENGTH=HOP_LENGTH,
+                FREQ_ACCURACY=FREQ_ACCURACY, DT=DT, LOW_IDX=LOW_IDX, HIGH_IDX=HIGH_IDX,
+                LOW_FREQ=(LOW_IDX - 1) * FREQ_ACCURACY, HIGH_FREQ=(HIGH_IDX - 1) * FREQ_ACCURACY)
+
+
+def _stream_ptr(stream) -> int:
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return int(s.cuda_stream)
+
+
+class FrontendPlan:
+    """Owns an ``nbm_frontend_plan`` (device twiddle tables) plus a reusable torch workspace."""
+
+    def __init__(self, freq_accuracy=33.3, dt=0.003, overlap_spectro=0.2, w_pix=1024,
+                 sample_rate=44100, h_pix=375, low_freq=500, device=None, stft_chunk=STFT_CHUNK):
+        if not torch.cuda.is_available():
+            raise _lib.NbmError("the NBM front-end needs a CUDA device (no CPU fallback)")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.const = derive_constants(freq_accuracy, dt, overlap_spectro, w_pix, sample_rate, h_pix, low_freq)
+        c = self.const
+        self.n_bins, self.w_pix = h_pix, w_pix
+        self.params = _lib.FrontendParams(
+            sample_rate=sample_rate, n_fft=c["WIN_LENGTH"], hop=c["HOP_LENGTH"], low_idx=c["LOW_IDX"],
+            n_bins=h_pix, w_pix=w_pix, hop_spectro=c["HOP_SPECTRO"], pad_mode=0, stft_chunk=int(stft_chunk),
+            min_level=float(np.exp(-100 / 20 * np.log(10))))                # prepare_dataset.py:229
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().nbm_frontend_plan_create(C.byref(self.params), C.byref(self._h)),
+                       "nbm_frontend_plan_create")
+        self._ws = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().nbm_frontend_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- host arithmetic -------------------------------------------------------------------
+    def query(self, n_samples: int):
+        nf, nt, ws = C.c_int64(), C.c_int64(), C.c_size_t()
+        _lib.check(_lib.lib().nbm_frontend_query(self._h, int(n_samples), C.byref(nf), C.byref(nt), C.byref(ws)),
+                   "nbm_frontend_query")
+        return nf.value, nt.value, ws.value
+
+    def query_batch(self, n_samples):
+        n = len(n_samples)
+        ns = (C.c_int64 * n)(*[int(v) for v in n_samples])
+        nf = (C.c_int64 * n)()
+        to = (C.c_int64 * (n + 1))()
+        ws = C.c_size_t()
+        _lib.check(_lib.lib().nbm_frontend_query_batch(self._h, ns, n, nf, to, C.byref(ws)), "nbm_frontend_query_batch")
+        return list(nf), list(to), ws.value
+
+    def _workspace(self, nbytes: int) -> torch.Tensor:
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(int(nbytes * 1.05) + 256, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    # -- device work --------------------------------------------------------------------------
+    @staticmethod
+    def _pcm_dtype(pcm: torch.Tensor) -> int:
+        if pcm.dtype == torch.int16:
+            return 0
+        if pcm.dtype == torch.float32:
+            return 1
+        raise TypeError("pcm must be int16 or float32")
+
+    def run(self, pcm: torch.Tensor, stream=None, out: torch.Tensor | None = None):
+        """pcm: CUDA tensor [n] or [n, channels] -> (tiles [n_tiles,1,n_bins,w_pix], minmax [2])."""
+        assert pcm.is_cuda and pcm.is_contiguous()
+        n = pcm.shape[0]
+        ch = 1 if pcm.dim() == 1 else pcm.shape[1]
+        tiles, _, minmax = self.run_batch(pcm, [0, n], channels=ch, stream=stream, out=out)
+        return tiles, minmax[0]
+
+    def run_batch(self, pcm: torch.Tensor, sample_offsets, channels=1, stream=None, out=None):
+        """pcm: flat CUDA tensor holding every file back to back; sample_offsets: n_files+1
+        per-channel sample indices.  Returns (tiles [total_tiles,1,n_bins,w_pix],
+        tile_offsets list[n_files+1], minmax [n_files, 2])."""
+        assert pcm.is_cuda and pcm.is_contiguous()
+        n_files = len(sample_offsets) - 1
+        sizes = [int(sample_offsets[i + 1] - sample_offsets[i]) for i in range(n_files)]
+        _, tile_off, ws_bytes = self.query_batch(sizes)
+        total = tile_off[-1]
+        if out is None:
+            out = torch.empty((total, 1, self.n_bins, self.w_pix), dtype=torch.float32, device=self.device)
+        else:
+            assert out.is_cuda and out.is_contiguous() and out.dtype == torch.float32 and \
+                out.numel() >= total * self.n_bins * self.w_pix
+        minmax = torch.empty((n_files, 2), dtype=torch.float32, device=self.device)
+        ws = self._workspace(ws_bytes)
+        offs = (C.c_int64 * (n_files + 1))(*[int(v) for v in sample_offsets])
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().nbm_frontend_run_batch(
+                self._h, pcm.data_ptr(), self._pcm_dtype(pcm), int(channels), offs, n_files, out.data_ptr(),
+                minmax.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(stream)), "nbm_frontend_run_batch")
+        self._last_sizes = sizes
+        return out, tile_off, minmax
+
+    def spectrogram_view(self, file_index: int = 0) -> torch.Tensor:
+        """Un-normalised dB band [n_bins, n_frames] of a file from the LAST run (a view into the
+        workspace; for tests and diagnostics)."""
+        sizes = self._last_sizes
+        n = len(sizes)
+        ns = (C.c_int64 * n)(*sizes)
+        off, stride = C.c_size_t(), C.c_int64()
+        _lib.check(_lib.lib().nbm_frontend_spectrogram_view(self._h, ns, n, file_index, C.byref(off), C.byref(stride)),
+                   "nbm_frontend_spectrogram_view")
+        nf = self.query(sizes[file_index])[0]
+        flat = self._ws[off.value: off.value + self.n_bins * stride.value * 4].view(torch.float32)
+        return flat.view(self.n_bins, stride.value)[:, :nf]
+
+
+_PLANS: dict = {}
+
+
+def get_plan(freq_accuracy=33.3, dt=0.003, overlap_spectro=0.2, w_pix=1024, sample_rate=44100,
+             h_pix=375, low_freq=500) -> FrontendPlan:
+    key = (freq_accuracy, dt, overlap_spectro, w_pix, sample_rate, h_pix, low_freq, torch.cuda.current_device())
+    if key not in _PLANS:
+        _PLANS[key] = FrontendPlan(freq_accuracy, dt, overlap_spectro, w_pix, sample_rate, h_pix, low_freq)
+    return _PLANS[key]
+
+
+class File_Processor:
+    """Drop-in for the reference class on the inference path (labels are not supported: the
+    label joins of prepare_dataset.py:297-376 are dataset preparation, out of scope)."""
+
+    H_PIX = 375      # px          prepare_dataset.py:96
+    LOW_FREQ = 500   # hz          prepare_dataset.py:97
+    FREQ = 44100     # hz          prepare_dataset.py:98
+
+    def __init__(self, filepath, extra_str_label="", labels=None):
+        if labels is not None:
+            raise NotImplementedError("label processing (training-set preparation) is out of scope")
+        self.labels = labels
+        self.ext = os.path.basename(filepath).split(".")[-1]
+        self.filename = os.path.basename(filepath).replace("." + self.ext, "").replace(extra_str_label, "")
+        self.filepath = filepath
+
+    def load(self):
+        """PCM16 wav -> pinned int16 host tensor (the /32768 scaling and mono mix happen on the
+        device).  Returns None on failure like the reference (prepare_dataset.py:160-165)."""
+        try:
+            pcm, sr = read_wav_pcm16(self.filepath)
+        except Exception:
+            print("File loading failed")
+            return None
+        if sr != self.FREQ:
+            # the reference shells out to ffmpeg here (prepare_dataset.py:166-182)
+            raise ValueError(f"{self.filepath}: sample rate {sr} != {self.FREQ}; resample first (no ffmpeg path)")
+        t = torch.from_numpy(np.ascontiguousarray(pcm))
+        return t.pin_memory() if torch.cuda.is_available() else t
+
+    def process_file(self, freq_accuracy=33.3, dt=0.003, overlap_spectro=0.2, w_pix=1024):
+        data = self.load()
+        if data is None:
+            return None, None
+        return self.process_pcm(data, freq_accuracy, dt, overlap_spectro, w_pix)
+
+    def process_pcm(self, data: torch.Tensor, freq_accuracy=33.3, dt=0.003, overlap_spectro=0.2, w_pix=1024):
+        """Same as process_file for PCM already in memory (host pinned or CUDA, int16/float32)."""
+        n = data.shape[0]
+        if n > LONG_FILE_SAMPLES:
+            # prepare_dataset.py:187-225 splits such files and returns a list-of-lists that
+            # run_detection.py:47-53 cannot consume; pre-chunk recordings into <= 3401 s files.
+            raise ValueError(f"{self.filepath}: {n} samples > {LONG_FILE_SAMPLES}; split the recording first")
+        plan = get_plan(freq_accuracy, dt, overlap_spectro, w_pix, self.FREQ, self.H_PIX, type(self).LOW_FREQ)
+        for k, v in plan.const.items():
+            setattr(self, k, v)
+        dev = data if data.is_cuda else data.to(plan.device, non_blocking=True)
+        tiles, minmax = plan.run(dev)
+        self.spectrogram_length, _, _ = plan.query(n)
+        self.s_min_max = minmax
+        return tiles[:, 0], None

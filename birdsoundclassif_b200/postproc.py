@@ -1,0 +1,282 @@
+"""Detector post-processing on the GPU behind the reference's Python symbols.
+
+Same names, argument meaning and return conventions as the reference functions they
+replace, so they can be patched into ``nbm_model.nets.layers`` / ``nbm_model.run_detection``
+(see INTEGRATION.md):
+
+  bbox_reg_to_coord   nets_utils.py:169-186
+  nms                 nets_utils.py:210-245   (in-order greedy, batch-min truncation, return_idx)
+  ProposalLayer       layers.py:219-303       (parameter-free nn.Module)
+  fastrcnn_inference_tail   layers.py:688-778 (the inference branch of FastRCNN.forward)
+  merge_images        run_detection.py:163-249
+
+All arithmetic is done by libnbm_b200.so on the tensors' CUDA device; torch only owns the
+memory.  There is no CPU fallback: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+
+
+def _stream() -> int:
+    return int(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if not t.is_cuda:
+            raise _lib.NbmError("libnbm_b200 post-processing needs CUDA tensors (no CPU fallback)")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.float32).contiguous()
+
+
+# ------------------------------------------------------------------------------- anchors ------
+_ANCHORS: dict = {}
+
+
+def make_anchors(base_size, ratios, scales, width, height, stride, device) -> torch.Tensor:
+    """[height*width*A, 4] float32 anchors (nets_utils.py:35-59 as combined at layers.py:252-258);
+    built once per configuration instead of every forward (layers.py:252-271)."""
+    key = (base_size, tuple(float(r) for r in ratios), tuple(int(s) for s in scales), width, height, stride,
+           str(device))
+    if key not in _ANCHORS:
+        r = (C.c_double * len(ratios))(*[float(x) for x in ratios])
+        s = (C.c_int64 * len(scales))(*[int(x) for x in scales])
+        out = np.empty((height * width * len(ratios) * len(scales), 4), dtype=np.float32)
+        _lib.check(_lib.lib().nbm_make_anchors(int(base_size), r, len(ratios), s, len(scales), int(width),
+                                               int(height), int(stride), out.ctypes.data), "nbm_make_anchors")
+        _ANCHORS[key] = torch.from_numpy(out).to(device)
+    return _ANCHORS[key]
+
+
+# -------------------------------------------------------------------------------- decode ------
+def decode_boxes(deltas: torch.Tensor, anchors: torch.Tensor, clip_w=0.0, clip_h=0.0, min_size=0.0,
+                 want_valid=False):
+    """deltas [B,N,4]; anchors [N,4] (shared) or [B,N,4] (per image)."""
+    _need_cuda(deltas, anchors)
+    deltas, anchors = _f32c(deltas), _f32c(anchors)
+    B, N = deltas.shape[0], deltas.shape[1]
+    boxes = torch.empty_like(deltas)
+    valid = torch.empty((B, N), dtype=torch.uint8, device=deltas.device) if want_valid else None
+    with torch.cuda.device(deltas.device):
+        _lib.check(_lib.lib().nbm_decode_boxes(deltas.data_ptr(), anchors.data_ptr(), B, N, int(anchors.dim() == 3),
+                                               float(clip_w), float(clip_h), float(min_size), boxes.data_ptr(),
+                                               valid.data_ptr() if want_valid else None, _stream()),
+                   "nbm_decode_boxes")
+    return (boxes, valid) if want_valid else boxes
+
+
+def bbox_reg_to_coord(bbox_pred: torch.Tensor, anchors: torch.Tensor) -> torch.Tensor:
+    """Drop-in for nets_utils.bbox_reg_to_coord: bbox_pred [..., N, 4], anchors [N, 4] -> [B, N, 4]."""
+    return decode_boxes(bbox_pred.reshape(-1, bbox_pred.shape[-2], 4), anchors)
+
+
+# ----------------------------------------------------------------------------------- NMS ------
+def nms_keep(boxes: torch.Tensor, thresh: float, n_valid: torch.Tensor | None = None):
+    """boxes [B,N,4] in priority order -> (keep_idx int32 [B,N] (first keep_cnt[b] valid), keep_cnt int32 [B])."""
+    _need_cuda(boxes)
+    boxes = _f32c(boxes)
+    B, N = boxes.shape[0], boxes.shape[1]
+    keep_idx = torch.empty((B, max(N, 1)), dtype=torch.int32, device=boxes.device)
+    keep_cnt = torch.empty((B,), dtype=torch.int32, device=boxes.device)
+    ws_bytes = _lib.lib().nbm_nms_workspace_bytes(B, N)
+    ws = torch.empty((max(ws_bytes, 8),), dtype=torch.uint8, device=boxes.device)
+    with torch.cuda.device(boxes.device):
+        _lib.check(_lib.lib().nbm_nms_greedy(boxes.data_ptr(), n_valid.data_ptr() if n_valid is not None else None,
+                                             B, N, float(thresh), keep_idx.data_ptr(), keep_cnt.data_ptr(),
+                                             ws.data_ptr(), ws.numel(), _stream()), "nbm_nms_greedy")
+    return keep_idx, keep_cnt
+
+
+def nms(bbox_pred: torch.Tensor, scores: torch.Tensor, nms_thresh=0.7, post_nms_topN=300, return_idx=False):
+    """Drop-in for nets_utils.nms.  Greedy IN INPUT ORDER (no sort), IoU >= thresh suppresses,
+    every row truncated to min(min_b len(keep_b), post_nms_topN); with return_idx the untruncated
+    keep lists come back as list[list[int]] (callers fancy-index with them, layers.py:746)."""
+    keep_idx, keep_cnt = nms_keep(bbox_pred, nms_thresh)
+    cnt = keep_cnt.tolist()
+    m = min(min(cnt), int(post_nms_topN))
+    sel = keep_idx[:, :m].long()
+    out_scores = torch.gather(scores, 1, sel)
+    out_boxes = torch.gather(bbox_pred, 1, sel[..., None].expand(-1, -1, 4))
+    if return_idx:
+        rows = keep_idx.cpu().tolist()
+        return out_boxes, out_scores, [rows[b][:cnt[b]] for b in range(len(cnt))]
+    return out_boxes, out_scores
+
+
+# ------------------------------------------------------------------------------ proposals -----
+class ProposalLayer(nn.Module):
+    """Drop-in for layers.ProposalLayer (eval branch): decode 15*24*64 anchors per image, clamp,
+    min-size filter, stable score sort, batch-coupled top-N, NMS, batch-coupled truncation -- one
+    library call, no per-image Python.  Holds no parameters (state_dict keys unaffected)."""
+
+    def __init__(self, config, n_layers):
+        super().__init__()
+        self.n_layers = n_layers
+        self.config = config
+        self._ws = None
+
+    def forward(self, labels_pred: torch.Tensor, bbox_reg: torch.Tensor):
+        cfg = self.config
+        if self.training:
+            raise NotImplementedError("training-time proposals are out of scope (inference hot path only)")
+        _need_cuda(labels_pred, bbox_reg)
+        B = labels_pred.shape[0]
+        H, W = labels_pred.shape[-2:]
+        scales = 2 ** np.arange(self.n_layers)
+        A = len(cfg.ratios) * len(scales)
+        dev = labels_pred.device
+        anchors = make_anchors(cfg.base_size, cfg.ratios, scales, W, H, cfg.anchor_stride, dev)
+        p = _lib.ProposalParams(A=A, H=H, W=W, img_width=float(cfg.img_width), img_height=float(cfg.img_height),
+                                min_size=float(cfg.min_threshold), nms_thresh=float(cfg.nms_thresh),
+                                pre_nms_topN=int(cfg.pre_nms_topN_eval), post_nms_topN=int(cfg.post_nms_topN_eval),
+                                rcnn_batch_size=int(cfg.rcnn_batch_size))
+        ws_bytes = _lib.lib().nbm_proposals_workspace_bytes(C.byref(p), B)
+        if self._ws is None or self._ws.numel() < ws_bytes or self._ws.device != dev:
+            self._ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        rois = torch.empty((B, p.post_nms_topN, 4), dtype=torch.float32, device=dev)
+        scores = torch.empty((B, p.post_nms_topN), dtype=torch.float32, device=dev)
+        M = C.c_int32(0)
+        cls, reg = _f32c(labels_pred), _f32c(bbox_reg)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().nbm_proposals(C.byref(p), cls.data_ptr(), reg.data_ptr(), anchors.data_ptr(), B,
+                                                rois.data_ptr(), scores.data_ptr(), C.byref(M), self._ws.data_ptr(),
+                                                self._ws.numel(), _stream()), "nbm_proposals")
+        if M.value < 0:
+            print("Not enough possible RoIs, RPN failed")                  # layers.py:288-290
+            return torch.tensor([]).to(dev), torch.tensor([]).to(dev)
+        return rois[:, :M.value], scores[:, :M.value]
+
+
+# ----------------------------------------------------------------------------- final tail -----
+def final_detections_flat(bbox_reg, bbox_classes, rois, num_classes, img_width, img_height,
+                          nms_thresh=0.3, min_score=0.5):
+    """Fused inference tail -> flat records (boxes [B,R,4], scores [B,R], classes int32 [B,R],
+    counts int32 [B]); the first counts[b] rows of image b are its detections in surviving
+    (score-descending) order."""
+    _need_cuda(bbox_reg, bbox_classes, rois)
+    B, R = rois.shape[0], rois.shape[1]
+    dev = rois.device
+    bbox_reg, bbox_classes, rois = _f32c(bbox_reg), _f32c(bbox_classes), _f32c(rois)
+    boxes = torch.empty((B, R, 4), dtype=torch.float32, device=dev)
+    scores = torch.empty((B, R), dtype=torch.float32, device=dev)
+    classes = torch.empty((B, R), dtype=torch.int32, device=dev)
+    counts = torch.empty((B,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().nbm_final_detections(bbox_reg.data_ptr(), bbox_classes.data_ptr(), rois.data_ptr(), B, R,
+                                                   int(num_classes), float(img_width), float(img_height),
+                                                   float(nms_thresh), float(min_score), boxes.data_ptr(),
+                                                   scores.data_ptr(), classes.data_ptr(), counts.data_ptr(),
+                                                   _stream()), "nbm_final_detections")
+    return boxes, scores, classes, counts
+
+
+def records_to_dicts(boxes, scores, classes, counts, num_classes, proposal_number=None):
+    """Flat records -> the reference's list(B) of {str(c): {'bbox_coord': [n,4], 'scores': [1,n]}}
+    (layers.py:750-775); empty classes are CPU ``torch.Tensor()`` like the reference."""
+    cnt = counts.tolist()
+    cls_host = classes.cpu()
+    out = []
+    for b, n in enumerate(cnt):
+        d = {str(c): dict(bbox_coord=torch.Tensor(), scores=torch.Tensor()) for c in range(1, num_classes + 1)}
+        if n:
+            cb = cls_host[b, :n]
+            for c in torch.unique(cb).tolist():
+                w = torch.nonzero(cb == c)[:, 0]
+                if proposal_number is not None:
+                    w = w[:proposal_number]
+                w = w.to(boxes.device)
+                d[str(c)] = dict(bbox_coord=boxes[b, w], scores=scores[b, w][None])
+        out.append(d)
+    return out
+
+
+def fastrcnn_inference_tail(bbox_reg, bbox_classes, rois, config, nms_thresh=0.3, min_score=0.5):
+    """Drop-in for the inference branch of FastRCNN.forward given the head outputs."""
+    rec = final_detections_flat(bbox_reg, bbox_classes, rois, config.num_classes, config.img_width,
+                                config.img_height, nms_thresh, min_score)
+    return records_to_dicts(*rec, config.num_classes, config.proposal_number)
+
+
+# ---------------------------------------------------------------------------------- merge -----
+def merge_flat(boxes, scores, classes, tiles, n_tiles, w_pix, hop_spectro, spectrogram_length, nms_thresh=0.3):
+    """Flat per-file candidates in tile-major order -> survivors (boxes [m,4], scores [m], classes [m])
+    in the reference's NMS order (class-major candidates, run_detection.py:180-233)."""
+    n = boxes.shape[0]
+    dev = boxes.device
+    if n == 0:
+        return boxes.new_zeros((0, 4)), scores.new_zeros((0,)), classes.new_zeros((0,))
+    _need_cuda(boxes, scores, classes, tiles)
+    boxes, scores = _f32c(boxes), _f32c(scores)
+    classes, tiles = classes.to(torch.int32).contiguous(), tiles.to(torch.int32).contiguous()
+    ob = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    os_ = torch.empty((n,), dtype=torch.float32, device=dev)
+    oc = torch.empty((n,), dtype=torch.int32, device=dev)
+    cnt = torch.empty((1,), dtype=torch.int32, device=dev)
+    ws_bytes = _lib.lib().nbm_merge_workspace_bytes(n)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().nbm_merge_detections(boxes.data_ptr(), scores.data_ptr(), classes.data_ptr(),
+                                                   tiles.data_ptr(), n, int(n_tiles), int(w_pix), int(hop_spectro),
+                                                   int(spectrogram_length), float(nms_thresh), ob.data_ptr(),
+                                                   os_.data_ptr(), oc.data_ptr(), cnt.data_ptr(), ws.data_ptr(),
+                                                   ws.numel(), _stream()), "nbm_merge_detections")
+    m = int(cnt.item())
+    return ob[:m], os_[:m], oc[:m]
+
+
+def flatten_tile_dicts(out: list, num_classes: int, device):
+    """list of per-tile dicts (the model's output format) -> flat (boxes, scores, classes, tiles),
+    tile-major, per tile class-major (any within-tile order works: merge sorts by class stably and
+    the per-class order inside a tile is preserved)."""
+    bb, ss, cc, tt = [], [], [], []
+    for i, d in enumerate(out):
+        for c in range(1, num_classes + 1):
+            e = d[str(c)]
+            n = len(e["bbox_coord"])
+            if n == 0:
+                continue
+            bb.append(e["bbox_coord"].reshape(-1, 4).to(device))
+            ss.append(e["scores"].reshape(-1).to(device))
+            cc.append(torch.full((n,), c, dtype=torch.int32, device=device))
+            tt.append(torch.full((n,), i, dtype=torch.int32, device=device))
+    if not bb:
+        z = torch.zeros((0,), device=device)
+        return z.reshape(0, 4), z, z.to(torch.int32), z.to(torch.int32)
+    return torch.cat(bb), torch.cat(ss), torch.cat(cc), torch.cat(tt)
+
+
+def survivors_to_class_dict(boxes, scores, classes, num_classes):
+    """-> {str(j): {'bbox_coord': [m,4], 'scores': [m]}} with ``torch.tensor([])`` for empty classes
+    (run_detection.py:238-247)."""
+    out = {}
+    cls_host = classes.cpu()
+    present = set(torch.unique(cls_host).tolist()) if len(cls_host) else set()
+    for j in range(1, num_classes + 1):
+        if j in present:
+            w = torch.nonzero(cls_host == j)[:, 0].to(boxes.device)
+            out[str(j)] = dict(bbox_coord=boxes[w], scores=scores[w])
+        else:
+            out[str(j)] = dict(bbox_coord=torch.tensor([]), scores=torch.tensor([]))
+    return out
+
+
+def merge_images(fp, outputs, num_classes, nms_thresh=0.3):
+    """Drop-in for run_detection.merge_images: `outputs` is the list of per-batch lists of per-tile
+    dicts the model returned; `fp` carries W_PIX, HOP_SPECTRO, spectrogram_length."""
+    out = []
+    for b in outputs:
+        out.extend(b)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    boxes, scores, classes, tiles = flatten_tile_dicts(out, num_classes, dev)
+    kb, ks, kc = merge_flat(boxes, scores, classes, tiles, len(out), fp.W_PIX, fp.HOP_SPECTRO,
+                            int(fp.spectrogram_length), nms_thresh)
+    return survivors_to_class_dict(kb, ks, kc, num_classes)

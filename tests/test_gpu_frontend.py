@@ -1,0 +1,164 @@
+"""GPU front-end (libnbm_b200 through the File_Processor mirror) against the CPU oracle,
+the committed golden vectors, and size-independent properties.
+
+Tolerance (stated, see DESIGN.md "Front-end accuracy"): the reference computes the STFT in
+float64 and stores complex64; the kernel computes in float32.  On the normalised [0,1] tiles:
+    max |gpu - oracle| <= 1e-4      (= 1e-4 * (s_max - s_min) dB, about 0.01 dB)
+and s_min / s_max within 5e-3 / 1e-3 dB.
+"""
+import numpy as np
+import pytest
+import torch
+
+from birdsoundclassif_b200 import synth
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+TOL_TILE = 1e-4
+TOL_SMIN_DB = 5e-3
+TOL_SMAX_DB = 1e-3
+
+
+@pytest.fixture(scope="module")
+def fe():
+    from birdsoundclassif_b200 import frontend
+    return frontend
+
+
+def _gpu_tiles(fe, pcm, **kw):
+    fp = fe.File_Processor("synthetic.wav")
+    tiles, none = fp.process_pcm(torch.from_numpy(pcm).cuda(), **kw)
+    assert none is None
+    torch.cuda.synchronize()
+    return fp, tiles
+
+
+@pytest.mark.parametrize("case", H.FRONTEND_CASES, ids=[c[0] for c in H.FRONTEND_CASES])
+def test_against_golden_and_oracle(fe, case):
+    from oracle import frontend_oracle as fo
+    gold = H.load("frontend.npz")
+    name, _, _, kw = case
+    pcm = H.frontend_pcm(case, gold)
+    fp, tiles = _gpu_tiles(fe, pcm, **kw)
+    t = tiles.cpu().numpy()
+    assert t.shape[0] == int(gold[name + "/n_tiles"]) and t.shape[1:] == (375, 1024) and t.dtype == np.float32
+    assert fp.spectrogram_length == int(gold[name + "/spectrogram_length"])
+    assert [fp.W_PIX, fp.HOP_SPECTRO, fp.WIN_LENGTH, fp.HOP_LENGTH, fp.LOW_IDX, fp.HIGH_IDX] == gold[name + "/consts"].tolist()
+    np.testing.assert_array_equal(np.array([fp.FREQ_ACCURACY, fp.DT, fp.LOW_FREQ, fp.HIGH_FREQ]), gold[name + "/fconsts"])
+    # golden (recorded from the reference's File_Processor)
+    assert np.abs(t[:, ::H.ROW_STRIDE, ::H.COL_STRIDE] - gold[name + "/sample"]).max() <= TOL_TILE
+    assert np.abs(t[:, :, -1] - gold[name + "/last_col"]).max() <= TOL_TILE
+    np.testing.assert_allclose(t.sum(axis=(1, 2), dtype=np.float64), gold[name + "/tile_sum"], rtol=0, atol=TOL_TILE * 375 * 1024 * 0.05)
+    # full oracle
+    r = fo.process(pcm, fo.derive_params(**kw))
+    ref = np.stack(r.tiles)
+    err = np.abs(t.astype(np.float64) - ref)
+    assert err.max() <= TOL_TILE, f"max abs err {err.max():.3e}"
+    smin, smax = fp.s_min_max.cpu().tolist()
+    assert abs(smin - r.s_min) <= TOL_SMIN_DB and abs(smax - r.s_max) <= TOL_SMAX_DB
+    assert t.min() == 0.0 and t.max() == 1.0
+
+
+def test_db_spectrogram_before_normalisation(fe):
+    """The un-normalised dB band (workspace view) against the oracle: abs error in dB."""
+    from oracle import frontend_oracle as fo
+    pcm = synth.synth_pcm(4.0, 77)
+    plan = fe.get_plan()
+    plan.run(torch.from_numpy(pcm).cuda())
+    torch.cuda.synchronize()
+    db = plan.spectrogram_view(0).cpu().numpy().astype(np.float64)
+    ref = fo.db_spectrogram(fo.to_float(pcm), fo.derive_params())[0]
+    assert db.shape == ref.shape
+    assert np.abs(db - ref).max() <= 1e-2           # dB, dominated by the deepest nulls
+    assert np.quantile(np.abs(db - ref), 0.999) <= 2e-4
+
+
+def test_tiling_properties_long_clip(fe):
+    """60 s clip (BASELINE config 2 unit): overlap columns of consecutive tiles are identical,
+    reflect-padded columns are exact copies, range is exactly [0, 1]."""
+    from oracle import frontend_oracle as fo
+    pcm = synth.synth_pcm(60.0, 5)
+    fp, tiles = _gpu_tiles(fe, pcm)
+    assert tiles.shape == (25, 375, 1024) and fp.spectrogram_length == 20046
+    ov = fp.W_PIX - fp.HOP_SPECTRO
+    for k in range(tiles.shape[0] - 1):
+        w = min(ov, fp.spectrogram_length - (k + 1) * fp.HOP_SPECTRO)
+        assert torch.equal(tiles[k][:, fp.HOP_SPECTRO:fp.HOP_SPECTRO + w], tiles[k + 1][:, :w])
+    last_w = fp.spectrogram_length - 24 * fp.HOP_SPECTRO
+    assert last_w == 390
+    last = tiles[-1].cpu().numpy()
+    for j in range(last_w, 1024):
+        np.testing.assert_array_equal(last[:, j], last[:, fo.reflect_index(j, last_w)])
+    assert tiles.min().item() == 0.0 and tiles.max().item() == 1.0
+
+
+def test_oracle_parity_30s(fe):
+    from oracle import frontend_oracle as fo
+    pcm = synth.synth_pcm(30.0, 1001)
+    fp, tiles = _gpu_tiles(fe, pcm)
+    r = fo.process(pcm)
+    assert len(r.tiles) == tiles.shape[0] == 12
+    err = np.abs(tiles.cpu().numpy().astype(np.float64) - np.stack(r.tiles))
+    assert err.max() <= TOL_TILE, f"max abs err {err.max():.3e}"
+
+
+def test_batch_equals_single(fe):
+    plan = fe.get_plan()
+    pcms = [synth.synth_pcm(s, 40 + i) for i, s in enumerate([1.0, 7.3, 0.2, 3.0])]
+    singles = [plan.run(torch.from_numpy(p).cuda())[0].clone() for p in pcms]
+    flat = torch.from_numpy(np.concatenate(pcms)).cuda()
+    offs = np.concatenate([[0], np.cumsum([len(p) for p in pcms])]).tolist()
+    tiles, tile_off, minmax = plan.run_batch(flat, offs)
+    torch.cuda.synchronize()
+    for i, s in enumerate(singles):
+        assert torch.equal(tiles[tile_off[i]:tile_off[i + 1]], s)
+    assert minmax.shape == (4, 2)
+
+
+def test_float_and_stereo_inputs(fe):
+    plan = fe.get_plan()
+    pcm = synth.synth_pcm(2.5, 9)
+    a = plan.run(torch.from_numpy(pcm).cuda())[0].clone()
+    f = torch.from_numpy(pcm.astype(np.float32) / np.float32(32768.0)).cuda()
+    b = plan.run(f)[0].clone()
+    assert torch.equal(a, b)
+    stereo = torch.from_numpy(np.stack([pcm, pcm], axis=1).copy()).cuda()
+    c = plan.run(stereo)[0].clone()
+    assert torch.equal(a, c)
+
+
+def test_stft_chunk_seam(fe, monkeypatch):
+    """Files longer than the STFT chunk are transformed chunk by chunk, each chunk centre-padded
+    on its own (prepare_dataset.py:234-237).  Exercised with a small chunk size on both sides."""
+    from oracle import frontend_oracle as fo
+    chunk = 100_000
+    monkeypatch.setattr(fo, "STFT_CHUNK", chunk)
+    plan = fe.FrontendPlan(stft_chunk=chunk)
+    for n in (250_000, 200_000, 330_123):
+        pcm = synth.synth_pcm(n / 44100.0, 60 + n % 7)[:n]
+        tiles, mm = plan.run(torch.from_numpy(pcm).cuda())
+        r = fo.process(pcm)
+        assert tiles.shape[0] == len(r.tiles)
+        err = np.abs(tiles[:, 0].cpu().numpy().astype(np.float64) - np.stack(r.tiles))
+        assert err.max() <= TOL_TILE, f"n={n}: {err.max():.3e}"
+    # seam quirk: a last window that starts in one chunk and ends past the file's end in the next
+    p = fo.derive_params()
+    n = chunk + 132 * 30
+    T = fo.n_frames(n, p)
+    assert fo.tile_plan([1 + chunk // 132, 1 + (n - chunk) // 132], p)[-1][0][0] == 0
+    pcm = synth.synth_pcm(n / 44100.0, 99)[:n]
+    tiles, _ = plan.run(torch.from_numpy(pcm).cuda())
+    r = fo.process(pcm)
+    assert tiles.shape[0] == len(r.tiles) and T == r.spectrogram_length
+    err = np.abs(tiles[:, 0].cpu().numpy().astype(np.float64) - np.stack(r.tiles))
+    assert err.max() <= TOL_TILE
+    plan.close()
+
+
+def test_errors(fe):
+    from birdsoundclassif_b200 import _lib
+    with pytest.raises(_lib.NbmError):
+        fe.FrontendPlan(h_pix=5000)
+    fp = fe.File_Processor("/nonexistent/file.wav")
+    assert fp.process_file() == (None, None)
