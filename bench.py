@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""Benchmark of the NBM audio front-end on B200 (BASELINE.json metric: audio-hours/sec).
+
+Workload (BASELINE.json configs[1]): the spectrogram front-end alone on 1024 synthetic 60 s
+mono 44.1 kHz PCM16 clips batched on one B200 -- int16 PCM -> 1324/132 Hann STFT -> dB ->
+band crop -> whole-file min/max -> [25600, 1, 375, 1024] float32 detector tiles.
+A "step" is one pass of the front-end over the whole batch (17.07 audio-hours per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--clips C] [--seconds S]
+    python bench.py --impl reference ...      # the reference's CPU path (oracle port) on host cores
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM.  `e2e`: the same metric through
+the public API with the PCM in pinned host memory (H2D inside the timed region, min/max read back).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_FRAME = 264 + 1500          # 132 int16 samples in + 375 fp32 bins out
+SAMPLE_RATE = 44100
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--clips", type=int, default=1024)
+    ap.add_argument("--seconds", type=float, default=60.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-clips", type=int, default=0, help="clips in the CPU baseline sample (0 = 2 per core)")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------ clocks sampling ---------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ synthetic audio ----------
+def synth_batch_gpu(clips: int, n: int, seed: int, device):
+    """int16 [clips*n] on the device: white noise (sigma 0.05 FS) + chirp 'calls' from a small
+    CPU-generated pool (synth.synth_pcm with the noise switched off)."""
+    import torch
+    from birdsoundclassif_b200 import synth
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    pool = [synth.synth_pcm(n / SAMPLE_RATE, 9000 + i, noise_sigma=0.0)[:n] for i in range(8)]
+    pool = torch.from_numpy(np.stack(pool).astype(np.float32)).to(device)
+    out = torch.empty((clips, n), dtype=torch.int16, device=device)
+    for c0 in range(0, clips, 64):
+        c1 = min(clips, c0 + 64)
+        x = torch.randn((c1 - c0, n), generator=g, device=device) * (0.05 * 32767.0)
+        x += pool[torch.arange(c0, c1, device=device) % pool.shape[0]]
+        out[c0:c1] = x.round_().clamp_(-32768, 32767).to(torch.int16)
+    return out.reshape(-1)
+
+
+# ------------------------------------------------------------------ CPU reference ------------
+def _cpu_one(args):
+    seconds, seed = args
+    from birdsoundclassif_b200 import synth
+    from oracle import frontend_oracle as fo
+    pcm = synth.synth_pcm(seconds, seed)
+    t = time.perf_counter()
+    r = fo.process(pcm)
+    # the reference hands float32 batches to the model (run_detection.py:53)
+    _ = [np.asarray(x, dtype=np.float32) for x in r.tiles]
+    return time.perf_counter() - t
+
+
+def cpu_reference(seconds: float, n_clips: int, procs: int):
+    """Oracle port of the reference front-end (File_Processor.process_file restated in numpy,
+    float64 pocketfft like librosa) on `procs` host processes, one clip per task."""
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    jobs = [(seconds, 7000 + i) for i in range(n_clips)]
+    with ctx.Pool(procs) as pool:
+        pool.map(_cpu_one, jobs[:procs])            # warm-up: imports, page-in
+        t = time.perf_counter()
+        per = pool.map(_cpu_one, jobs)
+        wall = time.perf_counter() - t
+    return n_clips * seconds / 3600.0 / wall, wall, float(np.mean(per))
+
+
+def run_reference(a):
+    """`--impl reference`: the reference's own CPU implementation of the path (its Python needs
+    librosa, absent here, so this is the oracle port) with all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    clips = a.cpu_clips or 2 * cores
+    per_step = []
+    for i in range(a.warmup + a.steps):
+        v, wall, _ = cpu_reference(a.seconds, clips, cores)
+        if i >= a.warmup:
+            per_step.append((v, wall))
+    v = float(np.mean([p[0] for p in per_step]))
+    ms = float(np.mean([p[1] for p in per_step])) * 1e3
+    sample = f"{clips} synthetic {a.seconds:g} s clips per step, one process per core"
+    line = {"impl": "reference", "metric": "audio-hours/sec", "value": v, "unit": "audio-hours/s", "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"front-end alone, {a.clips} x {a.seconds:g} s clips (BASELINE configs[1]); "
+                                   f"CPU arm timed on a bounded sample: {sample}"},
+            "cpu_baseline": {"value": v, "unit": "audio-hours/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "audio-hours/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ B200 arm ------------------
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    from birdsoundclassif_b200 import frontend
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = int(round(a.seconds * SAMPLE_RATE))
+    plan = frontend.get_plan()
+    pcm = synth_batch_gpu(a.clips, n, 1000 * 2 + rank, dev)          # seed = 1000*config + rank
+    offs = [i * n for i in range(a.clips + 1)]
+    n_frames, tile_off, ws_bytes = plan.query_batch([n] * a.clips)
+    frames = int(sum(n_frames))
+    tiles = torch.empty((tile_off[-1], 1, plan.n_bins, plan.w_pix), dtype=torch.float32, device=dev)
+    audio_hours = a.clips * a.seconds / 3600.0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        plan.run_batch(pcm, offs, out=tiles)
+
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    plan.set_profiling(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    stft_ms, tile_ms, runs = plan.get_profile()
+    plan.set_profiling(False)
+    clocks = sampler.stop()
+
+    # ---- end to end: PCM in pinned host memory -> tiles on the device, min/max read back -------
+    e2e = None
+    if not a.no_e2e:
+        host = torch.empty(pcm.shape, dtype=torch.int16).pin_memory()
+        host.copy_(pcm.cpu())
+        mm_host = torch.empty((a.clips, 2), dtype=torch.float32).pin_memory()
+        dpcm = torch.empty_like(pcm)
+
+        def e2e_step():
+            dpcm.copy_(host, non_blocking=True)
+            _, _, mm = plan.run_batch(dpcm, offs, out=tiles)
+            mm_host.copy_(mm, non_blocking=True)
+
+        for _ in range(max(1, a.warmup // 2)):
+            e2e_step()
+        barrier()
+        k = max(1, min(a.steps, 5))
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(k):
+            e2e_step()
+        f1.record()
+        barrier()
+        e2e_ms = f0.elapsed_time(f1) / k
+        e2e = (e2e_ms, host.numel() * 2, mm_host.numel() * 4)
+        del host, dpcm
+
+    # ---- parity spot check on this very data (first clip) against the oracle --------------------
+    parity = None
+    if rank == 0:
+        from oracle import frontend_oracle as fo
+        ref = np.stack(fo.process(pcm[:n].cpu().numpy()).tiles)
+        got = tiles[tile_off[0]:tile_off[1], 0].cpu().numpy().astype(np.float64)
+        err = np.abs(got - ref)
+        parity = {"clip": 0, "max_abs_err_norm": float(err.max()), "frac_gt_1e-4": float((err > 1e-4).mean()),
+                  "rms": float(np.sqrt((err ** 2).mean()))}
+
+    # ---- gather: max time over ranks, totals (NCCL all_gather of a small vector) ----------------
+    stats = torch.tensor([ms, frames, audio_hours * 1e6, stft_ms, tile_ms, e2e[0] if e2e else 0.0],
+                         dtype=torch.float64, device=dev)
+    if world > 1:
+        allst = [torch.empty_like(stats) for _ in range(world)]
+        dist.all_gather(allst, stats)
+        allst = torch.stack(allst).cpu().numpy()
+    else:
+        allst = stats.cpu().numpy()[None]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    t_ms = float(allst[:, 0].max())
+    total_hours = float(allst[:, 2].sum()) / 1e6
+    value = total_hours * a.steps / (t_ms / 1e3)
+    peak, peak_src = peaks()
+    stft_per_launch_ms = float(allst[0, 3]) / max(runs, 1)
+    achieved = frames * BYTES_PER_FRAME / (stft_per_launch_ms / 1e3) / 1e9
+    line = {
+        "metric": "audio-hours/sec", "value": value, "unit": "audio-hours/s", "n_gpus": world, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": t_ms / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"front-end alone, {a.clips} x {a.seconds:g} s mono 44.1 kHz PCM16 clips per GPU "
+                               "(BASELINE configs[1]): STFT 1324/132 Hann -> dB -> 375-bin crop -> file min/max -> "
+                               "1024x375 tiles @ hop 819",
+                   "clips_per_gpu": a.clips, "frames_per_gpu": frames, "tiles_per_gpu": int(tile_off[-1]),
+                   "l2": "inputs (%.1f GB) and outputs (%.1f GB) per step exceed L2 (126 MB); no flush needed"
+                         % (pcm.numel() * 2 / 1e9, tiles.numel() * 4 / 1e9),
+                   "sharding": "files sharded across ranks, no data-path collective"},
+        "roofline": {"bound": "hbm", "kernel": "stft_db_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_frame": BYTES_PER_FRAME, "frames_per_launch": frames,
+                     "ms_per_launch": stft_per_launch_ms,
+                     "tile_kernel_ms_per_launch": float(allst[0, 4]) / max(runs, 1)},
+        "clocks": clocks,
+        "gpu_launches": 4 * a.steps,
+        "parity": parity,
+    }
+    if e2e:
+        e_ms = float(allst[:, 5].max())
+        line["e2e"] = {"value": total_hours / (e_ms / 1e3), "unit": "audio-hours/s", "h2d_bytes_per_step": e2e[1],
+                       "d2h_bytes_per_step": e2e[2], "ms_per_step": e_ms,
+                       "note": "pinned host PCM16 -> H2D -> front-end -> tiles stay on the device for the detector; "
+                               "per-file (s_min, s_max) read back"}
+    if not a.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        clips = a.cpu_clips or 2 * cores
+        v, wall, per = cpu_reference(a.seconds, clips, cores)
+        line["cpu_baseline"] = {"value": v, "unit": "audio-hours/s", "cores": cores, "kind": "port",
+                                "sample": f"{clips} of the {a.seconds:g} s clips, one process per core, "
+                                          f"{wall:.1f} s wall, {per:.2f} s per clip per core"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

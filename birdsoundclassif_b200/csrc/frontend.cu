@@ -328,6 +328,12 @@ struct nbm_frontend_plan {
     void *h_stage = nullptr;
     size_t h_stage_bytes = 0;
     cudaEvent_t staged = nullptr;
+    // optional per-kernel timing (nbm_frontend_set_profiling)
+    bool profiling = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    double acc_ms[2] = {0.0, 0.0};
+    long long acc_runs = 0;
+    bool ev_pending = false;
 };
 
 namespace {
@@ -420,8 +426,9 @@ extern "C" int nbm_frontend_plan_create(const nbm_frontend_params *p, nbm_fronte
     if ((e = cudaMalloc(&pl->d_tw, N2 * sizeof(float2))) != cudaSuccess ||
         (e = cudaMemcpy(pl->d_tw, tw.data(), N2 * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&pl->staged, cudaEventDisableTiming)) != cudaSuccess ||
+        // the attribute is per function, not per plan: always allow the device maximum
         (e = cudaFuncSetAttribute(stft_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)pl->smem_bytes)) != cudaSuccess) {
+                                  max_smem)) != cudaSuccess) {
         int rc = cuda_fail(e, "plan_create");
         nbm_frontend_plan_destroy(pl);
         return rc;
@@ -436,6 +443,7 @@ extern "C" int nbm_frontend_plan_destroy(nbm_frontend_plan *pl) {
     if (pl->d_tw) cudaFree(pl->d_tw);
     if (pl->h_stage) cudaFreeHost(pl->h_stage);
     if (pl->staged) cudaEventDestroy(pl->staged);
+    for (auto &e : pl->ev) if (e) cudaEventDestroy(e);
     delete pl;
     return NBM_OK;
 }
@@ -478,6 +486,39 @@ extern "C" int nbm_frontend_spectrogram_view(const nbm_frontend_plan *pl, const 
         spec_floats += (size_t)L.row_stride * pl->prm.n_bins;
     }
     if (offset_bytes) *offset_bytes = desc_bytes(n_segs, n_files) + mine * sizeof(float);
+    return NBM_OK;
+}
+
+// fold the previous profiled run's event pairs into the accumulators (waits for that run)
+static int collect_profile(nbm_frontend_plan *pl) {
+    if (!pl->ev_pending) return NBM_OK;
+    NBM_CUDA(cudaEventSynchronize(pl->ev[3]));
+    float a = 0.f, b = 0.f;
+    NBM_CUDA(cudaEventElapsedTime(&a, pl->ev[0], pl->ev[1]));
+    NBM_CUDA(cudaEventElapsedTime(&b, pl->ev[2], pl->ev[3]));
+    pl->acc_ms[0] += a; pl->acc_ms[1] += b; pl->acc_runs += 1;
+    pl->ev_pending = false;
+    return NBM_OK;
+}
+
+extern "C" int nbm_frontend_set_profiling(nbm_frontend_plan *pl, int32_t enable) {
+    NBM_REQUIRE(pl, "null plan");
+    std::lock_guard<std::mutex> lock(pl->mu);
+    if (enable && !pl->ev[0])
+        for (auto &e : pl->ev) NBM_CUDA(cudaEventCreate(&e));
+    pl->profiling = enable != 0;
+    pl->acc_ms[0] = pl->acc_ms[1] = 0.0; pl->acc_runs = 0; pl->ev_pending = false;
+    return NBM_OK;
+}
+
+extern "C" int nbm_frontend_get_profile(nbm_frontend_plan *pl, double *stft_ms, double *tile_ms, int64_t *runs) {
+    NBM_REQUIRE(pl, "null plan");
+    std::lock_guard<std::mutex> lock(pl->mu);
+    int rc = collect_profile(pl);
+    if (rc != NBM_OK) return rc;
+    if (stft_ms) *stft_ms = pl->acc_ms[0];
+    if (tile_ms) *tile_ms = pl->acc_ms[1];
+    if (runs) *runs = pl->acc_runs;
     return NBM_OK;
 }
 
@@ -556,12 +597,21 @@ extern "C" int nbm_frontend_run_batch(const nbm_frontend_plan *cpl, const void *
         NBM_CUDA(cudaMemcpyAsync(ws, pl->h_stage, up, cudaMemcpyHostToDevice, stream));
         NBM_CUDA(cudaEventRecord(pl->staged, stream));
     }
+    const bool prof = pl->profiling;
+    if (prof) {
+        int rc = collect_profile(pl);
+        if (rc != NBM_OK) return rc;
+    }
     init_minmax_kernel<<<(n_files + 255) / 256, 256, 0, stream>>>(d_enc, n_files);
+    if (prof) NBM_CUDA(cudaEventRecord(pl->ev[0], stream));
     stft_db_kernel<<<groups, pl->n_threads, pl->smem_bytes, stream>>>(pl->kp, d_segs, (int)segs.size(), d_pcm,
                                                                       pcm_dtype, channels, d_spec, d_enc);
+    if (prof) NBM_CUDA(cudaEventRecord(pl->ev[1], stream));
     finalize_minmax_kernel<<<(n_files + 255) / 256, 256, 0, stream>>>(d_enc, d_minmax, n_files);
     dim3 grid((unsigned)tiles, (unsigned)((p.n_bins + TILE_ROWS - 1) / TILE_ROWS));
+    if (prof) NBM_CUDA(cudaEventRecord(pl->ev[2], stream));
     tile_kernel<<<grid, 256, 0, stream>>>(pl->kp, d_files, n_files, d_spec, d_minmax, d_tiles);
+    if (prof) { NBM_CUDA(cudaEventRecord(pl->ev[3], stream)); pl->ev_pending = true; }
     NBM_CUDA(cudaGetLastError());
     return NBM_OK;
 }

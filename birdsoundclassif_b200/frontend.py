@@ -145,6 +145,16 @@ class FrontendPlan:
         self._last_sizes = sizes
         return out, tile_off, minmax
 
+    def set_profiling(self, enable: bool):
+        _lib.check(_lib.lib().nbm_frontend_set_profiling(self._h, int(bool(enable))), "nbm_frontend_set_profiling")
+
+    def get_profile(self):
+        """(stft_ms, tile_ms, runs) accumulated since profiling was enabled; waits for the last run."""
+        a, b, n = C.c_double(), C.c_double(), C.c_int64()
+        _lib.check(_lib.lib().nbm_frontend_get_profile(self._h, C.byref(a), C.byref(b), C.byref(n)),
+                   "nbm_frontend_get_profile")
+        return a.value, b.value, n.value
+
     def spectrogram_view(self, file_index: int = 0) -> torch.Tensor:
         """Un-normalised dB band [n_bins, n_frames] of a file from the LAST run (a view into the
         workspace; for tests and diagnostics)."""

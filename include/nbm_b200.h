@@ -99,6 +99,13 @@ int nbm_frontend_spectrogram_view(const nbm_frontend_plan *plan, const int64_t *
                                   int32_t n_files, int32_t file_index, size_t *offset_bytes,
                                   int64_t *row_stride);
 
+/* Per-kernel device timing for benchmarks: when enabled, every run records CUDA events on the
+ * caller's stream around the STFT/dB kernel and the tiling kernel; get_profile waits for the
+ * last profiled run and returns the accumulated milliseconds and the number of runs since
+ * profiling was (re-)enabled. */
+int nbm_frontend_set_profiling(nbm_frontend_plan *plan, int32_t enable);
+int nbm_frontend_get_profile(nbm_frontend_plan *plan, double *stft_ms, double *tile_ms, int64_t *runs);
+
 /* ------------------------------------------------------------- post-processing --------
  * Anchor table: generate_anchors_frcnn + get_anchor_shifts_frcnn combined as in
  * ProposalLayer.forward (nets_utils.py:35-59, layers.py:252-258).  Host arithmetic;
