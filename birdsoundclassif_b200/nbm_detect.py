@@ -1,0 +1,86 @@
+"""CLI with the reference's ``nbm_detect.py`` contract (nbm_model/nbm_detect.py:6-29):
+
+    python -m birdsoundclassif_b200.nbm_detect --ckpt model_weights --audio_dir D [--min_score .2] [--batch 4]
+    torchrun --nproc-per-node N -m birdsoundclassif_b200.nbm_detect ...     # files sharded over N GPUs
+
+For every ``D/*.wav`` it writes ``str(output_dict)`` to the sibling ``.txt``.  The detector is the
+reference's own model, loaded by the reference's ``load_model`` (``nbm_model`` must be importable,
+e.g. PYTHONPATH=<reference checkout>); its hot-path symbols are patched to libnbm_b200."""
+from __future__ import annotations
+
+import argparse
+import glob
+import json
+import os
+import time
+
+import torch
+
+from . import run_detection as rd
+from . import sharding
+
+
+def detect_directory(model, model_args, audio_dir, bird_dict="bird_dict.json", min_score=0.2, bs=4,
+                     rank=0, world=1, skip_done=False, verbose=True) -> dict:
+    files = sharding.shard_files(glob.glob(os.path.join(audio_dir, "*.wav")), rank, world)
+    counts = dict.fromkeys(sharding.COUNT_FIELDS, 0)
+    t_wall = time.perf_counter()
+    for wav_path in files:
+        out_path = wav_path.replace(".wav", ".txt")
+        if skip_done and os.path.exists(out_path):
+            continue
+        tm = {}
+        try:
+            output = rd.run_detection(model, model_args, wav_path, bird_dicts_path=bird_dict, min_score=min_score,
+                                      bs=bs, timings=tm)
+        except Exception as e:          # per-file failure isolation (the reference crashes)
+            print(f"[rank {rank}] {wav_path}: FAILED: {e}")
+            continue
+        with open(out_path, "w") as f:
+            f.write(str(output))
+        counts["files"] += 1
+        counts["tiles"] += tm["tiles"]; counts["frames"] += tm["frames"]; counts["detections"] += tm["detections"]
+        counts["t_front_us"] += int(tm["frontend_s"] * 1e6); counts["t_model_us"] += int(tm["model_s"] * 1e6)
+        counts["t_post_us"] += int(tm["post_s"] * 1e6)
+        if verbose:
+            print(f"~~~~~ File {os.path.basename(wav_path).replace('.wav', '')} done ~~~~~")
+    torch.cuda.synchronize()
+    counts["t_wall_us"] = int((time.perf_counter() - t_wall) * 1e6)
+    return counts
+
+
+def main(argv=None):
+    parser = argparse.ArgumentParser("Bird call detection with NBM model (B200 hot path)")
+    parser.add_argument("--ckpt", dest="model_dirp", type=str, default="model_weights")
+    parser.add_argument("--audio_dir", dest="audio_dirp", type=str, required=True)
+    parser.add_argument("--min_score", type=float, default=0.2)
+    parser.add_argument("--batch", dest="bs", type=int, default=4)
+    parser.add_argument("--bird_dict", type=str, default="bird_dict.json")
+    parser.add_argument("--skip_done", action="store_true", help="skip wavs that already have a .txt")
+    args = parser.parse_args(argv)
+    assert os.path.isfile(args.bird_dict), "Missing dictionary of bird species names --> bird_dict.json."
+
+    rank, world, local = sharding.env_rank_world()
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+    try:
+        from nbm_model.run_detection import load_model      # the reference's loader, unchanged
+    except ImportError as e:
+        raise SystemExit("nbm_model (the reference checkout) must be importable: it provides the detector "
+                         f"network and load_model ({e})")
+    model, model_args = load_model(args.model_dirp)
+    rd.patch_reference()
+    rd.accelerate_model(model)
+    counts = detect_directory(model, model_args, args.audio_dirp, args.bird_dict, args.min_score, args.bs,
+                              rank, world, args.skip_done)
+    per_rank = sharding.gather_counts(counts, device=torch.device("cuda", local))
+    if rank == 0:
+        print(json.dumps({"per_rank": per_rank, "totals": sharding.totals(per_rank)}))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,99 @@
+"""GPU host driver with the reference's ``run_detection`` / ``merge_images`` call surface.
+
+Mirrors ``nbm_model/run_detection.py``: ``run_detection(model, config, wav_path,
+bird_dicts_path, min_score=0.5, bs=10, ...)`` (:28-84) returns the same
+``{species: {'bbox_coord': [[x1,y1,x2,y2],...], 'scores': [...]}}`` dictionary and batches the
+detector windows identically (bs, order, partial last batch -- the reference's ``nms`` and
+``ProposalLayer`` are batch-coupled).  Differences are only WHERE the work
+happens: PCM16 goes to the GPU once, the front-end produces the ``[n,1,375,1024]`` float32
+tensor on the device (no ``np.stack`` + host cast + H2D per batch, run_detection.py:53), and
+the per-file merge runs in one library call instead of a 150 x n_tiles Python loop.
+
+``model`` is the reference's ``NbmModel`` (loaded by its own ``load_model``, unchanged) or any
+callable with the same contract: ``model(batch[:, None], min_score=...)`` -> list (one per
+image) of ``{'1'..str(num_classes): {'bbox_coord': [n,4], 'scores': [1,n]}}``.
+``patch_reference()`` swaps the reference's hot-path symbols for the library-backed ones.
+"""
+from __future__ import annotations
+
+import json
+import sys
+import time
+
+import torch
+
+from . import postproc
+from .frontend import File_Processor
+
+
+def patch_reference() -> list[str]:
+    """Monkey-patch the reference modules (when importable as ``nbm_model.*``) so its unchanged
+    model code calls libnbm_b200: ``nms`` and ``bbox_reg_to_coord`` are imported BY NAME into
+    ``nbm_model.nets.layers`` (layers.py:4) and ``nbm_model.run_detection`` (run_detection.py:18).
+    Returns the list of patched symbols."""
+    done = []
+    for modname, names in (("nbm_model.nets.layers", ("nms", "bbox_reg_to_coord")),
+                           ("nbm_model.nets.util.nets_utils", ("nms", "bbox_reg_to_coord")),
+                           ("nbm_model.run_detection", ("nms", "merge_images", "File_Processor"))):
+        mod = sys.modules.get(modname)
+        if mod is None:
+            continue
+        for n in names:
+            if hasattr(mod, n):
+                setattr(mod, n, {"nms": postproc.nms, "bbox_reg_to_coord": postproc.bbox_reg_to_coord,
+                                 "merge_images": postproc.merge_images, "File_Processor": File_Processor}[n])
+                done.append(f"{modname}.{n}")
+    return done
+
+
+def accelerate_model(model):
+    """Swap the parameter-free ProposalLayer of a reference NbmModel (head.prop_layer,
+    head.py:18) for the fused one; state_dict keys are unaffected."""
+    head = getattr(model, "head", None)
+    if head is not None and hasattr(head, "prop_layer"):
+        old = head.prop_layer
+        head.prop_layer = postproc.ProposalLayer(old.config, old.n_layers).train(old.training)
+    return model
+
+
+def detect_tiles(model, tiles: torch.Tensor, min_score: float, bs: int) -> list:
+    """Run the detector over device-resident tiles [n, H, W] in the reference's batching
+    (run_detection.py:47-67).  Returns the list of per-batch outputs."""
+    outputs = []
+    n_img = len(tiles)
+    for s in range(0, n_img, bs):
+        batch = tiles[s:s + bs]
+        with torch.no_grad():
+            outputs.append(model(batch[:, None], min_score=min_score))
+    return outputs
+
+
+def run_detection(model, config, wav_path, bird_dicts_path, min_score=0.5, bs=10, visualise_outputs=False,
+                  show_sp_name=True, timings: dict | None = None):
+    """Same signature and return value as the reference's run_detection (plotting is not
+    offered: visualise_outputs must be False)."""
+    if visualise_outputs:
+        raise NotImplementedError("matplotlib visualisation is out of scope")
+    t0 = time.perf_counter()
+    fp = File_Processor(wav_path)
+    img_db, _ = fp.process_file()
+    if img_db is None:
+        raise RuntimeError(f"{wav_path}: could not be loaded")      # the reference crashes at len(None), :47
+    t1 = time.perf_counter()
+    outputs = detect_tiles(model, img_db, min_score, bs)
+    t2 = time.perf_counter()
+
+    with open(bird_dicts_path, "r") as f:
+        birds_dict = json.load(f)
+    birds_dict.update({"Non bird sound": 0})
+    reverse_dict = {idx: name for name, idx in birds_dict.items()}
+
+    class_bbox = postproc.merge_images(fp, outputs, config.num_classes)
+    output = {reverse_dict[idx]: {k: v.cpu().numpy().tolist() for k, v in class_bbox[str(idx)].items()}
+              for idx in range(1, len(class_bbox) + 1) if len(class_bbox[str(idx)]["bbox_coord"]) > 0}
+    if timings is not None:
+        t3 = time.perf_counter()
+        timings.update(frontend_s=t1 - t0, model_s=t2 - t1, post_s=t3 - t2, tiles=len(img_db),
+                       frames=int(fp.spectrogram_length),
+                       detections=sum(len(v["scores"]) for v in output.values()))
+    return output
