@@ -33,6 +33,7 @@ SIGNATURES = {
     "nbm_last_error": (C.c_char_p, []),
     "nbm_frontend_plan_create": (C.c_int, [C.POINTER(FrontendParams), C.POINTER(_p)]),
     "nbm_frontend_plan_destroy": (C.c_int, [_p]),
+    "nbm_frontend_impl": (C.c_int, [_p]),
     "nbm_frontend_query": (C.c_int, [_p, _i64, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_sz)]),
     "nbm_frontend_query_batch": (C.c_int, [_p, C.POINTER(_i64), _i32, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_sz)]),
     "nbm_frontend_run": (C.c_int, [_p, _p, _i32, _i32, _i64, _p, _p, _p, _sz, _p]),

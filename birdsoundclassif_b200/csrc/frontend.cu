@@ -17,25 +17,17 @@
 #include <vector>
 #include <cmath>
 
+#include <cstdlib>
+
 #include "common.cuh"
+#include "frontend_tc.cuh"
 
 namespace nbm {
 
-constexpr int GF = 64;      // frames per group (one anchor per group)
 constexpr int PASS = 32;    // frames slid per direction
 constexpr int BINS_PER_WARP = 30;
 constexpr int STAGE_LD = PASS + 1;
 constexpr int TILE_ROWS = 15;   // spectrogram rows per block in the tiling kernel
-
-struct SegDesc {
-    long long pcm_start;   // per-channel sample index of the segment's first sample
-    long long n_samples;   // samples in this STFT chunk (prepare_dataset.py:236-237)
-    long long spec_off;    // float offset of S[0][first column of this segment]
-    int n_frames;
-    int row_stride;
-    int file;
-    int group0;            // index of the segment's first 64-frame group
-};
 
 struct FileDesc {
     long long spec_off;    // float offset of the file's S[0][0]
@@ -323,6 +315,7 @@ struct nbm_frontend_plan {
     int device = 0;
     int n_threads = 0;
     size_t smem_bytes = 0;
+    TcPlan *tc = nullptr;           // tensor-core path (nullptr -> CUDA-core stft_db_kernel)
     // pinned staging for descriptor uploads
     std::mutex mu;
     void *h_stage = nullptr;
@@ -338,49 +331,96 @@ struct nbm_frontend_plan {
 
 namespace {
 
-struct FileLayout {
-    int64_t n_frames = 0, n_tiles = 0;
-    int last_width = 0;
-    int64_t row_stride = 0;
-    std::vector<int64_t> seg_samples, seg_frames;
+// Everything the host derives from the per-file sample counts: STFT chunks (prepare_dataset.py:236),
+// detector windows (:266) with the last window's valid width (:268-278 incl. the seam quirk), the
+// 64-frame groups, the anchor tasks of the tensor-core path, and the workspace carve-up
+//   [segs | files | task_seg | task_first | min/max codes | anchors | dB bands].
+struct BatchLayout {
+    std::vector<SegDesc> segs;
+    std::vector<FileDesc> files;
+    std::vector<int> task_seg, task_first;
+    std::vector<int64_t> n_frames;
+    size_t spec_floats = 0;
+    long long tiles = 0, n_anchors = 0;
+    int groups = 0;
+    size_t o_segs = 0, o_files = 0, o_tseg = 0, o_tfirst = 0, o_mm = 0, o_anchors = 0, o_spec = 0, total = 0;
+    size_t upload_bytes = 0;       // segs .. task_first are uploaded from the host
 };
 
-FileLayout layout_of(const nbm_frontend_params &p, int64_t n) {
-    FileLayout L;
-    const int64_t n_chunks = n / p.stft_chunk + 1;          // range(int(len/max_l)+1), :236
-    for (int64_t c = 0; c < n_chunks; ++c) {
-        int64_t len = std::max<int64_t>(0, std::min<int64_t>(n, (c + 1) * p.stft_chunk) - c * p.stft_chunk);
-        L.seg_samples.push_back(len);
-        L.seg_frames.push_back(1 + len / p.hop);
-        L.n_frames += 1 + len / p.hop;
-    }
-    const int64_t T = L.n_frames;
-    // max(1, int(1 + ceil((T - w_pix) / hop_spectro)))  :266
-    int64_t nt = 1;
-    if (T > p.w_pix) nt = 1 + (T - p.w_pix + p.hop_spectro - 1) / p.hop_spectro;
-    L.n_tiles = std::max<int64_t>(1, nt);
-    // valid width of the last window, including the reference's seam quirk (:268-278): a window
-    // that starts in chunk c and runs past the end of the file keeps chunk c's columns only.
-    const int64_t start = (L.n_tiles - 1) * (int64_t)p.hop_spectro;
-    const int64_t end = start + p.w_pix;
-    if (end <= T) {
-        L.last_width = p.w_pix;
-    } else {
-        int64_t edge = 0;
-        size_t c = 0;
-        for (; c < L.seg_frames.size(); ++c) {
-            if (start < edge + L.seg_frames[c]) break;
-            edge += L.seg_frames[c];
+int build_layout(const nbm_frontend_plan *pl, const int64_t *sizes, const int64_t *offsets, int n_files, BatchLayout &B) {
+    const nbm_frontend_params &p = pl->prm;
+    const int na_group = pl->tc ? tc_anchor_group() : 1;
+    B.files.resize(n_files);
+    B.n_frames.resize(n_files);
+    for (int f = 0; f < n_files; ++f) {
+        const int64_t n = sizes ? sizes[f] : offsets[f + 1] - offsets[f];
+        NBM_REQUIRE(n >= 0, "negative sample count for file %d", f);
+        FileDesc &fd = B.files[f];
+        fd.spec_off = (long long)B.spec_floats;
+        fd.tile0 = B.tiles;
+        long long T = 0, col = 0, s = offsets ? offsets[f] : 0;
+        const int64_t n_chunks = n / p.stft_chunk + 1;              // range(int(len/max_l)+1)
+        const size_t seg_first = B.segs.size();
+        for (int64_t c = 0; c < n_chunks; ++c) {
+            const int64_t len = std::max<int64_t>(0, std::min<int64_t>(n, (c + 1) * p.stft_chunk) - c * p.stft_chunk);
+            SegDesc sd;
+            sd.pcm_start = s;
+            sd.n_samples = len;
+            sd.spec_off = 0;                                         // patched below (needs row_stride)
+            sd.n_frames = (int)(1 + len / p.hop);
+            sd.row_stride = 0;
+            sd.file = f;
+            sd.group0 = B.groups;
+            const int tiles_seg = (sd.n_frames + GF - 1) / GF;
+            if (pl->tc)
+                for (int a0 = 0; a0 < tiles_seg + 1; a0 += na_group) { B.task_seg.push_back((int)B.segs.size()); B.task_first.push_back(a0); }
+            B.groups += tiles_seg;
+            B.n_anchors += tiles_seg + 1;
+            B.segs.push_back(sd);
+            T += sd.n_frames;
+            s += len;
         }
-        L.last_width = (int)(edge + L.seg_frames[c] - start);
+        NBM_REQUIRE(T < (1ll << 31) - 64, "file %d too long", f);
+        const long long stride = (long long)align_up((size_t)T, 32);
+        for (size_t i = seg_first; i < B.segs.size(); ++i) {
+            B.segs[i].spec_off = fd.spec_off + col;
+            B.segs[i].row_stride = (int)stride;
+            col += B.segs[i].n_frames;
+        }
+        long long nt = 1;                                            // max(1, int(1 + ceil((T - w_pix) / hop_spectro)))
+        if (T > p.w_pix) nt = 1 + (T - p.w_pix + p.hop_spectro - 1) / p.hop_spectro;
+        const long long start = (nt - 1) * (long long)p.hop_spectro;
+        int last_width = p.w_pix;
+        if (start + p.w_pix > T) {
+            // a window that starts in chunk c and runs past the end of the FILE keeps chunk c's columns only
+            long long edge = 0;
+            size_t i = seg_first;
+            for (; i < B.segs.size(); ++i) {
+                if (start < edge + B.segs[i].n_frames) break;
+                edge += B.segs[i].n_frames;
+            }
+            last_width = (int)(edge + B.segs[i].n_frames - start);
+        }
+        fd.row_stride = (int)stride;
+        fd.n_tiles = (int)nt;
+        fd.total_frames = (int)T;
+        fd.last_width = last_width;
+        B.n_frames[f] = T;
+        B.spec_floats += (size_t)stride * p.n_bins;
+        B.tiles += nt;
     }
-    L.row_stride = (int64_t)align_up((size_t)T, 32);
-    return L;
-}
-
-size_t desc_bytes(size_t n_segs, size_t n_files) {
-    return align_up(n_segs * sizeof(SegDesc), 256) + align_up(n_files * sizeof(FileDesc), 256) +
-           align_up(n_files * 2 * sizeof(unsigned int), 256);
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t at = o; o = align_up(o + bytes, 256); return at; };
+    B.o_segs = take(B.segs.size() * sizeof(SegDesc));
+    B.o_files = take(B.files.size() * sizeof(FileDesc));
+    B.o_tseg = take(B.task_seg.size() * sizeof(int));
+    B.o_tfirst = take(B.task_first.size() * sizeof(int));
+    B.upload_bytes = o;
+    B.o_mm = take((size_t)n_files * 2 * sizeof(unsigned int));
+    B.o_anchors = take(pl->tc ? tc_anchor_bytes(pl->tc, B.n_anchors) : 0);
+    B.o_spec = take(B.spec_floats * sizeof(float));
+    B.total = o;
+    return NBM_OK;
 }
 
 }  // namespace
@@ -434,6 +474,12 @@ extern "C" int nbm_frontend_plan_create(const nbm_frontend_params *p, nbm_fronte
         return rc;
     }
     k.tw = pl->d_tw;
+    // tensor-core path unless the parameters do not fit it or NBM_FRONTEND_IMPL=cuda-core asks for the other one
+    const char *impl = getenv("NBM_FRONTEND_IMPL");
+    if (!(impl && strcmp(impl, "cuda-core") == 0)) {
+        int rc = tc_plan_create(*p, &pl->tc);
+        if (rc != NBM_OK && rc != NBM_ERR_UNSUPPORTED) { nbm_frontend_plan_destroy(pl); return rc; }
+    }
     *out = pl;
     return NBM_OK;
 }
@@ -444,26 +490,25 @@ extern "C" int nbm_frontend_plan_destroy(nbm_frontend_plan *pl) {
     if (pl->h_stage) cudaFreeHost(pl->h_stage);
     if (pl->staged) cudaEventDestroy(pl->staged);
     for (auto &e : pl->ev) if (e) cudaEventDestroy(e);
+    tc_plan_destroy(pl->tc);
     delete pl;
     return NBM_OK;
 }
 
+extern "C" int nbm_frontend_impl(const nbm_frontend_plan *pl) { return pl && pl->tc ? 1 : 0; }
+
 extern "C" int nbm_frontend_query_batch(const nbm_frontend_plan *pl, const int64_t *n_samples, int32_t n_files,
                                         int64_t *n_frames, int64_t *tile_offsets, size_t *workspace_bytes) {
     NBM_REQUIRE(pl && n_samples && n_files >= 1, "bad argument");
-    size_t n_segs = 0, spec_floats = 0;
-    int64_t tiles = 0;
+    BatchLayout B;
+    int rc = build_layout(pl, n_samples, nullptr, n_files, B);
+    if (rc != NBM_OK) return rc;
     for (int f = 0; f < n_files; ++f) {
-        NBM_REQUIRE(n_samples[f] >= 0, "negative sample count");
-        FileLayout L = layout_of(pl->prm, n_samples[f]);
-        n_segs += L.seg_frames.size();
-        spec_floats += (size_t)L.row_stride * pl->prm.n_bins;
-        if (n_frames) n_frames[f] = L.n_frames;
-        if (tile_offsets) tile_offsets[f] = tiles;
-        tiles += L.n_tiles;
+        if (n_frames) n_frames[f] = B.n_frames[f];
+        if (tile_offsets) tile_offsets[f] = B.files[f].tile0;
     }
-    if (tile_offsets) tile_offsets[n_files] = tiles;
-    if (workspace_bytes) *workspace_bytes = desc_bytes(n_segs, n_files) + spec_floats * sizeof(float);
+    if (tile_offsets) tile_offsets[n_files] = B.tiles;
+    if (workspace_bytes) *workspace_bytes = B.total;
     return NBM_OK;
 }
 
@@ -478,14 +523,11 @@ extern "C" int nbm_frontend_query(const nbm_frontend_plan *pl, int64_t n_samples
 extern "C" int nbm_frontend_spectrogram_view(const nbm_frontend_plan *pl, const int64_t *n_samples, int32_t n_files,
                                              int32_t file_index, size_t *offset_bytes, int64_t *row_stride) {
     NBM_REQUIRE(pl && n_samples && file_index >= 0 && file_index < n_files, "bad argument");
-    size_t n_segs = 0, spec_floats = 0, mine = 0;
-    for (int f = 0; f < n_files; ++f) {
-        FileLayout L = layout_of(pl->prm, n_samples[f]);
-        n_segs += L.seg_frames.size();
-        if (f == file_index) { mine = spec_floats; if (row_stride) *row_stride = L.row_stride; }
-        spec_floats += (size_t)L.row_stride * pl->prm.n_bins;
-    }
-    if (offset_bytes) *offset_bytes = desc_bytes(n_segs, n_files) + mine * sizeof(float);
+    BatchLayout B;
+    int rc = build_layout(pl, n_samples, nullptr, n_files, B);
+    if (rc != NBM_OK) return rc;
+    if (offset_bytes) *offset_bytes = B.o_spec + (size_t)B.files[file_index].spec_off * sizeof(float);
+    if (row_stride) *row_stride = B.files[file_index].row_stride;
     return NBM_OK;
 }
 
@@ -533,58 +575,24 @@ extern "C" int nbm_frontend_run_batch(const nbm_frontend_plan *cpl, const void *
     cudaStream_t stream = (cudaStream_t)stream_;
     const nbm_frontend_params &p = pl->prm;
 
-    std::vector<SegDesc> segs;
-    std::vector<FileDesc> files(n_files);
-    size_t spec_floats = 0;
-    long long tiles = 0;
-    int groups = 0;
-    for (int f = 0; f < n_files; ++f) {
-        const int64_t n = sample_offsets[f + 1] - sample_offsets[f];
-        NBM_REQUIRE(n >= 0, "sample_offsets must be non-decreasing");
-        FileLayout L = layout_of(p, n);
-        NBM_REQUIRE(L.row_stride < (1ll << 31), "file too long");
-        FileDesc &fd = files[f];
-        fd.spec_off = (long long)spec_floats;
-        fd.tile0 = tiles;
-        fd.row_stride = (int)L.row_stride;
-        fd.n_tiles = (int)L.n_tiles;
-        fd.total_frames = (int)L.n_frames;
-        fd.last_width = L.last_width;
-        long long col = 0, s = sample_offsets[f];
-        for (size_t c = 0; c < L.seg_frames.size(); ++c) {
-            SegDesc sd;
-            sd.pcm_start = s;
-            sd.n_samples = L.seg_samples[c];
-            sd.spec_off = fd.spec_off + col;
-            sd.n_frames = (int)L.seg_frames[c];
-            sd.row_stride = fd.row_stride;
-            sd.file = f;
-            sd.group0 = groups;
-            segs.push_back(sd);
-            groups += (int)((L.seg_frames[c] + GF - 1) / GF);
-            col += L.seg_frames[c];
-            s += L.seg_samples[c];
-        }
-        spec_floats += (size_t)L.row_stride * p.n_bins;
-        tiles += L.n_tiles;
-    }
-    const size_t seg_b = align_up(segs.size() * sizeof(SegDesc), 256);
-    const size_t file_b = align_up(files.size() * sizeof(FileDesc), 256);
-    const size_t mm_b = align_up((size_t)n_files * 2 * sizeof(unsigned int), 256);
-    const size_t need = seg_b + file_b + mm_b + spec_floats * sizeof(float);
-    if (workspace_bytes < need) {
-        set_error("workspace too small: %zu < %zu", workspace_bytes, need);
+    BatchLayout B;
+    int rc = build_layout(pl, nullptr, sample_offsets, n_files, B);
+    if (rc != NBM_OK) return rc;
+    if (workspace_bytes < B.total) {
+        set_error("workspace too small: %zu < %zu", workspace_bytes, B.total);
         return NBM_ERR_WORKSPACE;
     }
     char *ws = reinterpret_cast<char *>(d_workspace);
-    SegDesc *d_segs = reinterpret_cast<SegDesc *>(ws);
-    FileDesc *d_files = reinterpret_cast<FileDesc *>(ws + seg_b);
-    unsigned int *d_enc = reinterpret_cast<unsigned int *>(ws + seg_b + file_b);
-    float *d_spec = reinterpret_cast<float *>(ws + seg_b + file_b + mm_b);
+    SegDesc *d_segs = reinterpret_cast<SegDesc *>(ws + B.o_segs);
+    FileDesc *d_files = reinterpret_cast<FileDesc *>(ws + B.o_files);
+    const int *d_tseg = reinterpret_cast<const int *>(ws + B.o_tseg);
+    const int *d_tfirst = reinterpret_cast<const int *>(ws + B.o_tfirst);
+    unsigned int *d_enc = reinterpret_cast<unsigned int *>(ws + B.o_mm);
+    float *d_spec = reinterpret_cast<float *>(ws + B.o_spec);
 
+    std::lock_guard<std::mutex> lock(pl->mu);
     {
-        std::lock_guard<std::mutex> lock(pl->mu);
-        const size_t up = seg_b + file_b;
+        const size_t up = B.upload_bytes;
         if (pl->h_stage_bytes < up) {
             if (pl->h_stage) { NBM_CUDA(cudaEventSynchronize(pl->staged)); cudaFreeHost(pl->h_stage); pl->h_stage = nullptr; }
             NBM_CUDA(cudaMallocHost(&pl->h_stage, up));
@@ -592,23 +600,34 @@ extern "C" int nbm_frontend_run_batch(const nbm_frontend_plan *cpl, const void *
         } else {
             NBM_CUDA(cudaEventSynchronize(pl->staged));     // previous upload has left the staging buffer
         }
-        memcpy(pl->h_stage, segs.data(), segs.size() * sizeof(SegDesc));
-        memcpy((char *)pl->h_stage + seg_b, files.data(), files.size() * sizeof(FileDesc));
+        char *h = reinterpret_cast<char *>(pl->h_stage);
+        memcpy(h + B.o_segs, B.segs.data(), B.segs.size() * sizeof(SegDesc));
+        memcpy(h + B.o_files, B.files.data(), B.files.size() * sizeof(FileDesc));
+        if (!B.task_seg.empty()) {
+            memcpy(h + B.o_tseg, B.task_seg.data(), B.task_seg.size() * sizeof(int));
+            memcpy(h + B.o_tfirst, B.task_first.data(), B.task_first.size() * sizeof(int));
+        }
         NBM_CUDA(cudaMemcpyAsync(ws, pl->h_stage, up, cudaMemcpyHostToDevice, stream));
         NBM_CUDA(cudaEventRecord(pl->staged, stream));
     }
     const bool prof = pl->profiling;
     if (prof) {
-        int rc = collect_profile(pl);
+        rc = collect_profile(pl);
         if (rc != NBM_OK) return rc;
     }
     init_minmax_kernel<<<(n_files + 255) / 256, 256, 0, stream>>>(d_enc, n_files);
     if (prof) NBM_CUDA(cudaEventRecord(pl->ev[0], stream));
-    stft_db_kernel<<<groups, pl->n_threads, pl->smem_bytes, stream>>>(pl->kp, d_segs, (int)segs.size(), d_pcm,
-                                                                      pcm_dtype, channels, d_spec, d_enc);
+    if (pl->tc) {
+        rc = tc_launch(pl->tc, d_segs, (int)B.segs.size(), B.groups, d_tseg, d_tfirst, (int)B.task_seg.size(), d_pcm,
+                       pcm_dtype, channels, d_spec, d_enc, ws + B.o_anchors, stream);
+        if (rc != NBM_OK) return rc;
+    } else {
+        stft_db_kernel<<<B.groups, pl->n_threads, pl->smem_bytes, stream>>>(pl->kp, d_segs, (int)B.segs.size(), d_pcm,
+                                                                          pcm_dtype, channels, d_spec, d_enc);
+    }
     if (prof) NBM_CUDA(cudaEventRecord(pl->ev[1], stream));
     finalize_minmax_kernel<<<(n_files + 255) / 256, 256, 0, stream>>>(d_enc, d_minmax, n_files);
-    dim3 grid((unsigned)tiles, (unsigned)((p.n_bins + TILE_ROWS - 1) / TILE_ROWS));
+    dim3 grid((unsigned)B.tiles, (unsigned)((p.n_bins + TILE_ROWS - 1) / TILE_ROWS));
     if (prof) NBM_CUDA(cudaEventRecord(pl->ev[2], stream));
     tile_kernel<<<grid, 256, 0, stream>>>(pl->kp, d_files, n_files, d_spec, d_minmax, d_tiles);
     if (prof) { NBM_CUDA(cudaEventRecord(pl->ev[3], stream)); pl->ev_pending = true; }

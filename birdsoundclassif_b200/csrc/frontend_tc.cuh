@@ -1,0 +1,33 @@
+// Tensor-core (tcgen05 / TMEM) front-end path, see frontend_tc.cu.
+#pragma once
+#include "common.cuh"
+
+namespace nbm {
+
+constexpr int GF = 64;      // frames per group / tile (one anchor per tile boundary)
+
+struct SegDesc {
+    long long pcm_start;   // per-channel sample index of the segment's first sample
+    long long n_samples;   // samples in this STFT chunk (prepare_dataset.py:236-237)
+    long long spec_off;    // float offset of S[0][first column of this segment]
+    int n_frames;
+    int row_stride;
+    int file;
+    int group0;            // index of the segment's first 64-frame group (tile)
+};
+
+struct TcPlan;
+
+// NBM_OK, or NBM_ERR_UNSUPPORTED when (n_fft, hop, n_bins) do not fit the tensor-core formulation
+int tc_plan_create(const nbm_frontend_params &p, TcPlan **out);
+void tc_plan_destroy(TcPlan *pl);
+// bytes of anchor scratch for `n_anchors` anchor frames (sum over segments of tiles + 1)
+size_t tc_anchor_bytes(const TcPlan *pl, long long n_anchors);
+// anchors per anchor task: the host builds one (segment, first anchor) task per this many anchors of a segment
+int tc_anchor_group();
+// anchors (tcgen05 GEMM over N/2 folded pairs) then slides (tcgen05 GEMM over hop/2 pairs + recurrence + Hann + dB)
+int tc_launch(const TcPlan *pl, const SegDesc *d_segs, int n_segs, int total_tiles, const int *d_task_seg,
+              const int *d_task_first, int n_tasks, const void *d_pcm, int dtype, int channels, float *d_spec,
+              unsigned int *d_minmax_enc, void *d_anchors, cudaStream_t stream);
+
+}  // namespace nbm

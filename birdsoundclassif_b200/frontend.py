@@ -70,6 +70,7 @@ class FrontendPlan:
             _lib.check(_lib.lib().nbm_frontend_plan_create(C.byref(self.params), C.byref(self._h)),
                        "nbm_frontend_plan_create")
         self._ws = None
+        self.impl = "tcgen05" if _lib.lib().nbm_frontend_impl(self._h) == 1 else "cuda-core"
 
     def close(self):
         if getattr(self, "_h", None):

@@ -63,6 +63,10 @@ typedef struct nbm_frontend_plan nbm_frontend_plan;
 int nbm_frontend_plan_create(const nbm_frontend_params *params, nbm_frontend_plan **out_plan);
 int nbm_frontend_plan_destroy(nbm_frontend_plan *plan);
 
+/* Which device implementation the plan uses: 1 = tensor cores (tcgen05/TMEM sliding DFT), 0 = CUDA cores
+ * (parameters outside the tensor-core formulation, or NBM_FRONTEND_IMPL=cuda-core in the environment). */
+int nbm_frontend_impl(const nbm_frontend_plan *plan);
+
 /* Pure host arithmetic (prepare_dataset.py:236,266): STFT columns (summed over the
  * <= stft_chunk-sample STFT chunks), detector windows, and the scratch bytes
  * nbm_frontend_run needs for a file of n_samples (per-channel samples). */
