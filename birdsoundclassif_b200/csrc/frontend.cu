@@ -272,6 +272,22 @@ __global__ void finalize_minmax_kernel(const unsigned int *enc, float *out, int 
 
 // Normalise by the file's min/max and cut detector windows (prepare_dataset.py:248-250, 255-294);
 // columns past the file's end mirror numpy's iterated 'reflect' pad of the partial window.
+// (x - s_min) / (s_max - s_min) as reciprocal + one FMA Newton step: correctly rounded for these operands
+// (in particular exactly 0 and 1 at the extremes) at a third of the cost of the IEEE divide sequence.
+__device__ __forceinline__ float norm_div(float num, float den, float inv) {
+    const float q = num * inv;
+    const float r = fmaf(-q, den, num);
+    return fmaf(r, inv, q);
+}
+
+__device__ __forceinline__ int reflect_src(int c, int width, int period) {
+    if (c < width) return c;
+    if (width == 1) return 0;
+    const int r = c % period;
+    return r < width ? r : period - r;
+}
+
+template <bool VEC4>
 __global__ void __launch_bounds__(256)
 tile_kernel(KParams P, const FileDesc *__restrict__ files, int n_files, const float *__restrict__ spec,
             const float *__restrict__ minmax, float *__restrict__ tiles) {
@@ -287,19 +303,37 @@ tile_kernel(KParams P, const FileDesc *__restrict__ files, int n_files, const fl
     const int width = (kt == fd.n_tiles - 1) ? fd.last_width : P.w_pix;
     const float smin = minmax[2 * lo_f], smax = minmax[2 * lo_f + 1];
     const float range = smax - smin;
+    const float inv = 1.0f / range;
     const int r0 = blockIdx.y * TILE_ROWS;
     const int r1 = min(r0 + TILE_ROWS, P.n_bins);
     const int period = 2 * (width - 1);
-    for (int c = threadIdx.x; c < P.w_pix; c += blockDim.x) {
-        int src = c;
-        if (c >= width) {
-            if (width == 1) src = 0;
-            else { int r = c % period; src = r < width ? r : period - r; }
+    const float *sbase = spec + fd.spec_off + start;
+    float *tbase = tiles + (tile * P.n_bins) * P.w_pix;
+    if (VEC4) {
+        for (int c = 4 * threadIdx.x; c < P.w_pix; c += 4 * blockDim.x) {
+            int src[4];
+            if (c + 3 < width) { src[0] = c; src[1] = c + 1; src[2] = c + 2; src[3] = c + 3; }
+            else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) src[e] = reflect_src(c + e, width, period);
+            }
+#pragma unroll 5
+            for (int r = r0; r < r1; ++r) {
+                const float *sp = sbase + (long long)r * fd.row_stride;
+                float4 o;
+                o.x = norm_div(sp[src[0]] - smin, range, inv);
+                o.y = norm_div(sp[src[1]] - smin, range, inv);
+                o.z = norm_div(sp[src[2]] - smin, range, inv);
+                o.w = norm_div(sp[src[3]] - smin, range, inv);
+                __stcs(reinterpret_cast<float4 *>(tbase + (long long)r * P.w_pix + c), o);
+            }
         }
-        const float *sp = spec + fd.spec_off + start + src;
-        float *tp = tiles + (tile * P.n_bins) * P.w_pix + c;
-        for (int r = r0; r < r1; ++r)
-            tp[(long long)r * P.w_pix] = __fdiv_rn(sp[(long long)r * fd.row_stride] - smin, range);
+    } else {
+        for (int c = threadIdx.x; c < P.w_pix; c += blockDim.x) {
+            const int src = reflect_src(c, width, period);
+            for (int r = r0; r < r1; ++r)
+                tbase[(long long)r * P.w_pix + c] = norm_div(sbase[(long long)r * fd.row_stride + src] - smin, range, inv);
+        }
     }
 }
 
@@ -629,7 +663,8 @@ extern "C" int nbm_frontend_run_batch(const nbm_frontend_plan *cpl, const void *
     finalize_minmax_kernel<<<(n_files + 255) / 256, 256, 0, stream>>>(d_enc, d_minmax, n_files);
     dim3 grid((unsigned)B.tiles, (unsigned)((p.n_bins + TILE_ROWS - 1) / TILE_ROWS));
     if (prof) NBM_CUDA(cudaEventRecord(pl->ev[2], stream));
-    tile_kernel<<<grid, 256, 0, stream>>>(pl->kp, d_files, n_files, d_spec, d_minmax, d_tiles);
+    if (p.w_pix % 4 == 0) tile_kernel<true><<<grid, 256, 0, stream>>>(pl->kp, d_files, n_files, d_spec, d_minmax, d_tiles);
+    else tile_kernel<false><<<grid, 256, 0, stream>>>(pl->kp, d_files, n_files, d_spec, d_minmax, d_tiles);
     if (prof) { NBM_CUDA(cudaEventRecord(pl->ev[3], stream)); pl->ev_pending = true; }
     NBM_CUDA(cudaGetLastError());
     return NBM_OK;

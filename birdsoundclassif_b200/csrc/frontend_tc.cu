@@ -126,6 +126,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// log2 of a normal positive float: one MUFU.LG2 (the C intrinsic adds a denormal fix-up we never need)
+__device__ __forceinline__ float fast_log2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // byte offset of element (row, k) in a K-major no-swizzle operand with K extent kext
 __host__ __device__ inline size_t umma_off(int row, int k, int kext) {
     return (size_t)(row >> 3) * (kext >> 3) * 128 + (size_t)(k >> 3) * 128 + (row & 7) * 16 + (k & 7) * 2;
@@ -306,13 +313,40 @@ anchor_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, const
 }
 
 // ------------------------------------------------------------------------- slide kernel --------
-// Persistent CTA: one 128-bin range, a strided sequence of 64-frame tiles.
+struct TileCtx {
+    SegDesc sd;
+    int t0;                 // first frame of the tile inside its segment
+    long long anchor_row;   // float2 index of this thread's anchor for its direction
+    long long s0;           // segment-relative sample index of buf[0]
+    int fast;               // 16-byte vector loads possible for this tile
+    unsigned full;          // bit e: prefetched vector e lies fully inside the segment
+};
+
+constexpr int PF = 6;       // prefetched 16-byte PCM vectors per thread (covers buf_len <= 8 * PF * TC_THREADS)
+
+// 8 PCM16 samples (one 16-byte vector) -> 8 floats in "int16 / 8" units, exact:
+// bits(2^20 + u/8) = 0x49800000 | u for u = x + 32768, so subtracting 2^20 + 4096 leaves x / 8.
+__device__ __forceinline__ void cvt8_pcm16(const int4 raw, float4 &lo, float4 &hi) {
+    const uint32_t w[4] = {(uint32_t)raw.x ^ 0x80008000u, (uint32_t)raw.y ^ 0x80008000u,
+                           (uint32_t)raw.z ^ 0x80008000u, (uint32_t)raw.w ^ 0x80008000u};
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f[2 * i] = __uint_as_float(0x49800000u | (w[i] & 0xffffu)) - 1052672.0f;
+        f[2 * i + 1] = __uint_as_float(0x49800000u | (w[i] >> 16)) - 1052672.0f;
+    }
+    lo = make_float4(f[0], f[1], f[2], f[3]);
+    hi = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+// Persistent CTA: one 128-bin range, a strided sequence of 64-frame tiles.  The MMAs of tile i run while
+// the CTA does the epilogue of tile i-1 (two TMEM accumulator buffers, one shared-memory B buffer).
 __global__ void __launch_bounds__(TC_THREADS, 1)
 slide_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int total_tiles,
-                const void *__restrict__ pcm, int dtype, int channels, const float2 *__restrict__ anchors,
-                float *__restrict__ spec, unsigned int *__restrict__ minmax_enc) {
+                const void *__restrict__ pcm, int dtype, int channels, int vec_ok,
+                const float2 *__restrict__ anchors, float *__restrict__ spec, unsigned int *__restrict__ minmax_enc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar[2];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int range = blockIdx.x % P.n_ranges;
@@ -325,7 +359,7 @@ slide_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int to
     float *buf = reinterpret_cast<float *>(sB + 6 * b_mat);     // samples (scaled), PADF + off front padding
     float2 *stage = reinterpret_cast<float2 *>(buf + P.buf_len);    // [128][STAGE_LD]
 
-    // ---- one-time: twiddles resident, B padding zeroed, TMEM, barrier ---------------------------
+    // ---- one-time: twiddles resident, B padding zeroed, TMEM, barriers --------------------------
     {
         const uint4 *ga = reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(P.a_slide) + (size_t)range * 4 * a_mat);
         uint4 *da = reinterpret_cast<uint4 *>(sA);
@@ -333,8 +367,8 @@ slide_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int to
         uint4 *db = reinterpret_cast<uint4 *>(sB);
         for (int i = tid; i < (int)(6 * b_mat / 16); i += TC_THREADS) db[i] = make_uint4(0, 0, 0, 0);
     }
-    if (warp == 0) tmem_alloc(&tmem_base_s, 128);
-    if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -347,157 +381,228 @@ slide_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int to
     const int row = quarter * 32 + lane;
     const float2 cf = P.cf[range * 128 + row];
     const float2 gg = dir == 0 ? P.gf[range * 128 + row] : P.gb[range * 128 + row];
-    const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
     const int njg = (P.npH + 7) / 8;
     const int half_hop = hop / 2;
-    uint32_t phase = 0;
+    const int n_iters = q0 < total_tiles ? (total_tiles - q0 + qstride - 1) / qstride : 0;
 
-    for (int tile = q0; tile < total_tiles; tile += qstride) {
-        const int seg_idx = find_seg(segs, n_segs, tile);
-        const SegDesc sd = segs[seg_idx];
-        const int lt = tile - sd.group0;                    // tile index inside the segment
-        const int t0 = lt * GF;
-        const long long anchor_row = ((long long)sd.group0 + seg_idx + lt) * (P.n_ranges * 128) + range * 128 + row;
-        const float2 anc = __ldg(anchors + anchor_row + (dir ? (long long)P.n_ranges * 128 : 0));
-
-        // ---- samples of the tile into shared memory (zero outside the segment) -----------------
-        const long long s0 = (long long)t0 * hop - N / 2 - (PADF + P.off);
-        for (int i = tid; i < P.buf_len; i += TC_THREADS) {
-            const long long s = s0 + i;
-            buf[i] = (s >= 0 && s < sd.n_samples) ? load_scaled(pcm, dtype, channels, sd.pcm_start + s) : 0.f;
-        }
-        __syncthreads();
-        // ---- B operand: folded differences, fp16 hi / lo / hi*2^-11 ------------------------------
-        for (int u = tid; u < GF * njg; u += TC_THREADS) {
-            const int n = u % GF, jg = u / GF;
-            const int base = PADF + P.off + n * hop;
-            const float4 *nh = reinterpret_cast<const float4 *>(buf + base + N + half_hop + 8 * jg);
-            const float4 *oh = reinterpret_cast<const float4 *>(buf + base + half_hop + 8 * jg);
-            const float4 *nl = reinterpret_cast<const float4 *>(buf + base + N + half_hop - 8 - 8 * jg);
-            const float4 *ol = reinterpret_cast<const float4 *>(buf + base + half_hop - 8 - 8 * jg);
-            const float4 a0 = nh[0], a1 = nh[1], b0 = oh[0], b1 = oh[1];
-            const float4 c0 = nl[0], c1 = nl[1], e0 = ol[0], e1 = ol[1];
-            const float dh[8] = {a0.x - b0.x, a0.y - b0.y, a0.z - b0.z, a0.w - b0.w,
-                                 a1.x - b1.x, a1.y - b1.y, a1.z - b1.z, a1.w - b1.w};
-            // lo pair of jj sits at position 7 - jj of the descending vector
-            const float dl[8] = {c1.w - e1.w, c1.z - e1.z, c1.y - e1.y, c1.x - e1.x,
-                                 c0.w - e0.w, c0.z - e0.z, c0.y - e0.y, c0.x - e0.x};
-            float ep[8], em[8];
+    int seg_idx = 0;
+    TileCtx cur{}, prev{}, nxt{};
+    int4 pre[PF];
+    const short *p16 = reinterpret_cast<const short *>(pcm);
+    const int nv = P.buf_len / 8;
+    const bool can_prefetch = vec_ok && nv <= PF * TC_THREADS;
+    // tile context + issue of the 16-byte PCM loads (they land while the previous tile's epilogue runs)
+    auto open_tile = [&](int it_) {
+        const int tile = q0 + it_ * qstride;
+        while (seg_idx + 1 < n_segs && segs[seg_idx + 1].group0 <= tile) ++seg_idx;
+        nxt.sd = segs[seg_idx];
+        const int lt = tile - nxt.sd.group0;
+        nxt.t0 = lt * GF;
+        nxt.anchor_row = ((long long)nxt.sd.group0 + seg_idx + lt + dir) * (P.n_ranges * 128) + range * 128 + row;
+        nxt.s0 = (long long)nxt.t0 * hop - N / 2 - (PADF + P.off);
+        const long long g0 = nxt.sd.pcm_start + nxt.s0;
+        nxt.fast = can_prefetch && (g0 & 7) == 0;
+        nxt.full = 0u;
+        if (nxt.fast) {
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-                const bool ok = 8 * jg + jj < P.npH;
-                ep[jj] = ok ? dh[jj] + dl[jj] : 0.f;
-                em[jj] = ok ? dh[jj] - dl[jj] : 0.f;
-            }
-            uint4 h, l, hs;
-            const size_t o = umma_off(n, jg * 8, KP);
-            split8(ep, h, l, hs);
-            *reinterpret_cast<uint4 *>(sB + 0 * b_mat + o) = h;
-            *reinterpret_cast<uint4 *>(sB + 1 * b_mat + o) = l;
-            *reinterpret_cast<uint4 *>(sB + 2 * b_mat + o) = hs;
-            split8(em, h, l, hs);
-            *reinterpret_cast<uint4 *>(sB + 3 * b_mat + o) = h;
-            *reinterpret_cast<uint4 *>(sB + 4 * b_mat + o) = l;
-            *reinterpret_cast<uint4 *>(sB + 5 * b_mat + o) = hs;
-        }
-        fence_async_smem();
-        tc_fence_before();          // previous tile's tcgen05.ld are ordered before the barrier
-        __syncthreads();
-        // ---- MMAs: cos accumulator cols [0,64), sin accumulator cols [64,128) --------------------
-        if (tid == 0) {
-            tc_fence_after();
-            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-            for (int kk = 0; kk < nk; ++kk) {
-                const uint32_t ko = kk * 256, acc = kk > 0 ? 1u : 0u;
-                const uint64_t ach = make_desc(a0 + 0 * (uint32_t)a_mat + ko, 128, SBO), acl = make_desc(a0 + 1 * (uint32_t)a_mat + ko, 128, SBO);
-                const uint64_t ash = make_desc(a0 + 2 * (uint32_t)a_mat + ko, 128, SBO), asl = make_desc(a0 + 3 * (uint32_t)a_mat + ko, 128, SBO);
-                const uint64_t bph = make_desc(b0 + 0 * (uint32_t)b_mat + ko, 128, SBO), bpl = make_desc(b0 + 1 * (uint32_t)b_mat + ko, 128, SBO);
-                const uint64_t bps = make_desc(b0 + 2 * (uint32_t)b_mat + ko, 128, SBO), bmh = make_desc(b0 + 3 * (uint32_t)b_mat + ko, 128, SBO);
-                const uint64_t bml = make_desc(b0 + 4 * (uint32_t)b_mat + ko, 128, SBO), bms = make_desc(b0 + 5 * (uint32_t)b_mat + ko, 128, SBO);
-                umma_f16(tmem_base, ach, bph, idesc, acc);
-                umma_f16(tmem_base, ach, bpl, idesc, 1u);
-                umma_f16(tmem_base, acl, bps, idesc, 1u);
-                umma_f16(tmem_base + GF, ash, bmh, idesc, acc);
-                umma_f16(tmem_base + GF, ash, bml, idesc, 1u);
-                umma_f16(tmem_base + GF, asl, bms, idesc, 1u);
-            }
-            umma_commit(&bar);
-        }
-        mbar_wait(&bar, phase);
-        phase ^= 1u;
-        tc_fence_after();
-
-        // ---- two half-phases of 32 frames: forward warps 16 frames up, backward warps 16 down ----
-        float Rr = anc.x, Ri = anc.y;
-        float vmin = INFINITY, vmax = -INFINITY;
-        float *spec_seg = spec + sd.spec_off;
-        for (int hp = 0; hp < 2; ++hp) {
-            float gc[16], gs[16];
-            if (dir == 0) {
-                // frames t0+16hp .. t0+16hp+15 ; G columns: hp=0 -> 0..14 (frame 0 is the anchor), hp=1 -> 15..30
-                const int c0 = hp == 0 ? 0 : 15;
-                tmem_ld16(tl + c0, gc);
-                tmem_ld16(tl + GF + c0, gs);
-                if (hp == 0) stage[row * STAGE_LD + 0] = make_float2(Rr, Ri);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    if (hp == 0 && i == 15) break;
-                    const float nr = cf.x * Rr - cf.y * Ri + gg.x * gc[i] + gg.y * gs[i];
-                    const float ni = cf.x * Ri + cf.y * Rr - gg.x * gs[i] + gg.y * gc[i];
-                    Rr = nr; Ri = ni;
-                    stage[row * STAGE_LD + (hp == 0 ? i + 1 : i)] = make_float2(Rr, Ri);
-                }
-            } else {
-                // frames t0+63-16hp down to t0+48-16hp ; G columns 63-16hp .. 48-16hp
-                const int c0 = 48 - 16 * hp;
-                tmem_ld16(tl + c0, gc);
-                tmem_ld16(tl + GF + c0, gs);
-#pragma unroll
-                for (int i = 15; i >= 0; --i) {
-                    const float nr = cf.x * Rr + cf.y * Ri - gg.x * gc[i] + gg.y * gs[i];
-                    const float ni = cf.x * Ri - cf.y * Rr + gg.x * gs[i] + gg.y * gc[i];
-                    Rr = nr; Ri = ni;
-                    stage[row * STAGE_LD + 16 + i] = make_float2(Rr, Ri);
+            for (int e = 0; e < PF; ++e) {
+                const int v = tid + e * TC_THREADS;
+                const long long sv = nxt.s0 + 8 * v;
+                if (v < nv && sv >= 0 && sv + 8 <= nxt.sd.n_samples) {
+                    pre[e] = __ldg(reinterpret_cast<const int4 *>(p16 + g0 + 8 * v));
+                    nxt.full |= 1u << e;
                 }
             }
-            __syncthreads();
-            // ---- Hann + dB + store: lane = frame column, warp = 16 bin rows ------------------------
-            {
-                const int fl = lane < 16 ? 16 * hp + lane : 48 - 16 * hp + (lane - 16);     // frame inside the tile
-                const bool fok = t0 + fl < sd.n_frames;
-                const int r_lo = 1 + 16 * warp, r_hi = min(r_lo + 16, 127);
-                float2 prev = stage[(r_lo - 1) * STAGE_LD + lane], cur = stage[r_lo * STAGE_LD + lane];
-                for (int r = r_lo; r < r_hi; ++r) {
-                    const float2 nxt = stage[(r + 1) * STAGE_LD + lane];
-                    const float xr = 0.5f * cur.x - 0.25f * (prev.x + nxt.x);
-                    const float xi = 0.5f * cur.y - 0.25f * (prev.y + nxt.y);
-                    const float pw = fmaxf(fmaf(xr, xr, xi * xi), P.min_level_sq);
-                    const float db = 3.0102999566398120f * __log2f(pw);
-                    const int ob = range * BINS_PER_RANGE + r - 1;
-                    if (fok && ob < P.n_bins) {
-                        spec_seg[(long long)ob * sd.row_stride + t0 + fl] = db;
-                        vmin = fminf(vmin, db);
-                        vmax = fmaxf(vmax, db);
-                    }
-                    prev = cur; cur = nxt;
-                }
-            }
-            __syncthreads();
         }
-        // ---- per-file min / max (one atomic pair per warp per tile) ------------------------------
+    };
+    float vmin = INFINITY, vmax = -INFINITY;
+    int mm_file = -1;
+    auto flush_minmax = [&]() {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
             vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
         }
-        if (lane == 0 && vmin <= vmax) {
-            atomicMin(minmax_enc + 2 * sd.file, float_to_ordered(vmin));
-            atomicMax(minmax_enc + 2 * sd.file + 1, float_to_ordered(vmax));
+        if (lane == 0 && mm_file >= 0 && vmin <= vmax) {
+            atomicMin(minmax_enc + 2 * mm_file, float_to_ordered(vmin));
+            atomicMax(minmax_enc + 2 * mm_file + 1, float_to_ordered(vmax));
         }
+        vmin = INFINITY; vmax = -INFINITY;
+    };
+
+    if (n_iters > 0) open_tile(0);
+    for (int it = 0; it <= n_iters; ++it) {
+        if (it < n_iters) {
+            cur = nxt;
+            // the MMAs of tile it-1 (issued one iteration ago) must have finished reading sB
+            if (it >= 1) mbar_wait(&bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
+
+            // ---- samples of the tile into shared memory (zero outside the segment) -------------
+            if (cur.fast) {
+                const long long g0 = cur.sd.pcm_start + cur.s0;
+#pragma unroll
+                for (int e = 0; e < PF; ++e) {
+                    const int v = tid + e * TC_THREADS;
+                    if (v < nv) {
+                        float4 lo, hi;
+                        if (cur.full & (1u << e)) {
+                            cvt8_pcm16(pre[e], lo, hi);
+                        } else {
+                            const long long sv = cur.s0 + 8 * v;
+                            float f[8];
+#pragma unroll
+                            for (int el = 0; el < 8; ++el)
+                                f[el] = (sv + el >= 0 && sv + el < cur.sd.n_samples) ? (float)__ldg(p16 + g0 + 8 * v + el) * 0.125f : 0.f;
+                            lo = make_float4(f[0], f[1], f[2], f[3]);
+                            hi = make_float4(f[4], f[5], f[6], f[7]);
+                        }
+                        reinterpret_cast<float4 *>(buf)[2 * v] = lo;
+                        reinterpret_cast<float4 *>(buf)[2 * v + 1] = hi;
+                    }
+                }
+            } else {
+                for (int i = tid; i < P.buf_len; i += TC_THREADS) {
+                    const long long sx = cur.s0 + i;
+                    buf[i] = (sx >= 0 && sx < cur.sd.n_samples) ? load_scaled(pcm, dtype, channels, cur.sd.pcm_start + sx) : 0.f;
+                }
+            }
+            __syncthreads();
+            // ---- B operand: folded differences, fp16 hi / lo / hi*2^-11 --------------------------
+            for (int u = tid; u < GF * njg; u += TC_THREADS) {
+                const int n = u % GF, jg = u / GF;
+                const int base = PADF + P.off + n * hop;
+                const float4 *nh = reinterpret_cast<const float4 *>(buf + base + N + half_hop + 8 * jg);
+                const float4 *oh = reinterpret_cast<const float4 *>(buf + base + half_hop + 8 * jg);
+                const float4 *nl = reinterpret_cast<const float4 *>(buf + base + N + half_hop - 8 - 8 * jg);
+                const float4 *ol = reinterpret_cast<const float4 *>(buf + base + half_hop - 8 - 8 * jg);
+                const float4 a0 = nh[0], a1 = nh[1], b0 = oh[0], b1 = oh[1];
+                const float4 c0 = nl[0], c1 = nl[1], e0 = ol[0], e1 = ol[1];
+                const float dh[8] = {a0.x - b0.x, a0.y - b0.y, a0.z - b0.z, a0.w - b0.w,
+                                     a1.x - b1.x, a1.y - b1.y, a1.z - b1.z, a1.w - b1.w};
+                // the lo sample of pair jj sits at position 7 - jj of the ascending vector
+                const float dl[8] = {c1.w - e1.w, c1.z - e1.z, c1.y - e1.y, c1.x - e1.x,
+                                     c0.w - e0.w, c0.z - e0.z, c0.y - e0.y, c0.x - e0.x};
+                float ep[8], em[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    const bool ok = 8 * jg + jj < P.npH;
+                    ep[jj] = ok ? dh[jj] + dl[jj] : 0.f;
+                    em[jj] = ok ? dh[jj] - dl[jj] : 0.f;
+                }
+                uint4 h, l, hs;
+                const size_t o = umma_off(n, jg * 8, KP);
+                split8(ep, h, l, hs);
+                *reinterpret_cast<uint4 *>(sB + 0 * b_mat + o) = h;
+                *reinterpret_cast<uint4 *>(sB + 1 * b_mat + o) = l;
+                *reinterpret_cast<uint4 *>(sB + 2 * b_mat + o) = hs;
+                split8(em, h, l, hs);
+                *reinterpret_cast<uint4 *>(sB + 3 * b_mat + o) = h;
+                *reinterpret_cast<uint4 *>(sB + 4 * b_mat + o) = l;
+                *reinterpret_cast<uint4 *>(sB + 5 * b_mat + o) = hs;
+            }
+            fence_async_smem();
+            tc_fence_before();          // the epilogue's tcgen05.ld of two tiles ago precede this barrier
+            __syncthreads();
+            // ---- MMAs into TMEM buffer it&1: cos cols [0,64), sin cols [64,128) -------------------
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t d0 = tmem_base + (uint32_t)(it & 1) * 128;
+                const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+                for (int kk = 0; kk < nk; ++kk) {
+                    const uint32_t ko = kk * 256, acc = kk > 0 ? 1u : 0u;
+                    const uint64_t ach = make_desc(a0 + 0 * (uint32_t)a_mat + ko, 128, SBO), acl = make_desc(a0 + 1 * (uint32_t)a_mat + ko, 128, SBO);
+                    const uint64_t ash = make_desc(a0 + 2 * (uint32_t)a_mat + ko, 128, SBO), asl = make_desc(a0 + 3 * (uint32_t)a_mat + ko, 128, SBO);
+                    const uint64_t bph = make_desc(b0 + 0 * (uint32_t)b_mat + ko, 128, SBO), bpl = make_desc(b0 + 1 * (uint32_t)b_mat + ko, 128, SBO);
+                    const uint64_t bps = make_desc(b0 + 2 * (uint32_t)b_mat + ko, 128, SBO), bmh = make_desc(b0 + 3 * (uint32_t)b_mat + ko, 128, SBO);
+                    const uint64_t bml = make_desc(b0 + 4 * (uint32_t)b_mat + ko, 128, SBO), bms = make_desc(b0 + 5 * (uint32_t)b_mat + ko, 128, SBO);
+                    umma_f16(d0, ach, bph, idesc, acc);
+                    umma_f16(d0, ach, bpl, idesc, 1u);
+                    umma_f16(d0, acl, bps, idesc, 1u);
+                    umma_f16(d0 + GF, ash, bmh, idesc, acc);
+                    umma_f16(d0 + GF, ash, bml, idesc, 1u);
+                    umma_f16(d0 + GF, asl, bms, idesc, 1u);
+                }
+                umma_commit(&bar[it & 1]);
+            }
+            if (it + 1 < n_iters) open_tile(it + 1);
+        }
+        if (it >= 1) {
+            // ================= epilogue of tile it-1 (its MMAs were issued one iteration ago) =======
+            const int pb = (it - 1) & 1;
+            const SegDesc &sd = prev.sd;
+            const int t0 = prev.t0;
+            if (sd.file != mm_file) { flush_minmax(); mm_file = sd.file; }
+            const float2 anc = __ldg(anchors + prev.anchor_row);
+            mbar_wait(&bar[pb], ((it - 1) >> 1) & 1);
+            tc_fence_after();
+            const uint32_t tl = tmem_base + (uint32_t)pb * 128 + lane_sel;
+            float Rr = anc.x, Ri = anc.y;
+            float *spec_seg = spec + sd.spec_off;
+            for (int hp = 0; hp < 2; ++hp) {
+                float gc[16], gs[16];
+                if (dir == 0) {
+                    // frames 16hp .. 16hp+15 ; G columns: hp=0 -> 0..14 (frame 0 is the anchor), hp=1 -> 15..30
+                    const int c0 = hp == 0 ? 0 : 15;
+                    tmem_ld16(tl + c0, gc);
+                    tmem_ld16(tl + GF + c0, gs);
+                    if (hp == 0) stage[row * STAGE_LD + 0] = make_float2(Rr, Ri);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        if (hp == 0 && i == 15) break;
+                        const float nr = cf.x * Rr - cf.y * Ri + gg.x * gc[i] + gg.y * gs[i];
+                        const float ni = cf.x * Ri + cf.y * Rr - gg.x * gs[i] + gg.y * gc[i];
+                        Rr = nr; Ri = ni;
+                        stage[row * STAGE_LD + (hp == 0 ? i + 1 : i)] = make_float2(Rr, Ri);
+                    }
+                } else {
+                    // frames 63-16hp down to 48-16hp ; G columns 63-16hp .. 48-16hp
+                    const int c0 = 48 - 16 * hp;
+                    tmem_ld16(tl + c0, gc);
+                    tmem_ld16(tl + GF + c0, gs);
+#pragma unroll
+                    for (int i = 15; i >= 0; --i) {
+                        const float nr = cf.x * Rr + cf.y * Ri - gg.x * gc[i] + gg.y * gs[i];
+                        const float ni = cf.x * Ri - cf.y * Rr + gg.x * gs[i] + gg.y * gc[i];
+                        Rr = nr; Ri = ni;
+                        stage[row * STAGE_LD + 16 + i] = make_float2(Rr, Ri);
+                    }
+                }
+                __syncthreads();
+                // ---- Hann + dB + store: lane = frame column, warp = 16 bin rows --------------------
+                {
+                    const int fl = lane < 16 ? 16 * hp + lane : 48 - 16 * hp + (lane - 16);     // frame inside the tile
+                    const int r_lo = 1 + 16 * warp;
+                    // rows r < ob_lim are inside the band (only the last range is cut short)
+                    const int r_hi = min(min(r_lo + 16, 127), P.n_bins - (range * BINS_PER_RANGE - 1));
+                    if (t0 + fl < sd.n_frames && r_lo < r_hi) {
+                        float2 pv = stage[(r_lo - 1) * STAGE_LD + lane], cu = stage[r_lo * STAGE_LD + lane];
+                        float *out = spec_seg + (long long)(range * BINS_PER_RANGE + r_lo - 1) * sd.row_stride + t0 + fl;
+#pragma unroll 4
+                        for (int r = r_lo; r < r_hi; ++r) {
+                            const float2 nx = stage[(r + 1) * STAGE_LD + lane];
+                            // 4 X = 2 R[k] - (R[k-1] + R[k+1]);  10 log10(|X|^2) = 10 log10(|4X|^2) - 10 log10(16)
+                            const float xr = fmaf(2.0f, cu.x, -(pv.x + nx.x));
+                            const float xi = fmaf(2.0f, cu.y, -(pv.y + nx.y));
+                            const float pw = fmaxf(fmaf(xr, xr, xi * xi), 16.0f * P.min_level_sq);
+                            const float db = fmaf(fast_log2(pw), 3.0102999566398120f, -12.041199826559248f);
+                            *out = db;
+                            vmin = fminf(vmin, db);
+                            vmax = fmaxf(vmax, db);
+                            out += sd.row_stride;
+                            pv = cu; cu = nx;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        prev = cur;
     }
+    flush_minmax();
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, 128);
+    if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
 }  // namespace nbm
@@ -528,7 +633,7 @@ int nbm::tc_plan_create(const nbm_frontend_params &p, TcPlan **out) {
     k.npH = npH; k.KP = KP; k.nk = KP / 16;
     k.npN = N / 2; k.n_stages = (k.npN + KS * 16 - 1) / (KS * 16);
     k.off = (4 - (npH % 4)) % 4;
-    k.buf_len = ((PADF + k.off + GF * hop + N + 16 + 3) / 4) * 4;   // +16: masked tail pairs read past the last block
+    k.buf_len = ((PADF + k.off + GF * hop + N + 16 + 7) / 8) * 8;   // +16: masked tail pairs read past the last block
     k.min_level_sq = (float)(p.min_level * p.min_level);
     const int R = k.n_ranges, N2 = 2 * N;
 
@@ -631,8 +736,10 @@ int nbm::tc_launch(const TcPlan *pl, const SegDesc *d_segs, int n_segs, int tota
     anchor_tc_kernel<<<ga, TC_THREADS, pl->smem_anchor, stream>>>(k, d_segs, n_segs, d_task_seg, d_task_first, d_pcm,
                                                                   dtype, channels, anchors);
     const int grid = std::min(pl->grid_slide, std::max(1, total_tiles) * k.n_ranges);
+    // 16-byte vector loads of PCM16 need a mono int16 stream on a 16-byte aligned base
+    const int vec_ok = (dtype == NBM_PCM_INT16 && channels == 1 && (reinterpret_cast<uintptr_t>(d_pcm) & 15) == 0) ? 1 : 0;
     slide_tc_kernel<<<(grid / k.n_ranges) * k.n_ranges, TC_THREADS, pl->smem_slide, stream>>>(
-        k, d_segs, n_segs, total_tiles, d_pcm, dtype, channels, anchors, d_spec, d_minmax_enc);
+        k, d_segs, n_segs, total_tiles, d_pcm, dtype, channels, vec_ok, anchors, d_spec, d_minmax_enc);
     NBM_CUDA(cudaGetLastError());
     return NBM_OK;
 }

@@ -7,7 +7,7 @@ magnitude (a few 1e-7 of the frame's RMS bin magnitude).  In dB that is far belo
 image range everywhere except in deep spectral nulls (|X| < ~1e-3 of the RMS), which white-noise
 backgrounds produce for about one pixel per million.  On the normalised [0,1] tiles we require
     |gpu - oracle| <= 1e-4   (= 1e-4 (s_max - s_min) dB, about 0.01 dB) for >= 99.9998 % of pixels,
-    |gpu - oracle| <= 5e-3   for every pixel (the deep-null outliers),  rms error <= 2e-5,
+    |gpu - oracle| <= 5e-3   for every pixel (the deep-null outliers),  rms error <= 5e-5,
     s_max within 1e-3 dB and s_min (itself a deepest-null pixel) within 3e-2 dB.
 """
 import numpy as np
@@ -22,7 +22,7 @@ pytestmark = pytest.mark.gpu
 TOL_TILE = 1e-4          # per pixel, all but TOL_OUTLIER_FRAC of them
 TOL_OUTLIER_FRAC = 2e-6
 TOL_TILE_WORST = 5e-3    # every pixel
-TOL_RMS = 2e-5
+TOL_RMS = 5e-5         # dominated by the common offset |d s_min| / range of the deepest-null pixel
 TOL_SMIN_DB = 3e-2
 TOL_SMAX_DB = 1e-3
 
