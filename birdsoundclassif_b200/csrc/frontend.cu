@@ -36,6 +36,8 @@ struct FileDesc {
     int n_tiles;
     int total_frames;
     int last_width;        // valid columns of the last tile (rest is reflect padding)
+    int group0, n_groups;  // the file's 64-frame groups (contiguous)
+    int seg0, n_segs;      // the file's STFT chunks (contiguous)
 };
 
 struct KParams {
@@ -67,7 +69,7 @@ __device__ __forceinline__ void fold_idx(int L, int j, int &hi, int &lo) {
 
 __global__ void __launch_bounds__(512, 1)
 stft_db_kernel(KParams P, const SegDesc *__restrict__ segs, int n_segs, const void *__restrict__ pcm,
-               int dtype, int channels, float *__restrict__ spec, unsigned int *__restrict__ minmax_enc) {
+               int dtype, int channels, float *__restrict__ spec, float2 *__restrict__ tile_mm) {
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
 
@@ -253,21 +255,118 @@ stft_db_kernel(KParams P, const SegDesc *__restrict__ segs, int n_segs, const vo
             vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
             vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
         }
-        if (lane == 0) {
-            atomicMin(minmax_enc + 2 * sd.file, float_to_ordered(vmin));
-            atomicMax(minmax_enc + 2 * sd.file + 1, float_to_ordered(vmax));
-        }
+        if (lane == 0) tile_mm[blockIdx.x] = make_float2(vmin, vmax);     // one slot per group on this path
     }
 }
 
-__global__ void init_minmax_kernel(unsigned int *enc, int n_files) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_files) { enc[2 * i] = 0xffffffffu; enc[2 * i + 1] = 0u; }
+// ---------------------------------------------------------------------------------------------
+// Whole-file min / max (prepare_dataset.py:248-250) from the per-(group, slot) partials, with the
+// minimum made exact.  s_min is by construction the deepest spectral null of the file, where any
+// float32 transform has its largest relative error, and it shifts EVERY normalised pixel.  So the
+// few pixels within `margin_db` of the float32 minimum are recomputed as the reference computes
+// them (float64 windowed DFT -> complex64 -> float32 |.| -> float64 log10), patched in the dB band,
+// and the minimum is taken over the patched values.  One block per file.
+struct RefineParams {
+    int N, hop, low_idx, n_bins, n_slots, bins_per_slot;
+    double min_level;
+    float margin_db;
+};
+constexpr int REFINE_CAP = 64;
+
+__device__ __forceinline__ double block_sum_256(double v, double *red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();                                 // red[] free again
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w];
+    return t;
 }
 
-__global__ void finalize_minmax_kernel(const unsigned int *enc, float *out, int n_files) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_files) { out[2 * i] = ordered_to_float(enc[2 * i]); out[2 * i + 1] = ordered_to_float(enc[2 * i + 1]); }
+__global__ void __launch_bounds__(256)
+refine_minmax_kernel(RefineParams R, const SegDesc *__restrict__ segs, const FileDesc *__restrict__ files,
+                     const float2 *__restrict__ tile_mm, float *__restrict__ spec, const void *__restrict__ pcm,
+                     int dtype, int channels, float *__restrict__ out) {
+    __shared__ float s_red[16];
+    __shared__ double d_red[16];
+    __shared__ int c_seg[REFINE_CAP], c_bin[REFINE_CAP], c_frame[REFINE_CAP];
+    __shared__ int n_cand;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const FileDesc fd = files[blockIdx.x];
+    const int n_ent = fd.n_groups * R.n_slots;
+    const float2 *mm = tile_mm + (size_t)fd.group0 * R.n_slots;
+
+    float vmin = INFINITY, vmax = -INFINITY;
+    for (int i = tid; i < n_ent; i += 256) {
+        const float2 v = mm[i];
+        vmin = fminf(vmin, v.x);
+        vmax = fmaxf(vmax, v.y);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    }
+    if (lane == 0) { s_red[warp] = vmin; s_red[8 + warp] = vmax; }
+    if (tid == 0) n_cand = 0;
+    __syncthreads();
+    vmin = s_red[0]; vmax = s_red[8];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) { vmin = fminf(vmin, s_red[w]); vmax = fmaxf(vmax, s_red[8 + w]); }
+    const float thr = vmin + R.margin_db;
+
+    // candidates: pixels within the margin of the float32 minimum (only groups whose partial says so are read)
+    for (int i = 0; i < n_ent; ++i) {
+        if (!(mm[i].x <= thr)) continue;                       // block-uniform
+        const int g = fd.group0 + i / R.n_slots, slot = i % R.n_slots;
+        int si = fd.seg0 + fd.n_segs - 1;
+        while (si > fd.seg0 && segs[si].group0 > g) --si;
+        const SegDesc sd = segs[si];
+        const int t0 = (g - sd.group0) * GF, nf = min(GF, sd.n_frames - t0);
+        const int b0 = slot * R.bins_per_slot, nb = min(R.bins_per_slot, R.n_bins - b0);
+        for (int p = tid; p < nb * nf; p += 256) {
+            const int b = b0 + p / nf, t = t0 + p % nf;
+            if (spec[sd.spec_off + (long long)b * sd.row_stride + t] <= thr) {
+                const int at = atomicAdd(&n_cand, 1);
+                if (at < REFINE_CAP) { c_seg[at] = si; c_bin[at] = b; c_frame[at] = t; }
+            }
+        }
+    }
+    __syncthreads();
+    const int nc = min(n_cand, REFINE_CAP);
+    double best = INFINITY;
+    for (int c = 0; c < nc; ++c) {
+        const SegDesc sd = segs[c_seg[c]];
+        const long long k = R.low_idx + c_bin[c];
+        const long long s0 = (long long)c_frame[c] * R.hop - R.N / 2;
+        double ar = 0.0, ai = 0.0;
+        for (int n = tid; n < R.N; n += 256) {
+            const long long s = s0 + n;
+            if (s < 0 || s >= sd.n_samples) continue;           // centre padding, pad_mode='constant'
+            const double x = (double)load_sample(pcm, dtype, channels, sd.pcm_start + s);
+            const double w = 0.5 - 0.5 * cospi(2.0 * (double)n / (double)R.N);     // periodic Hann
+            double sn, cs;
+            sincospi(2.0 * (double)((k * n) % R.N) / (double)R.N, &sn, &cs);
+            ar += x * w * cs;
+            ai -= x * w * sn;
+        }
+        ar = block_sum_256(ar, d_red);
+        ai = block_sum_256(ai, d_red);
+        const float re = (float)ar, im = (float)ai;                                 // stored complex64
+        const float mag = (float)hypot((double)re, (double)im);                    // np.abs -> float32
+        const double db = 20.0 * log10(fmax(R.min_level, (double)mag));
+        best = fmin(best, db);
+        if (tid == 0) spec[sd.spec_off + (long long)c_bin[c] * sd.row_stride + c_frame[c]] = (float)db;
+    }
+    if (tid == 0) {
+        // every pixel within the margin was recomputed unless the list overflowed (e.g. digital silence)
+        float smin = vmin;
+        if (nc > 0) smin = n_cand > REFINE_CAP ? fminf(vmin, (float)best) : (float)best;
+        out[2 * blockIdx.x] = smin;
+        out[2 * blockIdx.x + 1] = vmax;
+    }
 }
 
 // Normalise by the file's min/max and cut detector windows (prepare_dataset.py:248-250, 255-294);
@@ -277,7 +376,8 @@ __global__ void finalize_minmax_kernel(const unsigned int *enc, float *out, int 
 __device__ __forceinline__ float norm_div(float num, float den, float inv) {
     const float q = num * inv;
     const float r = fmaf(-q, den, num);
-    return fmaf(r, inv, q);
+    // the reference's image lies in [0, 1]; only unrefined floor pixels of digital silence can leave it by an ulp
+    return fminf(fmaxf(fmaf(r, inv, q), 0.0f), 1.0f);
 }
 
 __device__ __forceinline__ int reflect_src(int c, int width, int period) {
@@ -392,6 +492,8 @@ int build_layout(const nbm_frontend_plan *pl, const int64_t *sizes, const int64_
         FileDesc &fd = B.files[f];
         fd.spec_off = (long long)B.spec_floats;
         fd.tile0 = B.tiles;
+        fd.group0 = B.groups;
+        fd.seg0 = (int)B.segs.size();
         long long T = 0, col = 0, s = offsets ? offsets[f] : 0;
         const int64_t n_chunks = n / p.stft_chunk + 1;              // range(int(len/max_l)+1)
         const size_t seg_first = B.segs.size();
@@ -435,6 +537,8 @@ int build_layout(const nbm_frontend_plan *pl, const int64_t *sizes, const int64_
             }
             last_width = (int)(edge + B.segs[i].n_frames - start);
         }
+        fd.n_groups = B.groups - fd.group0;
+        fd.n_segs = (int)B.segs.size() - fd.seg0;
         fd.row_stride = (int)stride;
         fd.n_tiles = (int)nt;
         fd.total_frames = (int)T;
@@ -450,7 +554,7 @@ int build_layout(const nbm_frontend_plan *pl, const int64_t *sizes, const int64_
     B.o_tseg = take(B.task_seg.size() * sizeof(int));
     B.o_tfirst = take(B.task_first.size() * sizeof(int));
     B.upload_bytes = o;
-    B.o_mm = take((size_t)n_files * 2 * sizeof(unsigned int));
+    B.o_mm = take((size_t)B.groups * (pl->tc ? tc_n_ranges(pl->tc) : 1) * sizeof(float2));   // per-(group, slot) min/max
     B.o_anchors = take(pl->tc ? tc_anchor_bytes(pl->tc, B.n_anchors) : 0);
     B.o_spec = take(B.spec_floats * sizeof(float));
     B.total = o;
@@ -621,7 +725,7 @@ extern "C" int nbm_frontend_run_batch(const nbm_frontend_plan *cpl, const void *
     FileDesc *d_files = reinterpret_cast<FileDesc *>(ws + B.o_files);
     const int *d_tseg = reinterpret_cast<const int *>(ws + B.o_tseg);
     const int *d_tfirst = reinterpret_cast<const int *>(ws + B.o_tfirst);
-    unsigned int *d_enc = reinterpret_cast<unsigned int *>(ws + B.o_mm);
+    float2 *d_tile_mm = reinterpret_cast<float2 *>(ws + B.o_mm);
     float *d_spec = reinterpret_cast<float *>(ws + B.o_spec);
 
     std::lock_guard<std::mutex> lock(pl->mu);
@@ -649,18 +753,26 @@ extern "C" int nbm_frontend_run_batch(const nbm_frontend_plan *cpl, const void *
         rc = collect_profile(pl);
         if (rc != NBM_OK) return rc;
     }
-    init_minmax_kernel<<<(n_files + 255) / 256, 256, 0, stream>>>(d_enc, n_files);
     if (prof) NBM_CUDA(cudaEventRecord(pl->ev[0], stream));
     if (pl->tc) {
         rc = tc_launch(pl->tc, d_segs, (int)B.segs.size(), B.groups, d_tseg, d_tfirst, (int)B.task_seg.size(), d_pcm,
-                       pcm_dtype, channels, d_spec, d_enc, ws + B.o_anchors, stream);
+                       pcm_dtype, channels, d_spec, d_tile_mm, ws + B.o_anchors, stream);
         if (rc != NBM_OK) return rc;
     } else {
         stft_db_kernel<<<B.groups, pl->n_threads, pl->smem_bytes, stream>>>(pl->kp, d_segs, (int)B.segs.size(), d_pcm,
-                                                                          pcm_dtype, channels, d_spec, d_enc);
+                                                                          pcm_dtype, channels, d_spec, d_tile_mm);
     }
     if (prof) NBM_CUDA(cudaEventRecord(pl->ev[1], stream));
-    finalize_minmax_kernel<<<(n_files + 255) / 256, 256, 0, stream>>>(d_enc, d_minmax, n_files);
+    {
+        RefineParams rp;
+        rp.N = p.n_fft; rp.hop = p.hop; rp.low_idx = p.low_idx; rp.n_bins = p.n_bins;
+        rp.n_slots = pl->tc ? tc_n_ranges(pl->tc) : 1;
+        rp.bins_per_slot = pl->tc ? tc_bins_per_range() : p.n_bins;
+        rp.min_level = p.min_level;
+        rp.margin_db = 0.25f;
+        refine_minmax_kernel<<<n_files, 256, 0, stream>>>(rp, d_segs, d_files, d_tile_mm, d_spec, d_pcm, pcm_dtype,
+                                                         channels, d_minmax);
+    }
     dim3 grid((unsigned)B.tiles, (unsigned)((p.n_bins + TILE_ROWS - 1) / TILE_ROWS));
     if (prof) NBM_CUDA(cudaEventRecord(pl->ev[2], stream));
     if (p.w_pix % 4 == 0) tile_kernel<true><<<grid, 256, 0, stream>>>(pl->kp, d_files, n_files, d_spec, d_minmax, d_tiles);

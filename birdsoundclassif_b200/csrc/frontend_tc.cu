@@ -344,10 +344,11 @@ __device__ __forceinline__ void cvt8_pcm16(const int4 raw, float4 &lo, float4 &h
 __global__ void __launch_bounds__(TC_THREADS, 1)
 slide_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int total_tiles,
                 const void *__restrict__ pcm, int dtype, int channels, int vec_ok,
-                const float2 *__restrict__ anchors, float *__restrict__ spec, unsigned int *__restrict__ minmax_enc) {
+                const float2 *__restrict__ anchors, float *__restrict__ spec, float2 *__restrict__ tile_mm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t bar[2];
     __shared__ uint32_t tmem_base_s;
+    __shared__ unsigned int s_mm[2];            // this (tile, range)'s min / max, order-preserving encoding
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int range = blockIdx.x % P.n_ranges;
     const int q0 = blockIdx.x / P.n_ranges, qstride = gridDim.x / P.n_ranges;
@@ -368,7 +369,10 @@ slide_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int to
         for (int i = tid; i < (int)(6 * b_mat / 16); i += TC_THREADS) db[i] = make_uint4(0, 0, 0, 0);
     }
     if (warp == 0) tmem_alloc(&tmem_base_s, 256);
-    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (tid == 0) {
+        mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_mm[0] = 0xffffffffu; s_mm[1] = 0u;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -417,19 +421,6 @@ slide_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int to
         }
     };
     float vmin = INFINITY, vmax = -INFINITY;
-    int mm_file = -1;
-    auto flush_minmax = [&]() {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
-            vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-        }
-        if (lane == 0 && mm_file >= 0 && vmin <= vmax) {
-            atomicMin(minmax_enc + 2 * mm_file, float_to_ordered(vmin));
-            atomicMax(minmax_enc + 2 * mm_file + 1, float_to_ordered(vmax));
-        }
-        vmin = INFINITY; vmax = -INFINITY;
-    };
 
     if (n_iters > 0) open_tile(0);
     for (int it = 0; it <= n_iters; ++it) {
@@ -532,7 +523,6 @@ slide_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int to
             const int pb = (it - 1) & 1;
             const SegDesc &sd = prev.sd;
             const int t0 = prev.t0;
-            if (sd.file != mm_file) { flush_minmax(); mm_file = sd.file; }
             const float2 anc = __ldg(anchors + prev.anchor_row);
             mbar_wait(&bar[pb], ((it - 1) >> 1) & 1);
             tc_fence_after();
@@ -596,10 +586,26 @@ slide_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int to
                 }
                 __syncthreads();
             }
+            // ---- this (tile, range)'s min / max for the whole-file reduction (refine_minmax_kernel) ----
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+                vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+            }
+            if (lane == 0 && vmin <= vmax) {
+                atomicMin(&s_mm[0], float_to_ordered(vmin));
+                atomicMax(&s_mm[1], float_to_ordered(vmax));
+            }
+            vmin = INFINITY; vmax = -INFINITY;
+            __syncthreads();
+            if (tid == 0) {
+                const long long tile = q0 + (long long)(it - 1) * qstride;
+                tile_mm[tile * P.n_ranges + range] = make_float2(ordered_to_float(s_mm[0]), ordered_to_float(s_mm[1]));
+                s_mm[0] = 0xffffffffu; s_mm[1] = 0u;        // next use is behind at least one more barrier
+            }
         }
         prev = cur;
     }
-    flush_minmax();
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, 256);
@@ -726,10 +732,12 @@ size_t nbm::tc_anchor_bytes(const TcPlan *pl, long long n_anchors) {
 }
 
 int nbm::tc_anchor_group() { return NA; }
+int nbm::tc_n_ranges(const TcPlan *pl) { return pl->p.n_ranges; }
+int nbm::tc_bins_per_range() { return BINS_PER_RANGE; }
 
 int nbm::tc_launch(const TcPlan *pl, const SegDesc *d_segs, int n_segs, int total_tiles, const int *d_task_seg,
                    const int *d_task_first, int n_tasks, const void *d_pcm, int dtype, int channels, float *d_spec,
-                   unsigned int *d_minmax_enc, void *d_anchors, cudaStream_t stream) {
+                   float2 *d_tile_mm, void *d_anchors, cudaStream_t stream) {
     const TcParams &k = pl->p;
     float2 *anchors = reinterpret_cast<float2 *>(d_anchors);
     dim3 ga((unsigned)n_tasks, (unsigned)k.n_ranges);
@@ -739,7 +747,7 @@ int nbm::tc_launch(const TcPlan *pl, const SegDesc *d_segs, int n_segs, int tota
     // 16-byte vector loads of PCM16 need a mono int16 stream on a 16-byte aligned base
     const int vec_ok = (dtype == NBM_PCM_INT16 && channels == 1 && (reinterpret_cast<uintptr_t>(d_pcm) & 15) == 0) ? 1 : 0;
     slide_tc_kernel<<<(grid / k.n_ranges) * k.n_ranges, TC_THREADS, pl->smem_slide, stream>>>(
-        k, d_segs, n_segs, total_tiles, d_pcm, dtype, channels, vec_ok, anchors, d_spec, d_minmax_enc);
+        k, d_segs, n_segs, total_tiles, d_pcm, dtype, channels, vec_ok, anchors, d_spec, d_tile_mm);
     NBM_CUDA(cudaGetLastError());
     return NBM_OK;
 }

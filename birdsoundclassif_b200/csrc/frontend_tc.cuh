@@ -25,9 +25,11 @@ void tc_plan_destroy(TcPlan *pl);
 size_t tc_anchor_bytes(const TcPlan *pl, long long n_anchors);
 // anchors per anchor task: the host builds one (segment, first anchor) task per this many anchors of a segment
 int tc_anchor_group();
+int tc_n_ranges(const TcPlan *pl);      // 128-row bin ranges (min/max slots per group)
+int tc_bins_per_range();               // output bins per range
 // anchors (tcgen05 GEMM over N/2 folded pairs) then slides (tcgen05 GEMM over hop/2 pairs + recurrence + Hann + dB)
 int tc_launch(const TcPlan *pl, const SegDesc *d_segs, int n_segs, int total_tiles, const int *d_task_seg,
               const int *d_task_first, int n_tasks, const void *d_pcm, int dtype, int channels, float *d_spec,
-              unsigned int *d_minmax_enc, void *d_anchors, cudaStream_t stream);
+              float2 *d_tile_mm, void *d_anchors, cudaStream_t stream);
 
 }  // namespace nbm
