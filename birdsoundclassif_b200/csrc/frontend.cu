@@ -267,7 +267,9 @@ stft_db_kernel(KParams P, const SegDesc *__restrict__ segs, int n_segs, const vo
 // them (float64 windowed DFT -> complex64 -> float32 |.| -> float64 log10), patched in the dB band,
 // and the minimum is taken over the patched values.  One block per file.
 struct RefineParams {
-    int N, hop, low_idx, n_bins, n_slots, bins_per_slot;
+    int N, hop, low_idx, n_bins;
+    int mm_frames;          // frames per min/max partial group (a divisor of GF)
+    int n_ranges, slots_per_range, bins_per_range, bins_per_slot;
     double min_level;
     float margin_db;
 };
@@ -295,8 +297,9 @@ refine_minmax_kernel(RefineParams R, const SegDesc *__restrict__ segs, const Fil
     __shared__ int n_cand;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const FileDesc fd = files[blockIdx.x];
-    const int n_ent = fd.n_groups * R.n_slots;
-    const float2 *mm = tile_mm + (size_t)fd.group0 * R.n_slots;
+    const int per_gf = GF / R.mm_frames, n_slots = R.n_ranges * R.slots_per_range;
+    const int n_ent = fd.n_groups * per_gf * n_slots;
+    const float2 *mm = tile_mm + (size_t)fd.group0 * per_gf * n_slots;
 
     float vmin = INFINITY, vmax = -INFINITY;
     for (int i = tid; i < n_ent; i += 256) {
@@ -320,12 +323,14 @@ refine_minmax_kernel(RefineParams R, const SegDesc *__restrict__ segs, const Fil
     // candidates: pixels within the margin of the float32 minimum (only groups whose partial says so are read)
     for (int i = 0; i < n_ent; ++i) {
         if (!(mm[i].x <= thr)) continue;                       // block-uniform
-        const int g = fd.group0 + i / R.n_slots, slot = i % R.n_slots;
+        const int mg = fd.group0 * per_gf + i / n_slots, slot = i % n_slots;     // partial group (mm_frames frames)
         int si = fd.seg0 + fd.n_segs - 1;
-        while (si > fd.seg0 && segs[si].group0 > g) --si;
+        while (si > fd.seg0 && segs[si].group0 * per_gf > mg) --si;
         const SegDesc sd = segs[si];
-        const int t0 = (g - sd.group0) * GF, nf = min(GF, sd.n_frames - t0);
-        const int b0 = slot * R.bins_per_slot, nb = min(R.bins_per_slot, R.n_bins - b0);
+        const int t0 = (mg - sd.group0 * per_gf) * R.mm_frames, nf = min(R.mm_frames, sd.n_frames - t0);
+        const int rng = slot / R.slots_per_range, sl = slot % R.slots_per_range;
+        const int b0 = rng * R.bins_per_range + sl * R.bins_per_slot;
+        const int nb = min(min(R.bins_per_slot, R.bins_per_range - sl * R.bins_per_slot), R.n_bins - b0);
         for (int p = tid; p < nb * nf; p += 256) {
             const int b = b0 + p / nf, t = t0 + p % nf;
             if (spec[sd.spec_off + (long long)b * sd.row_stride + t] <= thr) {
@@ -554,7 +559,8 @@ int build_layout(const nbm_frontend_plan *pl, const int64_t *sizes, const int64_
     B.o_tseg = take(B.task_seg.size() * sizeof(int));
     B.o_tfirst = take(B.task_first.size() * sizeof(int));
     B.upload_bytes = o;
-    B.o_mm = take((size_t)B.groups * (pl->tc ? tc_n_ranges(pl->tc) : 1) * sizeof(float2));   // per-(group, slot) min/max
+    B.o_mm = take((size_t)B.groups * (pl->tc ? (GF / tc_chain_frames()) * tc_n_ranges(pl->tc) * tc_slots_per_range() : 1) *
+                  sizeof(float2));                                  // min/max partials
     B.o_anchors = take(pl->tc ? tc_anchor_bytes(pl->tc, B.n_anchors) : 0);
     B.o_spec = take(B.spec_floats * sizeof(float));
     B.total = o;
@@ -754,7 +760,9 @@ extern "C" int nbm_frontend_run_batch(const nbm_frontend_plan *cpl, const void *
         if (rc != NBM_OK) return rc;
     }
     if (prof) NBM_CUDA(cudaEventRecord(pl->ev[0], stream));
-    if (pl->tc) {
+    // the tensor-core kernels stage mono PCM16; float or multi-channel input takes the CUDA-core kernel
+    const bool use_tc = pl->tc && pcm_dtype == NBM_PCM_INT16 && channels == 1;
+    if (use_tc) {
         rc = tc_launch(pl->tc, d_segs, (int)B.segs.size(), B.groups, d_tseg, d_tfirst, (int)B.task_seg.size(), d_pcm,
                        pcm_dtype, channels, d_spec, d_tile_mm, ws + B.o_anchors, stream);
         if (rc != NBM_OK) return rc;
@@ -766,8 +774,11 @@ extern "C" int nbm_frontend_run_batch(const nbm_frontend_plan *cpl, const void *
     {
         RefineParams rp;
         rp.N = p.n_fft; rp.hop = p.hop; rp.low_idx = p.low_idx; rp.n_bins = p.n_bins;
-        rp.n_slots = pl->tc ? tc_n_ranges(pl->tc) : 1;
-        rp.bins_per_slot = pl->tc ? tc_bins_per_range() : p.n_bins;
+        rp.mm_frames = use_tc ? tc_chain_frames() : GF;
+        rp.n_ranges = use_tc ? tc_n_ranges(pl->tc) : 1;
+        rp.slots_per_range = use_tc ? tc_slots_per_range() : 1;
+        rp.bins_per_range = use_tc ? tc_bins_per_range() : p.n_bins;
+        rp.bins_per_slot = use_tc ? tc_bins_per_slot() : p.n_bins;
         rp.min_level = p.min_level;
         rp.margin_db = 0.25f;
         refine_minmax_kernel<<<n_files, 256, 0, stream>>>(rp, d_segs, d_files, d_tile_mm, d_spec, d_pcm, pcm_dtype,

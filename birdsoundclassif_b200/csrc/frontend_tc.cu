@@ -60,15 +60,16 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    // the hardware parks the thread up to the time hint (ns) before reporting "not yet"
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
     return ok != 0;
 }
 // bounded wait: a lost arrival traps (launch error) instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    const long long t0 = clock64();
+    int spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000ll) __trap();
+        if (++spins > (1 << 24)) __trap();
     }
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
@@ -313,302 +314,481 @@ anchor_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, const
 }
 
 // ------------------------------------------------------------------------- slide kernel --------
-struct TileCtx {
-    SegDesc sd;
-    int t0;                 // first frame of the tile inside its segment
-    long long anchor_row;   // float2 index of this thread's anchor for its direction
-    long long s0;           // segment-relative sample index of buf[0]
-    int fast;               // 16-byte vector loads possible for this tile
-    unsigned full;          // bit e: prefetched vector e lies fully inside the segment
-};
+// Persistent CTA = one 128-bin range; work unit = a 32-frame CHAIN: even chains slide forward from the
+// anchor at frame 64k (frames 64k .. 64k+31), odd chains slide backward from the anchor at frame 64(k+1)
+// (frames 64k+63 .. 64k+32).  The CTA is G identical, independent warp GROUPS (4 warps = 128 threads = the
+// 128 TMEM lanes); group g takes every G-th chain of the CTA and runs all stages on it:
+//
+//   fill      PCM16 -> offset-binary uint16 in shared memory (16-byte vectors prefetched one chain ahead)
+//   build     folded differences of the chain's 32 hop blocks -> fp16 hi/lo B operand (UMMA K-major layout)
+//   MMA       one elected thread: 30 x tcgen05.mma (M=128 bins, N=32 frames, K=16 pairs); A = the twiddles,
+//             resident in TMEM (an SS-mode MMA at N=32 would re-read 4 KB of A per instruction from shared
+//             memory, the binding resource of this kernel); B from shared memory; D = the group's accumulator
+//   recur     thread = bin: tcgen05.ld the chain's D columns, 32-step recurrence in registers, R parked in
+//             the group's shared-memory stage (float2 [128 bins][32 frames])
+//   emit      thread = frame: Hann over neighbouring bins, |.|^2, dB, coalesced 128-byte row stores, min/max
+//
+// The MMA of chain i+1 is issued before the emit stage of chain i, so it runs under it; groups are out of
+// phase with each other, which is what overlaps the latency-bound stages (named barriers are group-local,
+// there is no CTA-wide barrier after start-up).
+constexpr int CF = 32;                      // frames per chain
+constexpr int ST_LD = CF + 2;               // float2 per bin row of the R stage: 272 B pitch, conflict-free STS.128
+constexpr int ROWS_PER_EWARP = 32;          // emit rows per warp
+constexpr int TM_A_COL = 256;               // TMEM: accumulators in [0, 256), twiddles from column 256
+constexpr int TM_COLS = 512;
 
-constexpr int PF = 6;       // prefetched 16-byte PCM vectors per thread (covers buf_len <= 8 * PF * TC_THREADS)
-
-// 8 PCM16 samples (one 16-byte vector) -> 8 floats in "int16 / 8" units, exact:
-// bits(2^20 + u/8) = 0x49800000 | u for u = x + 32768, so subtracting 2^20 + 4096 leaves x / 8.
-__device__ __forceinline__ void cvt8_pcm16(const int4 raw, float4 &lo, float4 &hi) {
-    const uint32_t w[4] = {(uint32_t)raw.x ^ 0x80008000u, (uint32_t)raw.y ^ 0x80008000u,
-                           (uint32_t)raw.z ^ 0x80008000u, (uint32_t)raw.w ^ 0x80008000u};
-    float f[8];
+// one lane of the (converged) warp; the compiler treats the guarded region as single-threaded, so warp-uniform
+// operands of tcgen05 instructions need no per-value election loop
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        f[2 * i] = __uint_as_float(0x49800000u | (w[i] & 0xffffu)) - 1052672.0f;
-        f[2 * i + 1] = __uint_as_float(0x49800000u | (w[i] >> 16)) - 1052672.0f;
-    }
-    lo = make_float4(f[0], f[1], f[2], f[3]);
-    hi = make_float4(f[4], f[5], f[6], f[7]);
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint4 &lo, const uint4 &hi) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 
-// Persistent CTA: one 128-bin range, a strided sequence of 64-frame tiles.  The MMAs of tile i run while
-// the CTA does the epilogue of tile i-1 (two TMEM accumulator buffers, one shared-memory B buffer).
-__global__ void __launch_bounds__(TC_THREADS, 1)
-slide_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int total_tiles,
-                const void *__restrict__ pcm, int dtype, int channels, int vec_ok,
-                const float2 *__restrict__ anchors, float *__restrict__ spec, float2 *__restrict__ tile_mm) {
+// 8 values -> fp16 hi and lo (= v - hi), each packed as one 16-byte vector
+__device__ __forceinline__ void split8_hl(const float (&v)[8], uint4 &h, uint4 &l) {
+    uint32_t hh[4], ll[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half2 hp = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        const float2 hf = __half22float2(hp);
+        const __half2 lp = __floats2half2_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+        hh[i] = *reinterpret_cast<const uint32_t *>(&hp);
+        ll[i] = *reinterpret_cast<const uint32_t *>(&lp);
+    }
+    h = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+    l = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+}
+__device__ __forceinline__ __half2 u32_as_h2(uint32_t u) { return *reinterpret_cast<__half2 *>(&u); }
+__device__ __forceinline__ uint32_t h2_as_u32(__half2 h) { return *reinterpret_cast<uint32_t *>(&h); }
+// two offset-binary PCM16 samples packed in one word -> floats 2^9 + u 2^-14 (differences of two such are exact)
+__device__ __forceinline__ void unpack2(uint32_t w, float &f0, float &f1) {
+    f0 = __uint_as_float(__byte_perm(w, 0x44000000u, 0x7610));
+    f1 = __uint_as_float(__byte_perm(w, 0x44000000u, 0x7632));
+}
+
+// Chain -> segment bookkeeping kept in registers; the descriptor is re-read only when the segment changes.
+struct ChainWalk {
+    const SegDesc *segs;
+    int n_segs, seg_idx, next_chain0;
+    SegDesc sd;
+    __device__ void init(const SegDesc *s, int n) {
+        segs = s; n_segs = n; seg_idx = 0; sd = s[0];
+        next_chain0 = n > 1 ? 2 * s[1].group0 : 0x7fffffff;
+    }
+    // chains are visited in increasing order
+    __device__ __forceinline__ void seek(int chain) {
+        while (chain >= next_chain0) {
+            ++seg_idx;
+            sd = segs[seg_idx];
+            next_chain0 = seg_idx + 1 < n_segs ? 2 * segs[seg_idx + 1].group0 : 0x7fffffff;
+        }
+    }
+};
+
+#ifdef NBM_WS_TIMING
+// diagnostic build only (scripts/ws_timing.py): cycles per pipeline phase, summed over the warps of CTA 0
+__device__ unsigned long long ws_dbg[32];
+#define WS_T0() long long t_mark = clock64(); unsigned long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define WS_MARK(i) do { const long long t_now = clock64(); t_acc[i] += (unsigned long long)(t_now - t_mark); t_mark = t_now; } while (0)
+#define WS_FLUSH(base) do { if (blockIdx.x == 0 && lane == 0) for (int i_ = 0; i_ < 8; ++i_) atomicAdd(&ws_dbg[(base) + i_], t_acc[i_]); } while (0)
+#else
+#define WS_T0()
+#define WS_MARK(i)
+#define WS_FLUSH(base)
+#endif
+
+// Warp roles of the CTA (16 warps; registers are allocated in units of 4 warps, so 16 x 128 registers is the
+// shape that fills the register file):
+//   warps 0 .. 4G-1   G worker groups of 4 warps: recur -> build(next) -> emit
+//   warp  4G          MMA issuer for every group (one elected thread)
+//   warps 4G+1 .. +G  one fill warp per group: PCM16 of the group's next chain -> shared memory
+constexpr int WS_G = 3;
+constexpr int WS_THREADS = 32 * (4 * WS_G + 1 + WS_G);
+constexpr int PV = 22;                      // 16-byte PCM vectors per fill lane per round
+
+__global__ void __launch_bounds__(WS_THREADS, 1)
+slide_ws_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int total_chains,
+                const short *__restrict__ pcm, const float2 *__restrict__ anchors,
+                float *__restrict__ spec, float2 *__restrict__ chain_mm) {
+    constexpr int G = WS_G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ uint64_t bar[2];
+    __shared__ uint64_t acc_full[G], b_ready[G], s_full[G], s_free[G];
     __shared__ uint32_t tmem_base_s;
-    __shared__ unsigned int s_mm[2];            // this (tile, range)'s min / max, order-preserving encoding
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool is_worker = warp < 4 * G, is_mma_warp = warp == 4 * G;
+    const int g = is_worker ? warp >> 2 : (is_mma_warp ? 0 : warp - 4 * G - 1);    // group served
+    const int wq = warp & 3, gt = tid & 127;                       // worker: warp in group (= TMEM lane quarter), thread in group
     const int range = blockIdx.x % P.n_ranges;
     const int q0 = blockIdx.x / P.n_ranges, qstride = gridDim.x / P.n_ranges;
 
     const int KP = P.KP, nk = P.nk, hop = P.hop, N = P.N;
-    const size_t a_mat = (size_t)128 * KP * 2, b_mat = (size_t)GF * KP * 2;
-    unsigned char *sA = smem_raw;                               // 4 x [128 x KP]
-    unsigned char *sB = sA + 4 * a_mat;                         // 6 x [64 x KP]
-    float *buf = reinterpret_cast<float *>(sB + 6 * b_mat);     // samples (scaled), PADF + off front padding
-    float2 *stage = reinterpret_cast<float2 *>(buf + P.buf_len);    // [128][STAGE_LD]
+    const size_t b_mat = (size_t)CF * KP * 2;
+    const size_t grp_bytes = 4 * b_mat + (size_t)128 * ST_LD * 8 + (size_t)P.buf_len * 2;
+    unsigned char *gbase = smem_raw + (size_t)g * grp_bytes;
+    unsigned char *sB = gbase;                                           // 4 x [32 x KP] fp16
+    float2 *stage = reinterpret_cast<float2 *>(gbase + 4 * b_mat);       // [128][ST_LD]
+    uint16_t *buf16 = reinterpret_cast<uint16_t *>(stage + 128 * ST_LD); // samples of one chain, offset binary
 
-    // ---- one-time: twiddles resident, B padding zeroed, TMEM, barriers --------------------------
-    {
-        const uint4 *ga = reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(P.a_slide) + (size_t)range * 4 * a_mat);
-        uint4 *da = reinterpret_cast<uint4 *>(sA);
-        for (int i = tid; i < (int)(4 * a_mat / 16); i += TC_THREADS) da[i] = __ldg(ga + i);
+    if (is_worker) {   // B zeroed once: the K padding columns are never written again
         uint4 *db = reinterpret_cast<uint4 *>(sB);
-        for (int i = tid; i < (int)(6 * b_mat / 16); i += TC_THREADS) db[i] = make_uint4(0, 0, 0, 0);
+        for (int i = gt; i < (int)(4 * b_mat / 16); i += 128) db[i] = make_uint4(0, 0, 0, 0);
     }
-    if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+    if (warp == 0) tmem_alloc(&tmem_base_s, TM_COLS);
     if (tid == 0) {
-        mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        s_mm[0] = 0xffffffffu; s_mm[1] = 0u;
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            mbar_init(&acc_full[i], 1); mbar_init(&b_ready[i], 4);
+            mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
-    const uint32_t idesc = make_idesc(128, GF);
+    const uint32_t tmem_a = tmem_base + TM_A_COL;                  // 4 matrices x (KP / 2) columns
+    // ---- twiddles into TMEM: thread = bin row = TMEM lane, 16 fp16 (one k-step) = 8 columns per store ----
+    if (warp < 4) {
+        const uint4 *grow = reinterpret_cast<const uint4 *>(
+            reinterpret_cast<const unsigned char *>(P.a_slide) + ((size_t)range * 128 + gt) * 4 * KP * 2);
+        const uint32_t tl = tmem_a + ((uint32_t)(wq * 32) << 16);
+        for (int m = 0; m < 4; ++m)
+            for (int kk = 0; kk < nk; ++kk) {
+                const uint4 lo = __ldg(grow + (m * KP + kk * 16) / 8), hi = __ldg(grow + (m * KP + kk * 16) / 8 + 1);
+                tmem_st8(tl + (uint32_t)(m * (KP / 2) + kk * 8), lo, hi);
+            }
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    // chains of group g: q0 + (j * G + g) * qstride
+    const int first = q0 + g * qstride, cstride = G * qstride;
+    const int n_iters = first < total_chains ? (total_chains - first + cstride - 1) / cstride : 0;
+    const uint32_t idesc = make_idesc(128, CF);
     const uint32_t SBO = (uint32_t)(KP / 8) * 128;
+    const uint32_t kp2 = (uint32_t)KP / 2;
 
-    // epilogue-1 role: bin row, direction
-    const int quarter = warp & 3, dir = warp >> 2;
-    const int row = quarter * 32 + lane;
-    const float2 cf = P.cf[range * 128 + row];
-    const float2 gg = dir == 0 ? P.gf[range * 128 + row] : P.gb[range * 128 + row];
-    const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
-    const int njg = (P.npH + 7) / 8;
-    const int half_hop = hop / 2;
-    const int n_iters = q0 < total_tiles ? (total_tiles - q0 + qstride - 1) / qstride : 0;
-
-    int seg_idx = 0;
-    TileCtx cur{}, prev{}, nxt{};
-    int4 pre[PF];
-    const short *p16 = reinterpret_cast<const short *>(pcm);
-    const int nv = P.buf_len / 8;
-    const bool can_prefetch = vec_ok && nv <= PF * TC_THREADS;
-    // tile context + issue of the 16-byte PCM loads (they land while the previous tile's epilogue runs)
-    auto open_tile = [&](int it_) {
-        const int tile = q0 + it_ * qstride;
-        while (seg_idx + 1 < n_segs && segs[seg_idx + 1].group0 <= tile) ++seg_idx;
-        nxt.sd = segs[seg_idx];
-        const int lt = tile - nxt.sd.group0;
-        nxt.t0 = lt * GF;
-        nxt.anchor_row = ((long long)nxt.sd.group0 + seg_idx + lt + dir) * (P.n_ranges * 128) + range * 128 + row;
-        nxt.s0 = (long long)nxt.t0 * hop - N / 2 - (PADF + P.off);
-        const long long g0 = nxt.sd.pcm_start + nxt.s0;
-        nxt.fast = can_prefetch && (g0 & 7) == 0;
-        nxt.full = 0u;
-        if (nxt.fast) {
-#pragma unroll
-            for (int e = 0; e < PF; ++e) {
-                const int v = tid + e * TC_THREADS;
-                const long long sv = nxt.s0 + 8 * v;
-                if (v < nv && sv >= 0 && sv + 8 <= nxt.sd.n_samples) {
-                    pre[e] = __ldg(reinterpret_cast<const int4 *>(p16 + g0 + 8 * v));
-                    nxt.full |= 1u << e;
+    if (is_mma_warp) {
+        // ================================ MMA issuer (all groups, round robin) =========================
+        // b_ready[g] (4 warp arrivals) says: B operand of group g's next chain is in shared memory AND the group
+        // has pulled its previous accumulator into registers.
+        WS_T0();
+        for (int it = 0; it < n_iters; ++it) {          // n_iters of group 0 is the largest
+#pragma unroll 1
+            for (int gg = 0; gg < G; ++gg) {
+                if (q0 + (it * G + gg) * qstride >= total_chains) break;
+                mbar_wait(&b_ready[gg], it & 1);
+                tc_fence_after();
+                WS_MARK(0);
+                if (elect_one()) {
+                    const uint32_t b0 = smem_u32(smem_raw + (size_t)gg * grp_bytes);
+                    const uint64_t dph = make_desc(b0 + 0 * (uint32_t)b_mat, 128, SBO), dpl = make_desc(b0 + 1 * (uint32_t)b_mat, 128, SBO);
+                    const uint64_t dmh = make_desc(b0 + 2 * (uint32_t)b_mat, 128, SBO), dml = make_desc(b0 + 3 * (uint32_t)b_mat, 128, SBO);
+                    const uint32_t dcol = tmem_base + (uint32_t)gg * (2 * CF);
+#pragma unroll 1
+                    for (int kk = 0; kk < nk; ++kk) {
+                        const uint64_t ko = (uint64_t)(kk * 16);        // 256 B per k-step in the 16-byte address field
+                        const uint32_t acc = kk > 0 ? 1u : 0u, ka = tmem_a + kk * 8;
+                        // (cos_h + cos_l)(p_hi + p_lo) and (sin_h + sin_l)(m_hi + m_lo); the two accumulators alternate
+                        umma_f16_ts(dcol, ka + 0 * kp2, dph + ko, idesc, acc);
+                        umma_f16_ts(dcol + CF, ka + 2 * kp2, dmh + ko, idesc, acc);
+                        umma_f16_ts(dcol, ka + 0 * kp2, dpl + ko, idesc, 1u);
+                        umma_f16_ts(dcol + CF, ka + 2 * kp2, dml + ko, idesc, 1u);
+                        umma_f16_ts(dcol, ka + 1 * kp2, dph + ko, idesc, 1u);
+                        umma_f16_ts(dcol + CF, ka + 3 * kp2, dmh + ko, idesc, 1u);
+                        umma_f16_ts(dcol, ka + 1 * kp2, dpl + ko, idesc, 1u);
+                        umma_f16_ts(dcol + CF, ka + 3 * kp2, dml + ko, idesc, 1u);
+                    }
+                    umma_commit(&acc_full[gg]);
                 }
+                __syncwarp();
+                WS_MARK(1);
             }
         }
-    };
-    float vmin = INFINITY, vmax = -INFINITY;
-
-    if (n_iters > 0) open_tile(0);
-    for (int it = 0; it <= n_iters; ++it) {
-        if (it < n_iters) {
-            cur = nxt;
-            // the MMAs of tile it-1 (issued one iteration ago) must have finished reading sB
-            if (it >= 1) mbar_wait(&bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
-
-            // ---- samples of the tile into shared memory (zero outside the segment) -------------
-            if (cur.fast) {
-                const long long g0 = cur.sd.pcm_start + cur.s0;
+        WS_FLUSH(8);
+    } else if (!is_worker) {
+        // ================================ fill warp of group g ============================================
+        // Chain j's samples: 16-byte global loads issued first (they fly while the group still reads chain j-1's
+        // samples), then, once the group has released the buffer, flipped to offset binary and stored.
+        WS_T0();
+        ChainWalk cw;
+        cw.init(segs, n_segs);
+        const int nv = P.buf_len / 8;
+        for (int it = 0; it < n_iters; ++it) {
+            const int chain = first + it * cstride;
+            cw.seek(chain);
+            const int t0 = (chain - 2 * cw.sd.group0) * CF;
+            const long long s0 = (long long)t0 * hop - N / 2 - (PADF + P.off);
+            const long long pcm0 = cw.sd.pcm_start, ns = cw.sd.n_samples;
+            const long long g0 = pcm0 + s0;
+            const bool fast = (g0 & 7) == 0 && (reinterpret_cast<uintptr_t>(pcm) & 15) == 0;
+            // vector v covers samples s0 + 8v .. +7: fully inside the segment iff v_lo <= v < v_hi
+            const int v_lo = s0 >= 0 ? 0 : (int)((-s0 + 7) >> 3);
+            const long long room = ns - s0;
+            const int v_hi = room <= 0 ? 0 : (int)(room >> 3 < nv ? room >> 3 : nv);
+            if (fast) {
+                for (int vb = 0; vb < nv; vb += 32 * PV) {
+                    int4 pre[PV];
+                    const int4 *src = reinterpret_cast<const int4 *>(pcm + g0) + vb + lane;
 #pragma unroll
-                for (int e = 0; e < PF; ++e) {
-                    const int v = tid + e * TC_THREADS;
-                    if (v < nv) {
-                        float4 lo, hi;
-                        if (cur.full & (1u << e)) {
-                            cvt8_pcm16(pre[e], lo, hi);
-                        } else {
-                            const long long sv = cur.s0 + 8 * v;
-                            float f[8];
+                    for (int e = 0; e < PV; ++e) {
+                        const int v = vb + lane + 32 * e;
+                        if (v >= v_lo && v < v_hi) pre[e] = __ldg(src + 32 * e);
+                    }
+                    WS_MARK(0);
+                    if (vb == 0 && it > 0) mbar_wait(&s_free[g], (it - 1) & 1);   // every warp is done with chain it-1's samples
+                    WS_MARK(1);
+#pragma unroll
+                    for (int e = 0; e < PV; ++e) {
+                        const int v = vb + lane + 32 * e;
+                        if (v >= v_lo && v < v_hi) {
+                            reinterpret_cast<uint4 *>(buf16)[v] =
+                                make_uint4((uint32_t)pre[e].x ^ 0x80008000u, (uint32_t)pre[e].y ^ 0x80008000u,
+                                           (uint32_t)pre[e].z ^ 0x80008000u, (uint32_t)pre[e].w ^ 0x80008000u);
+                        } else if (v < nv) {        // straddles or lies outside the segment: centre padding (first / last chains)
+                            const long long sv = s0 + 8 * v;
+                            uint32_t u[8];
 #pragma unroll
                             for (int el = 0; el < 8; ++el)
-                                f[el] = (sv + el >= 0 && sv + el < cur.sd.n_samples) ? (float)__ldg(p16 + g0 + 8 * v + el) * 0.125f : 0.f;
-                            lo = make_float4(f[0], f[1], f[2], f[3]);
-                            hi = make_float4(f[4], f[5], f[6], f[7]);
+                                u[el] = (sv + el >= 0 && sv + el < ns) ? ((uint32_t)(uint16_t)__ldg(pcm + pcm0 + sv + el) ^ 0x8000u) : 0x8000u;
+                            reinterpret_cast<uint4 *>(buf16)[v] =
+                                make_uint4(u[0] | (u[1] << 16), u[2] | (u[3] << 16), u[4] | (u[5] << 16), u[6] | (u[7] << 16));
                         }
-                        reinterpret_cast<float4 *>(buf)[2 * v] = lo;
-                        reinterpret_cast<float4 *>(buf)[2 * v + 1] = hi;
                     }
+                }
+            } else {                                // file start not 16-byte aligned in the batch buffer
+                if (it > 0) mbar_wait(&s_free[g], (it - 1) & 1);
+                for (int i = lane; i < P.buf_len; i += 32) {
+                    const long long sx = s0 + i;
+                    buf16[i] = (sx >= 0 && sx < ns) ? (uint16_t)((uint16_t)__ldg(pcm + pcm0 + sx) ^ 0x8000u) : (uint16_t)0x8000u;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_full[g]);
+            WS_MARK(2);
+        }
+        WS_FLUSH(16);
+    } else {
+    // ================================ worker group g ======================================================
+    ChainWalk cw;
+    cw.init(segs, n_segs);
+    const int bar_id = 1 + g;
+    const int half_hop = hop / 2;
+    const int njg = (P.npH + 7) / 8;
+    const int n = gt & 31;                                         // build: frame column of this thread
+    const int base = PADF + P.off + n * hop;
+    const uint32_t acc_col = tmem_base + (uint32_t)g * (2 * CF);
+    const uint32_t lane_sel = (uint32_t)(wq * 32) << 16;
+    const float2 cf = P.cf[range * 128 + gt];
+    const float2 gF = P.gf[range * 128 + gt], gB = P.gb[range * 128 + gt];
+    const int r_lo = 1 + ROWS_PER_EWARP * wq;
+    // rows inside the band (only the last range is cut short)
+    const int r_hi = min(min(r_lo + ROWS_PER_EWARP, 127), P.n_bins - (range * BINS_PER_RANGE - 1));
+    const float floor_pw = 16.0f * P.min_level_sq;
+
+    // Byte-plane split.  With u = x + 32768 = 256 uh + ul (offset binary, the offsets cancel in differences),
+    //   ep = (a - b) + (c - d),  em = (a - b) - (c - d)     (a, b: new/old sample above the block centre; c, d: below)
+    // are formed separately on the high and the low bytes in packed fp16 arithmetic: a byte b becomes the half
+    // 0x6400 | b = 1024 + b (high plane) or 0x4400 | b = 4 + b/256 (low plane, pre-scaled), so every difference and
+    // sum is an exactly representable small number.  B = (ep_hi, ep_lo/256, em_hi, em_lo/256), value ep/256 = hi + lo.
+    auto planes = [&](uint32_t wa, uint32_t wb, uint32_t wc, uint32_t we, uint32_t &ph, uint32_t &pl, uint32_t &mh, uint32_t &ml) {
+        // wa, wb: samples (2q, 2q+1) above the centre (new, old), bytes [l0 h0 l1 h1]
+        const __half2 ah = u32_as_h2(__byte_perm(wa, 0x64646464u, 0x4341)), al = u32_as_h2(__byte_perm(wa, 0x44444444u, 0x4240));
+        const __half2 bh = u32_as_h2(__byte_perm(wb, 0x64646464u, 0x4341)), bl = u32_as_h2(__byte_perm(wb, 0x44444444u, 0x4240));
+        // wc, we: the mirrored samples below the centre, stored ascending: half 0 <- sample 1 of the word, half 1 <- sample 0
+        const __half2 ch = u32_as_h2(__byte_perm(wc, 0x64646464u, 0x4143)), cl = u32_as_h2(__byte_perm(wc, 0x44444444u, 0x4042));
+        const __half2 eh = u32_as_h2(__byte_perm(we, 0x64646464u, 0x4143)), el = u32_as_h2(__byte_perm(we, 0x44444444u, 0x4042));
+        const __half2 dhh = __hsub2(ah, bh), dhl = __hsub2(al, bl), dlh = __hsub2(ch, eh), dll = __hsub2(cl, el);
+        ph = h2_as_u32(__hadd2(dhh, dlh)); pl = h2_as_u32(__hadd2(dhl, dll));
+        mh = h2_as_u32(__hsub2(dhh, dlh)); ml = h2_as_u32(__hsub2(dhl, dll));
+    };
+    auto build_unit = [&](int jg) {         // thread = (frame n, pairs 8 jg .. 8 jg + 7), all live
+        // 8 consecutive samples = two 8-byte loads (frames are 8-byte, not 16-byte, aligned)
+        const uint2 *nh = reinterpret_cast<const uint2 *>(buf16 + base + N + half_hop + 8 * jg);
+        const uint2 *oh = reinterpret_cast<const uint2 *>(buf16 + base + half_hop + 8 * jg);
+        const uint2 *nl = reinterpret_cast<const uint2 *>(buf16 + base + N + half_hop - 8 - 8 * jg);
+        const uint2 *ol = reinterpret_cast<const uint2 *>(buf16 + base + half_hop - 8 - 8 * jg);
+        const uint2 a0 = nh[0], a1 = nh[1], b0 = oh[0], b1 = oh[1];
+        const uint2 c0 = nl[0], c1 = nl[1], e0 = ol[0], e1 = ol[1];
+        const uint32_t wa[4] = {a0.x, a0.y, a1.x, a1.y}, wb[4] = {b0.x, b0.y, b1.x, b1.y};
+        // the lo sample of pair jj sits at position 7 - jj of the ascending vector: words in reverse
+        const uint32_t wc[4] = {c1.y, c1.x, c0.y, c0.x}, we[4] = {e1.y, e1.x, e0.y, e0.x};
+        uint32_t ph[4], pl[4], mh[4], ml[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) planes(wa[q], wb[q], wc[q], we[q], ph[q], pl[q], mh[q], ml[q]);
+        const size_t o = umma_off(n, jg * 8, KP);
+        *reinterpret_cast<uint4 *>(sB + 0 * b_mat + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+        *reinterpret_cast<uint4 *>(sB + 1 * b_mat + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+        *reinterpret_cast<uint4 *>(sB + 2 * b_mat + o) = make_uint4(mh[0], mh[1], mh[2], mh[3]);
+        *reinterpret_cast<uint4 *>(sB + 3 * b_mat + o) = make_uint4(ml[0], ml[1], ml[2], ml[3]);
+    };
+    auto build_tail = [&](int jg) {         // the last, partial group of pairs (npH % 8 in {2, 4, 6}), word by word
+        const uint32_t *nh = reinterpret_cast<const uint32_t *>(buf16 + base + N + half_hop + 8 * jg);
+        const uint32_t *oh = reinterpret_cast<const uint32_t *>(buf16 + base + half_hop + 8 * jg);
+        const uint32_t *nl = reinterpret_cast<const uint32_t *>(buf16 + base + N + half_hop - 8 - 8 * jg);
+        const uint32_t *ol = reinterpret_cast<const uint32_t *>(buf16 + base + half_hop - 8 - 8 * jg);
+        const size_t o = umma_off(n, jg * 8, KP);
+        for (int q = 0; 8 * jg + 2 * q < P.npH; ++q) {
+            uint32_t ph, pl, mh, ml;
+            planes(nh[q], oh[q], nl[3 - q], ol[3 - q], ph, pl, mh, ml);
+            *reinterpret_cast<uint32_t *>(sB + 0 * b_mat + o + 4 * q) = ph;
+            *reinterpret_cast<uint32_t *>(sB + 1 * b_mat + o + 4 * q) = pl;
+            *reinterpret_cast<uint32_t *>(sB + 2 * b_mat + o + 4 * q) = mh;
+            *reinterpret_cast<uint32_t *>(sB + 3 * b_mat + o + 4 * q) = ml;
+        }
+    };
+    // B operand of the group's chain `it`; hands the operand to the MMA warp and the samples back to the fill warp
+    auto build = [&](int it) {
+        mbar_wait(&s_full[g], it & 1);
+        const int n_full = P.npH / 8;                               // units with all 8 pairs live
+        for (int jg = wq; jg < n_full; jg += 4) build_unit(jg);
+        if (n_full < njg && wq == (it & 3)) build_tail(n_full);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&b_ready[g]); mbar_arrive(&s_free[g]); }
+    };
+    auto anchor_of = [&](int chain) {       // the chain's anchor for this thread's bin (look-ahead walk)
+        ChainWalk w2 = cw;
+        w2.seek(chain);
+        const int lc = chain - 2 * w2.sd.group0;
+        return __ldg(anchors + ((long long)w2.sd.group0 + w2.seg_idx + ((lc + 1) >> 1)) * (P.n_ranges * 128) + range * 128 + gt);
+    };
+
+    float2 anc_next = make_float2(0.f, 0.f);
+    if (n_iters > 0) {
+        anc_next = anchor_of(first);
+        build(0);
+    }
+    WS_T0();
+    for (int it = 0; it < n_iters; ++it) {
+        const int chain = first + it * cstride;
+        cw.seek(chain);
+        const int lc = chain - 2 * cw.sd.group0;
+        const int t0 = lc * CF;
+        const bool fwd = (lc & 1) == 0;
+        const float2 anc = anc_next;
+        if (it + 1 < n_iters) anc_next = anchor_of(chain + cstride);
+        WS_MARK(0);
+        // ---- recur: accumulator -> registers -> 32-step recurrence -> stage ---------------------------
+        {
+            float gc[CF], gs[CF];
+            mbar_wait(&acc_full[g], it & 1);
+            WS_MARK(1);
+            tc_fence_after();
+            tmem_ld32_nowait(acc_col + lane_sel, gc);
+            tmem_ld32_nowait(acc_col + lane_sel + CF, gs);
+            tmem_ld_wait();
+            tc_fence_before();
+            float4 *st4 = reinterpret_cast<float4 *>(stage + (size_t)gt * ST_LD);
+            float Rr = anc.x, Ri = anc.y;
+            if (fwd) {
+                // frames t0 .. t0+31 ; column i+1 from column i with D_i
+                float pr = Rr, pi = Ri;
+#pragma unroll
+                for (int i = 0; i < CF - 1; ++i) {
+                    const float gr = gF.x * gc[i] + gF.y * gs[i];
+                    const float gi = gF.y * gc[i] - gF.x * gs[i];
+                    const float nr = fmaf(cf.x, Rr, fmaf(-cf.y, Ri, gr));
+                    const float ni = fmaf(cf.x, Ri, fmaf(cf.y, Rr, gi));
+                    Rr = nr; Ri = ni;
+                    if (i & 1) { pr = Rr; pi = Ri; }                       // column i+1 even: first of a pair
+                    else st4[i >> 1] = make_float4(pr, pi, Rr, Ri);       // columns (i, i+1)
                 }
             } else {
-                for (int i = tid; i < P.buf_len; i += TC_THREADS) {
-                    const long long sx = cur.s0 + i;
-                    buf[i] = (sx >= 0 && sx < cur.sd.n_samples) ? load_scaled(pcm, dtype, channels, cur.sd.pcm_start + sx) : 0.f;
-                }
-            }
-            __syncthreads();
-            // ---- B operand: folded differences, fp16 hi / lo / hi*2^-11 --------------------------
-            for (int u = tid; u < GF * njg; u += TC_THREADS) {
-                const int n = u % GF, jg = u / GF;
-                const int base = PADF + P.off + n * hop;
-                const float4 *nh = reinterpret_cast<const float4 *>(buf + base + N + half_hop + 8 * jg);
-                const float4 *oh = reinterpret_cast<const float4 *>(buf + base + half_hop + 8 * jg);
-                const float4 *nl = reinterpret_cast<const float4 *>(buf + base + N + half_hop - 8 - 8 * jg);
-                const float4 *ol = reinterpret_cast<const float4 *>(buf + base + half_hop - 8 - 8 * jg);
-                const float4 a0 = nh[0], a1 = nh[1], b0 = oh[0], b1 = oh[1];
-                const float4 c0 = nl[0], c1 = nl[1], e0 = ol[0], e1 = ol[1];
-                const float dh[8] = {a0.x - b0.x, a0.y - b0.y, a0.z - b0.z, a0.w - b0.w,
-                                     a1.x - b1.x, a1.y - b1.y, a1.z - b1.z, a1.w - b1.w};
-                // the lo sample of pair jj sits at position 7 - jj of the ascending vector
-                const float dl[8] = {c1.w - e1.w, c1.z - e1.z, c1.y - e1.y, c1.x - e1.x,
-                                     c0.w - e0.w, c0.z - e0.z, c0.y - e0.y, c0.x - e0.x};
-                float ep[8], em[8];
+                // frames t0+31 down to t0 ; column i from column i+1 with D_i ; column 32 is the anchor
+                float pr = 0.f, pi = 0.f;
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                    const bool ok = 8 * jg + jj < P.npH;
-                    ep[jj] = ok ? dh[jj] + dl[jj] : 0.f;
-                    em[jj] = ok ? dh[jj] - dl[jj] : 0.f;
+                for (int i = CF - 1; i >= 0; --i) {
+                    const float gr = gB.y * gs[i] - gB.x * gc[i];
+                    const float gi = gB.x * gs[i] + gB.y * gc[i];
+                    const float nr = fmaf(cf.x, Rr, fmaf(cf.y, Ri, gr));
+                    const float ni = fmaf(cf.x, Ri, fmaf(-cf.y, Rr, gi));
+                    Rr = nr; Ri = ni;
+                    if (i & 1) { pr = Rr; pi = Ri; }                       // odd column: second of a pair
+                    else st4[i >> 1] = make_float4(Rr, Ri, pr, pi);       // columns (i, i+1)
                 }
-                uint4 h, l, hs;
-                const size_t o = umma_off(n, jg * 8, KP);
-                split8(ep, h, l, hs);
-                *reinterpret_cast<uint4 *>(sB + 0 * b_mat + o) = h;
-                *reinterpret_cast<uint4 *>(sB + 1 * b_mat + o) = l;
-                *reinterpret_cast<uint4 *>(sB + 2 * b_mat + o) = hs;
-                split8(em, h, l, hs);
-                *reinterpret_cast<uint4 *>(sB + 3 * b_mat + o) = h;
-                *reinterpret_cast<uint4 *>(sB + 4 * b_mat + o) = l;
-                *reinterpret_cast<uint4 *>(sB + 5 * b_mat + o) = hs;
             }
-            fence_async_smem();
-            tc_fence_before();          // the epilogue's tcgen05.ld of two tiles ago precede this barrier
-            __syncthreads();
-            // ---- MMAs into TMEM buffer it&1: cos cols [0,64), sin cols [64,128) -------------------
-            if (tid == 0) {
-                tc_fence_after();
-                const uint32_t d0 = tmem_base + (uint32_t)(it & 1) * 128;
-                const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-                for (int kk = 0; kk < nk; ++kk) {
-                    const uint32_t ko = kk * 256, acc = kk > 0 ? 1u : 0u;
-                    const uint64_t ach = make_desc(a0 + 0 * (uint32_t)a_mat + ko, 128, SBO), acl = make_desc(a0 + 1 * (uint32_t)a_mat + ko, 128, SBO);
-                    const uint64_t ash = make_desc(a0 + 2 * (uint32_t)a_mat + ko, 128, SBO), asl = make_desc(a0 + 3 * (uint32_t)a_mat + ko, 128, SBO);
-                    const uint64_t bph = make_desc(b0 + 0 * (uint32_t)b_mat + ko, 128, SBO), bpl = make_desc(b0 + 1 * (uint32_t)b_mat + ko, 128, SBO);
-                    const uint64_t bps = make_desc(b0 + 2 * (uint32_t)b_mat + ko, 128, SBO), bmh = make_desc(b0 + 3 * (uint32_t)b_mat + ko, 128, SBO);
-                    const uint64_t bml = make_desc(b0 + 4 * (uint32_t)b_mat + ko, 128, SBO), bms = make_desc(b0 + 5 * (uint32_t)b_mat + ko, 128, SBO);
-                    umma_f16(d0, ach, bph, idesc, acc);
-                    umma_f16(d0, ach, bpl, idesc, 1u);
-                    umma_f16(d0, acl, bps, idesc, 1u);
-                    umma_f16(d0 + GF, ash, bmh, idesc, acc);
-                    umma_f16(d0 + GF, ash, bml, idesc, 1u);
-                    umma_f16(d0 + GF, asl, bms, idesc, 1u);
-                }
-                umma_commit(&bar[it & 1]);
-            }
-            if (it + 1 < n_iters) open_tile(it + 1);
         }
-        if (it >= 1) {
-            // ================= epilogue of tile it-1 (its MMAs were issued one iteration ago) =======
-            const int pb = (it - 1) & 1;
-            const SegDesc &sd = prev.sd;
-            const int t0 = prev.t0;
-            const float2 anc = __ldg(anchors + prev.anchor_row);
-            mbar_wait(&bar[pb], ((it - 1) >> 1) & 1);
-            tc_fence_after();
-            const uint32_t tl = tmem_base + (uint32_t)pb * 128 + lane_sel;
-            float Rr = anc.x, Ri = anc.y;
-            float *spec_seg = spec + sd.spec_off;
-            for (int hp = 0; hp < 2; ++hp) {
-                float gc[16], gs[16];
-                if (dir == 0) {
-                    // frames 16hp .. 16hp+15 ; G columns: hp=0 -> 0..14 (frame 0 is the anchor), hp=1 -> 15..30
-                    const int c0 = hp == 0 ? 0 : 15;
-                    tmem_ld16(tl + c0, gc);
-                    tmem_ld16(tl + GF + c0, gs);
-                    if (hp == 0) stage[row * STAGE_LD + 0] = make_float2(Rr, Ri);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        if (hp == 0 && i == 15) break;
-                        const float nr = cf.x * Rr - cf.y * Ri + gg.x * gc[i] + gg.y * gs[i];
-                        const float ni = cf.x * Ri + cf.y * Rr - gg.x * gs[i] + gg.y * gc[i];
-                        Rr = nr; Ri = ni;
-                        stage[row * STAGE_LD + (hp == 0 ? i + 1 : i)] = make_float2(Rr, Ri);
-                    }
-                } else {
-                    // frames 63-16hp down to 48-16hp ; G columns 63-16hp .. 48-16hp
-                    const int c0 = 48 - 16 * hp;
-                    tmem_ld16(tl + c0, gc);
-                    tmem_ld16(tl + GF + c0, gs);
-#pragma unroll
-                    for (int i = 15; i >= 0; --i) {
-                        const float nr = cf.x * Rr + cf.y * Ri - gg.x * gc[i] + gg.y * gs[i];
-                        const float ni = cf.x * Ri - cf.y * Rr + gg.x * gs[i] + gg.y * gc[i];
-                        Rr = nr; Ri = ni;
-                        stage[row * STAGE_LD + 16 + i] = make_float2(Rr, Ri);
-                    }
+        WS_MARK(2);
+        named_bar_sync(bar_id, 128);        // stage complete; accumulator and B operand free (MMA(it) done, D loaded)
+        WS_MARK(3);
+        // ---- next chain's B operand: its MMAs run under this chain's emit stage ------------------------
+        if (it + 1 < n_iters) build(it + 1);
+        WS_MARK(4);
+        // ---- emit: Hann + dB + store, lane = frame, warp = 32 bin rows ----------------------------------
+        {
+            float vmin = INFINITY, vmax = -INFINITY;
+            const float2 *st = stage + lane;
+            if (t0 + lane < cw.sd.n_frames && r_lo < r_hi) {
+                float2 pv = st[(r_lo - 1) * ST_LD], cu = st[r_lo * ST_LD];
+                const int stride = cw.sd.row_stride;
+                float *out = spec + cw.sd.spec_off + (long long)(range * BINS_PER_RANGE + r_lo - 1) * stride + t0 + lane;
+                const long long stride_b = (long long)stride * 4;
+#pragma unroll 8
+                for (int r = r_lo; r < r_hi; ++r) {
+                    const float2 nx = st[(r + 1) * ST_LD];
+                    // 4 X = 2 R[k] - (R[k-1] + R[k+1]);  10 log10(|X|^2) = 10 log10(|4X|^2) - 10 log10(16)
+                    const float xr = fmaf(2.0f, cu.x, -(pv.x + nx.x));
+                    const float xi = fmaf(2.0f, cu.y, -(pv.y + nx.y));
+                    const float pw = fmaxf(fmaf(xr, xr, xi * xi), floor_pw);
+                    const float db = fmaf(fast_log2(pw), 3.0102999566398120f, -12.041199826559248f);
+                    *out = db;
+                    out = reinterpret_cast<float *>(reinterpret_cast<char *>(out) + stride_b);
+                    vmin = fminf(vmin, db);
+                    vmax = fmaxf(vmax, db);
+                    pv = cu; cu = nx;
                 }
-                __syncthreads();
-                // ---- Hann + dB + store: lane = frame column, warp = 16 bin rows --------------------
-                {
-                    const int fl = lane < 16 ? 16 * hp + lane : 48 - 16 * hp + (lane - 16);     // frame inside the tile
-                    const int r_lo = 1 + 16 * warp;
-                    // rows r < ob_lim are inside the band (only the last range is cut short)
-                    const int r_hi = min(min(r_lo + 16, 127), P.n_bins - (range * BINS_PER_RANGE - 1));
-                    if (t0 + fl < sd.n_frames && r_lo < r_hi) {
-                        float2 pv = stage[(r_lo - 1) * STAGE_LD + lane], cu = stage[r_lo * STAGE_LD + lane];
-                        float *out = spec_seg + (long long)(range * BINS_PER_RANGE + r_lo - 1) * sd.row_stride + t0 + fl;
-#pragma unroll 4
-                        for (int r = r_lo; r < r_hi; ++r) {
-                            const float2 nx = stage[(r + 1) * STAGE_LD + lane];
-                            // 4 X = 2 R[k] - (R[k-1] + R[k+1]);  10 log10(|X|^2) = 10 log10(|4X|^2) - 10 log10(16)
-                            const float xr = fmaf(2.0f, cu.x, -(pv.x + nx.x));
-                            const float xi = fmaf(2.0f, cu.y, -(pv.y + nx.y));
-                            const float pw = fmaxf(fmaf(xr, xr, xi * xi), 16.0f * P.min_level_sq);
-                            const float db = fmaf(fast_log2(pw), 3.0102999566398120f, -12.041199826559248f);
-                            *out = db;
-                            vmin = fminf(vmin, db);
-                            vmax = fmaxf(vmax, db);
-                            out += sd.row_stride;
-                            pv = cu; cu = nx;
-                        }
-                    }
-                }
-                __syncthreads();
             }
-            // ---- this (tile, range)'s min / max for the whole-file reduction (refine_minmax_kernel) ----
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
                 vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
             }
-            if (lane == 0 && vmin <= vmax) {
-                atomicMin(&s_mm[0], float_to_ordered(vmin));
-                atomicMax(&s_mm[1], float_to_ordered(vmax));
-            }
-            vmin = INFINITY; vmax = -INFINITY;
-            __syncthreads();
-            if (tid == 0) {
-                const long long tile = q0 + (long long)(it - 1) * qstride;
-                tile_mm[tile * P.n_ranges + range] = make_float2(ordered_to_float(s_mm[0]), ordered_to_float(s_mm[1]));
-                s_mm[0] = 0xffffffffu; s_mm[1] = 0u;        // next use is behind at least one more barrier
-            }
+            if (lane == 0) chain_mm[((size_t)chain * P.n_ranges + range) * 4 + wq] = make_float2(vmin, vmax);
         }
-        prev = cur;
+        WS_MARK(5);
+        named_bar_sync(bar_id, 128);        // stage free for the next recurrence
+        WS_MARK(6);
+    }
+    WS_FLUSH(0);
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, 256);
+    if (warp == 0) tmem_dealloc(tmem_base, TM_COLS);
 }
 
 }  // namespace nbm
@@ -617,11 +797,19 @@ slide_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int to
 using namespace nbm;
 
 namespace {
+// anchor tables: w = h + 2^-11 l   (the B side carries a 2^-11-scaled copy of its hi part)
 inline void put_split(std::vector<__half> &dst, size_t base_elems_h, size_t base_elems_l, size_t off_bytes, double w) {
     const __half h = __float2half_rn((float)w);
     const double rem = (w - (double)__half2float(h)) * 2048.0;
     dst[base_elems_h + off_bytes / 2] = h;
     dst[base_elems_l + off_bytes / 2] = __float2half_rn((float)rem);
+}
+// slide tables: 2^11 w = H + L, both at the same scale, so (H, L) x (hi, lo) needs no rescaled operand copy
+inline void put_split_scaled(std::vector<__half> &dst, size_t base_elems_h, size_t base_elems_l, size_t off_bytes, double w) {
+    const double ws = w * 2048.0;
+    const __half h = __float2half_rn((float)ws);
+    dst[base_elems_h + off_bytes / 2] = h;
+    dst[base_elems_l + off_bytes / 2] = __float2half_rn((float)(ws - (double)__half2float(h)));
 }
 }  // namespace
 
@@ -629,7 +817,7 @@ int nbm::tc_plan_create(const nbm_frontend_params &p, TcPlan **out) {
     *out = nullptr;
     const int N = p.n_fft, hop = p.hop;
     const int npH = hop / 2, KP = ((npH + 15) / 16) * 16;
-    const bool ok = (N % 4 == 0) && (hop % 4 == 0) && KP <= 80 && hop >= 8 && p.n_bins <= 3 * BINS_PER_RANGE &&
+    const bool ok = (N % 4 == 0) && (hop % 4 == 0) && TM_A_COL + 4 * (KP / 2) <= TM_COLS && hop >= 8 && p.n_bins <= 3 * BINS_PER_RANGE &&
                     p.low_idx >= 1 && N >= 2 * hop;
     if (!ok) return NBM_ERR_UNSUPPORTED;
     auto *pl = new TcPlan();
@@ -639,7 +827,7 @@ int nbm::tc_plan_create(const nbm_frontend_params &p, TcPlan **out) {
     k.npH = npH; k.KP = KP; k.nk = KP / 16;
     k.npN = N / 2; k.n_stages = (k.npN + KS * 16 - 1) / (KS * 16);
     k.off = (4 - (npH % 4)) % 4;
-    k.buf_len = ((PADF + k.off + GF * hop + N + 16 + 7) / 8) * 8;   // +16: masked tail pairs read past the last block
+    k.buf_len = ((PADF + k.off + CF * hop + N + 16 + 7) / 8) * 8;   // +16: masked tail pairs read past the last block
     k.min_level_sq = (float)(p.min_level * p.min_level);
     const int R = k.n_ranges, N2 = 2 * N;
 
@@ -648,17 +836,18 @@ int nbm::tc_plan_create(const nbm_frontend_params &p, TcPlan **out) {
     std::vector<__half> a_slide(slide_elems, __float2half_rn(0.f)), a_anchor(anchor_elems, __float2half_rn(0.f));
     std::vector<float2> cf(R * 128), gf(R * 128), gb(R * 128), rot(R * 128);
     auto ang = [&](long long q) { return M_PI * (double)(q % N2) / (double)N; };
-    const double s12 = 1.0 / 4096.0;
+    const double s12 = 1.0 / 4096.0;          // anchors: samples / 8, twiddles x 1
+    const double s18 = 1.0 / 262144.0;        // slides: byte planes (ep / 256), twiddles x 2^11
     for (int r = 0; r < R; ++r)
         for (int row = 0; row < 128; ++row) {
             const long long kbin = p.low_idx - 1 + (long long)r * BINS_PER_RANGE + row;
-            // slide twiddles: pair j <-> u = j + 1/2
-            const size_t mat = (size_t)128 * KP;
+            // slide twiddles: pair j <-> u = j + 1/2 ; [range][row][cos_h, cos_l, sin_h, sin_l][KP], row-contiguous
+            // because each thread copies its own row into its TMEM lane
+            const size_t rbase = ((size_t)r * 128 + row) * 4 * KP;
             for (int j = 0; j < npH; ++j) {
                 const double a = ang(kbin * (2 * j + 1));
-                const size_t o = umma_off(row, j, KP);
-                put_split(a_slide, ((size_t)r * 4 + 0) * mat, ((size_t)r * 4 + 1) * mat, o, cos(a));
-                put_split(a_slide, ((size_t)r * 4 + 2) * mat, ((size_t)r * 4 + 3) * mat, o, sin(a));
+                put_split_scaled(a_slide, rbase + 0 * KP, rbase + 1 * KP, (size_t)j * 2, cos(a));
+                put_split_scaled(a_slide, rbase + 2 * KP, rbase + 3 * KP, (size_t)j * 2, sin(a));
             }
             const size_t amat = (size_t)128 * (KS * 16);
             for (int j = 0; j < k.npN; ++j) {
@@ -673,9 +862,9 @@ int nbm::tc_plan_create(const nbm_frontend_params &p, TcPlan **out) {
             double a = ang(kbin * 2 * hop);
             cf[i] = make_float2((float)cos(a), (float)sin(a));
             a = ang(kbin * (hop + 1));
-            gf[i] = make_float2((float)(cos(a) * s12), (float)(sin(a) * s12));
+            gf[i] = make_float2((float)(cos(a) * s18), (float)(sin(a) * s18));
             a = ang(kbin * (hop - 1));
-            gb[i] = make_float2((float)(cos(a) * s12), (float)(sin(a) * s12));
+            gb[i] = make_float2((float)(cos(a) * s18), (float)(sin(a) * s18));
             a = ang(kbin * (N - 1));
             rot[i] = make_float2((float)(cos(a) * s12), (float)(sin(a) * s12));
         }
@@ -696,7 +885,7 @@ int nbm::tc_plan_create(const nbm_frontend_params &p, TcPlan **out) {
     k.gf = reinterpret_cast<const float2 *>(d + b_slide + b_anchor + b_c);
     k.gb = reinterpret_cast<const float2 *>(d + b_slide + b_anchor + 2 * b_c);
     k.rot = reinterpret_cast<const float2 *>(d + b_slide + b_anchor + 3 * b_c);
-    pl->smem_slide = (size_t)4 * 128 * KP * 2 + (size_t)6 * GF * KP * 2 + (size_t)k.buf_len * 4 + (size_t)128 * STAGE_LD * 8;
+    pl->smem_slide = WS_G * ((size_t)4 * CF * KP * 2 + (size_t)128 * ST_LD * 8 + (size_t)k.buf_len * 2);
     pl->smem_anchor = (size_t)KS * 4 * 128 * 16 * 2 + (size_t)6 * NA * KS * 16 * 2;
     int dev = 0, sms = 0, max_smem = 0;
     cudaGetDevice(&dev);
@@ -704,7 +893,7 @@ int nbm::tc_plan_create(const nbm_frontend_params &p, TcPlan **out) {
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     pl->grid_slide = std::max(1, sms / R) * R;
     cudaFuncAttributes fa_s{}, fa_a{};
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa_s, slide_tc_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa_s, slide_ws_kernel);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa_a, anchor_tc_kernel);
     if (e == cudaSuccess && ((size_t)max_smem < pl->smem_slide + fa_s.sharedSizeBytes ||
                              (size_t)max_smem < pl->smem_anchor + fa_a.sharedSizeBytes)) {
@@ -712,7 +901,7 @@ int nbm::tc_plan_create(const nbm_frontend_params &p, TcPlan **out) {
         return NBM_ERR_UNSUPPORTED;
     }
     // per-function attribute (not per plan): allow the device maximum minus the kernel's static shared memory
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(slide_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(slide_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    max_smem - (int)fa_s.sharedSizeBytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(anchor_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    max_smem - (int)fa_a.sharedSizeBytes);
@@ -731,9 +920,21 @@ size_t nbm::tc_anchor_bytes(const TcPlan *pl, long long n_anchors) {
     return align_up((size_t)n_anchors * pl->p.n_ranges * 128 * sizeof(float2), 256);
 }
 
+#ifdef NBM_WS_TIMING
+extern "C" int nbm_debug_ws_timing(unsigned long long *out, int reset) {
+    unsigned long long z[32] = {0};
+    if (out && cudaMemcpyFromSymbol(out, ws_dbg, sizeof(z)) != cudaSuccess) return -1;
+    if (reset && cudaMemcpyToSymbol(ws_dbg, z, sizeof(z)) != cudaSuccess) return -1;
+    return 0;
+}
+#endif
+
 int nbm::tc_anchor_group() { return NA; }
 int nbm::tc_n_ranges(const TcPlan *pl) { return pl->p.n_ranges; }
 int nbm::tc_bins_per_range() { return BINS_PER_RANGE; }
+int nbm::tc_chain_frames() { return CF; }
+int nbm::tc_slots_per_range() { return 4; }
+int nbm::tc_bins_per_slot() { return ROWS_PER_EWARP; }
 
 int nbm::tc_launch(const TcPlan *pl, const SegDesc *d_segs, int n_segs, int total_tiles, const int *d_task_seg,
                    const int *d_task_first, int n_tasks, const void *d_pcm, int dtype, int channels, float *d_spec,
@@ -743,11 +944,10 @@ int nbm::tc_launch(const TcPlan *pl, const SegDesc *d_segs, int n_segs, int tota
     dim3 ga((unsigned)n_tasks, (unsigned)k.n_ranges);
     anchor_tc_kernel<<<ga, TC_THREADS, pl->smem_anchor, stream>>>(k, d_segs, n_segs, d_task_seg, d_task_first, d_pcm,
                                                                   dtype, channels, anchors);
-    const int grid = std::min(pl->grid_slide, std::max(1, total_tiles) * k.n_ranges);
-    // 16-byte vector loads of PCM16 need a mono int16 stream on a 16-byte aligned base
-    const int vec_ok = (dtype == NBM_PCM_INT16 && channels == 1 && (reinterpret_cast<uintptr_t>(d_pcm) & 15) == 0) ? 1 : 0;
-    slide_tc_kernel<<<(grid / k.n_ranges) * k.n_ranges, TC_THREADS, pl->smem_slide, stream>>>(
-        k, d_segs, n_segs, total_tiles, d_pcm, dtype, channels, vec_ok, anchors, d_spec, d_tile_mm);
+    const int total_chains = 2 * total_tiles;
+    const int grid = std::min(pl->grid_slide, std::max(1, total_chains) * k.n_ranges);
+    slide_ws_kernel<<<(grid / k.n_ranges) * k.n_ranges, WS_THREADS, pl->smem_slide, stream>>>(
+        k, d_segs, n_segs, total_chains, reinterpret_cast<const short *>(d_pcm), anchors, d_spec, d_tile_mm);
     NBM_CUDA(cudaGetLastError());
     return NBM_OK;
 }

@@ -27,6 +27,10 @@ size_t tc_anchor_bytes(const TcPlan *pl, long long n_anchors);
 int tc_anchor_group();
 int tc_n_ranges(const TcPlan *pl);      // 128-row bin ranges (min/max slots per group)
 int tc_bins_per_range();               // output bins per range
+// min/max partials: one float2 per (32-frame chain, range, slot); slot s of a range covers tc_bins_per_slot() bins
+int tc_chain_frames();
+int tc_slots_per_range();
+int tc_bins_per_slot();
 // anchors (tcgen05 GEMM over N/2 folded pairs) then slides (tcgen05 GEMM over hop/2 pairs + recurrence + Hann + dB)
 int tc_launch(const TcPlan *pl, const SegDesc *d_segs, int n_segs, int total_tiles, const int *d_task_seg,
               const int *d_task_first, int n_tasks, const void *d_pcm, int dtype, int channels, float *d_spec,
