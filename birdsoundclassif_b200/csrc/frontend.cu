@@ -294,7 +294,7 @@ refine_minmax_kernel(RefineParams R, const SegDesc *__restrict__ segs, const Fil
     __shared__ float s_red[16];
     __shared__ double d_red[16];
     __shared__ int c_seg[REFINE_CAP], c_bin[REFINE_CAP], c_frame[REFINE_CAP];
-    __shared__ int n_cand;
+    __shared__ int n_cand, n_hot, hot[REFINE_CAP];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const FileDesc fd = files[blockIdx.x];
     const int per_gf = GF / R.mm_frames, n_slots = R.n_ranges * R.slots_per_range;
@@ -313,16 +313,23 @@ refine_minmax_kernel(RefineParams R, const SegDesc *__restrict__ segs, const Fil
         vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
     }
     if (lane == 0) { s_red[warp] = vmin; s_red[8 + warp] = vmax; }
-    if (tid == 0) n_cand = 0;
+    if (tid == 0) { n_cand = 0; n_hot = 0; }
     __syncthreads();
     vmin = s_red[0]; vmax = s_red[8];
 #pragma unroll
     for (int w = 1; w < 8; ++w) { vmin = fminf(vmin, s_red[w]); vmax = fmaxf(vmax, s_red[8 + w]); }
     const float thr = vmin + R.margin_db;
 
-    // candidates: pixels within the margin of the float32 minimum (only groups whose partial says so are read)
-    for (int i = 0; i < n_ent; ++i) {
-        if (!(mm[i].x <= thr)) continue;                       // block-uniform
+    // partial groups whose minimum is within the margin (a handful), then their pixels
+    for (int i = tid; i < n_ent; i += 256)
+        if (mm[i].x <= thr) {
+            const int at = atomicAdd(&n_hot, 1);
+            if (at < REFINE_CAP) hot[at] = i;
+        }
+    __syncthreads();
+    const int nh = min(n_hot, REFINE_CAP);
+    for (int h = 0; h < nh; ++h) {
+        const int i = hot[h];
         const int mg = fd.group0 * per_gf + i / n_slots, slot = i % n_slots;     // partial group (mm_frames frames)
         int si = fd.seg0 + fd.n_segs - 1;
         while (si > fd.seg0 && segs[si].group0 * per_gf > mg) --si;
@@ -368,7 +375,7 @@ refine_minmax_kernel(RefineParams R, const SegDesc *__restrict__ segs, const Fil
     if (tid == 0) {
         // every pixel within the margin was recomputed unless the list overflowed (e.g. digital silence)
         float smin = vmin;
-        if (nc > 0) smin = n_cand > REFINE_CAP ? fminf(vmin, (float)best) : (float)best;
+        if (nc > 0) smin = (n_cand > REFINE_CAP || n_hot > REFINE_CAP) ? fminf(vmin, (float)best) : (float)best;
         out[2 * blockIdx.x] = smin;
         out[2 * blockIdx.x + 1] = vmax;
     }

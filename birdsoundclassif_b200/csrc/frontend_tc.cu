@@ -27,21 +27,17 @@ namespace nbm {
 
 constexpr int TC_THREADS = 256;
 constexpr int BINS_PER_RANGE = 126;     // rows 1..126 of each 128-row range are emitted, 0 and 127 are Hann halos
-constexpr int STAGE_LD = 33;            // float2 per bin row of the R stage (32 frames + pad)
 constexpr int PADF = 8;                 // front padding (floats) of the sample buffer
-constexpr int NA = 32;                  // anchors per anchor task (MMA N)
-constexpr int KS = 4;                   // k-steps (of 16 pairs) per anchor stage
-constexpr int NP = 8;                   // partial accumulators of the anchor contraction
 
 struct TcParams {
     int N, hop, low_idx, n_bins, n_ranges;
     int npH, KP, nk;            // hop/2 pairs, padded K of the slide GEMM, k-steps
-    int npN, n_stages;          // N/2 pairs, anchor stages of KS k-steps
+    int npN, n_stages;          // N/2 pairs, anchor k-blocks of AKB pairs
     int off;                    // sample-buffer offset making the 8-pair vectors 16 B aligned
     int buf_len;                // floats in the sample buffer
     float min_level_sq;
     const __half *a_slide;      // [n_ranges][4][128 x KP]  (cos_h, cos_l, sin_h, sin_l) UMMA layout
-    const __half *a_anchor;     // [n_ranges][n_stages][4][128 x 64]
+    const __half *a_anchor;     // [n_ranges][n_stages][cos_h, cos_l, sin_h, sin_l][128 x AKB] UMMA layout
     const float2 *cf, *gf, *gb, *rot;   // [n_ranges*128] per-bin constants
 };
 
@@ -139,39 +135,7 @@ __host__ __device__ inline size_t umma_off(int row, int k, int kext) {
     return (size_t)(row >> 3) * (kext >> 3) * 128 + (size_t)(k >> 3) * 128 + (row & 7) * 16 + (k & 7) * 2;
 }
 
-__device__ __forceinline__ float load_scaled(const void *pcm, int dtype, int channels, long long idx) {
-    // sample in "int16 units / 8": exact for PCM16, so that 18-bit pair sums split exactly into fp16 hi + lo
-    float s = 0.f;
-    if (dtype == NBM_PCM_INT16) {
-        const short *p = reinterpret_cast<const short *>(pcm) + idx * channels;
-        for (int c = 0; c < channels; ++c) s += (float)__ldg(p + c);
-        s *= 0.125f;
-    } else {
-        const float *p = reinterpret_cast<const float *>(pcm) + idx * channels;
-        for (int c = 0; c < channels; ++c) s += __ldg(p + c);
-        s *= 4096.0f;
-    }
-    return channels == 1 ? s : s / (float)channels;
-}
 
-// 8 values -> fp16 hi, lo (= v - hi) and hi' (= hi * 2^-11), each packed as one 16-byte vector
-__device__ __forceinline__ void split8(const float (&v)[8], uint4 &h, uint4 &l, uint4 &hs) {
-    uint32_t hh[4], ll[4], ss[4];
-    const __half2 scale = __float2half2_rn(0.00048828125f);     // 2^-11
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const __half2 hp = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-        const float2 hf = __half22float2(hp);
-        const __half2 lp = __floats2half2_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
-        const __half2 sp = __hmul2(hp, scale);
-        hh[i] = *reinterpret_cast<const uint32_t *>(&hp);
-        ll[i] = *reinterpret_cast<const uint32_t *>(&lp);
-        ss[i] = *reinterpret_cast<const uint32_t *>(&sp);
-    }
-    h = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-    l = make_uint4(ll[0], ll[1], ll[2], ll[3]);
-    hs = make_uint4(ss[0], ss[1], ss[2], ss[3]);
-}
 
 __device__ __forceinline__ int find_seg(const SegDesc *segs, int n_segs, int tile) {
     int lo = 0, hi = n_segs - 1;
@@ -182,14 +146,86 @@ __device__ __forceinline__ int find_seg(const SegDesc *segs, int n_segs, int til
     return lo;
 }
 
+// ------------------------------------------------------------------------- shared helpers -----
+// one lane of the (converged) warp; the compiler treats the guarded region as single-threaded, so warp-uniform
+// operands of tcgen05 instructions need no per-value election loop
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ __half2 u32_as_h2(uint32_t u) { return *reinterpret_cast<__half2 *>(&u); }
+__device__ __forceinline__ uint32_t h2_as_u32(__half2 h) { return *reinterpret_cast<uint32_t *>(&h); }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint4 &lo, const uint4 &hi) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+
+
 // ------------------------------------------------------------------------- anchor kernel -------
-// One task = NA consecutive anchor frames (frames 64*i) of one segment x one 128-bin range.
-__global__ void __launch_bounds__(TC_THREADS, 1)
-anchor_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, const int *__restrict__ task_seg,
-                 const int *__restrict__ task_first, const void *__restrict__ pcm, int dtype, int channels,
-                 float2 *__restrict__ anchors) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ uint64_t bar;
+// Anchors: the rectangular-window DFT of every 64th frame, R_a[k] = sum over the N/2 folded sample pairs.
+// One CTA = AN consecutive anchors of one segment x one 128-bin range: a GEMM with M = 128 bins, N = AN anchors,
+// K = N/2 pairs, streamed in k-blocks of AKB pairs through a two-stage shared-memory ring:
+//   builder warps (8)  PCM16 straight from global memory (prefetched one k-block ahead) -> byte-plane fp16 B
+//                      operand (same exact hi/lo split as the slide kernel); one elected thread also starts the
+//                      cp.async.bulk of the k-block's pre-laid-out twiddle block (A operand)
+//   MMA warp (1)       8 x tcgen05.mma per k-step (4 hi/lo products x cos/sin), accumulators in TMEM.  The hi x hi
+//                      products are integers (twiddle x 2^11 times a byte-plane sum) and get an accumulator of
+//                      their own, where fp32 addition is exact up to 2^24; the three small products (2^-8 .. 2^-19
+//                      of the first) go to a second one, so they are not absorbed by the large partial sums
+// Epilogue: thread = bin, add the two accumulators, rotate to the frame-start phase reference, store float2.
+constexpr int AN = 128;                 // anchors per task (MMA N)
+constexpr int AKB = 32;                 // pairs per k-block (2 k-steps)
+constexpr int A_BUILD_WARPS = 8;
+constexpr int A_THREADS = 32 * (A_BUILD_WARPS + 1);
+constexpr int A_MAT_BYTES = 128 * AKB * 2;          // one [128 x AKB] fp16 matrix (A: bins, B: anchors)
+constexpr int A_STAGE_BYTES = 8 * A_MAT_BYTES;      // 4 twiddle + 4 sample matrices
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(A_THREADS, 1)
+anchor_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, const int *__restrict__ task_seg,
+                 const int *__restrict__ task_first, const short *__restrict__ pcm, float2 *__restrict__ anchors) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t full_a[2], full_b[2], empty[2], done;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int range = blockIdx.y;
@@ -198,113 +234,152 @@ anchor_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, const
     const SegDesc sd = segs[seg_idx];
     const int n_anch_seg = (sd.n_frames + GF - 1) / GF + 1;
     const long long anchor_base = (long long)sd.group0 + seg_idx;      // global index of the segment's anchor 0
-
-    unsigned char *sA = smem_raw;                                   // KS x 4 x [128 x 16]  = 64 KB, stage-contiguous
-    unsigned char *sB = smem_raw + (size_t)KS * 4 * 128 * 16 * 2;   // 6 x [NA x 64]
-    constexpr int A_STAGE_BYTES = KS * 4 * 128 * 16 * 2;
-    constexpr int B_MAT_BYTES = NA * KS * 16 * 2;
+    const int n_kb = P.n_stages;
 
     if (warp == 0) tmem_alloc(&tmem_base_s, 512);
-    if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) { mbar_init(&full_a[i], 1); mbar_init(&full_b[i], A_BUILD_WARPS); mbar_init(&empty[i], 1); }
+        mbar_init(&done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
-    const uint32_t idesc = make_idesc(128, NA);
-    const int N = P.N, half = N / 2;
 
-    for (int st = 0; st < P.n_stages; ++st) {
-        // ---- A stage: straight 16-byte copies of the pre-laid-out twiddle block -------------------
-        const uint4 *ga = reinterpret_cast<const uint4 *>(
-            reinterpret_cast<const unsigned char *>(P.a_anchor) + ((size_t)range * P.n_stages + st) * A_STAGE_BYTES);
-        uint4 *da = reinterpret_cast<uint4 *>(sA);
-        for (int i = tid; i < A_STAGE_BYTES / 16; i += TC_THREADS) da[i] = __ldg(ga + i);
-        // ---- B stage: thread = (anchor a, group of 8 pairs) --------------------------------------
-        {
-            const int a = tid % NA, jg = tid / NA;                // jg in [0, 8): pairs 8*jg .. 8*jg+7 of this stage
-            const int ai = first + a;
-            float fp[8], fm[8];
-            const long long f0 = (long long)ai * GF * P.hop - half;   // segment-relative start of the anchor frame
-            const bool live = ai < n_anch_seg;
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-                const int j = st * (KS * 16) + jg * 8 + jj;
-                float hi = 0.f, lo = 0.f;
-                if (live && j < P.npN) {
-                    const long long shi = f0 + half + j, slo = f0 + half - 1 - j;
-                    if (shi >= 0 && shi < sd.n_samples) hi = load_scaled(pcm, dtype, channels, sd.pcm_start + shi);
-                    if (slo >= 0 && slo < sd.n_samples) lo = load_scaled(pcm, dtype, channels, sd.pcm_start + slo);
-                }
-                fp[jj] = hi + lo;
-                fm[jj] = hi - lo;
-            }
-            uint4 h, l, hs;
-            const size_t o = umma_off(a, jg * 8, KS * 16);
-            split8(fp, h, l, hs);
-            *reinterpret_cast<uint4 *>(sB + 0 * B_MAT_BYTES + o) = h;
-            *reinterpret_cast<uint4 *>(sB + 1 * B_MAT_BYTES + o) = l;
-            *reinterpret_cast<uint4 *>(sB + 2 * B_MAT_BYTES + o) = hs;
-            split8(fm, h, l, hs);
-            *reinterpret_cast<uint4 *>(sB + 3 * B_MAT_BYTES + o) = h;
-            *reinterpret_cast<uint4 *>(sB + 4 * B_MAT_BYTES + o) = l;
-            *reinterpret_cast<uint4 *>(sB + 5 * B_MAT_BYTES + o) = hs;
-        }
-        fence_async_smem();
-        __syncthreads();
-        if (tid == 0) {
+    if (warp == A_BUILD_WARPS) {
+        // ================================ MMA issuer ===================================================
+        const uint32_t idesc = make_idesc(128, AN);
+        constexpr uint32_t SBO = (AKB / 8) * 128;
+        for (int kb = 0; kb < n_kb; ++kb) {
+            const int s = kb & 1, ph = (kb >> 1) & 1;
+            mbar_wait(&full_a[s], ph);
+            mbar_wait(&full_b[s], ph);
             tc_fence_after();
-            const int part = st % NP;
-            const uint32_t d_cos = tmem_base + part * (2 * NA), d_sin = d_cos + NA;
-            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-            constexpr uint32_t A_MAT = 128 * KS * 16 * 2;          // one of the 4 A matrices of the stage
-            constexpr uint32_t SBO = (KS * 16 / 8) * 128;
+            if (elect_one()) {
+                const uint32_t a0 = smem_u32(smem_raw + (size_t)s * A_STAGE_BYTES), b0 = a0 + 4 * A_MAT_BYTES;
+                const uint32_t d_cos = tmem_base, d_sin = d_cos + AN;            // hi x hi (integer-valued) sums
+                const uint32_t e_cos = tmem_base + 2 * AN, e_sin = e_cos + AN;   // the small products
 #pragma unroll
-            for (int kk = 0; kk < KS; ++kk) {
-                const uint32_t acc = (st >= NP || kk > 0) ? 1u : 0u;
-                const uint32_t ko = kk * 256;
-                const uint64_t ach = make_desc(a0 + 0 * A_MAT + ko, 128, SBO), acl = make_desc(a0 + 1 * A_MAT + ko, 128, SBO);
-                const uint64_t ash = make_desc(a0 + 2 * A_MAT + ko, 128, SBO), asl = make_desc(a0 + 3 * A_MAT + ko, 128, SBO);
-                const uint64_t bph = make_desc(b0 + 0 * B_MAT_BYTES + ko, 128, SBO), bpl = make_desc(b0 + 1 * B_MAT_BYTES + ko, 128, SBO);
-                const uint64_t bps = make_desc(b0 + 2 * B_MAT_BYTES + ko, 128, SBO), bmh = make_desc(b0 + 3 * B_MAT_BYTES + ko, 128, SBO);
-                const uint64_t bml = make_desc(b0 + 4 * B_MAT_BYTES + ko, 128, SBO), bms = make_desc(b0 + 5 * B_MAT_BYTES + ko, 128, SBO);
-                umma_f16(d_cos, ach, bph, idesc, acc);
-                umma_f16(d_cos, ach, bpl, idesc, 1u);
-                umma_f16(d_cos, acl, bps, idesc, 1u);
-                umma_f16(d_sin, ash, bmh, idesc, acc);
-                umma_f16(d_sin, ash, bml, idesc, 1u);
-                umma_f16(d_sin, asl, bms, idesc, 1u);
+                for (int kk = 0; kk < AKB / 16; ++kk) {
+                    const uint32_t acc = (kb > 0 || kk > 0) ? 1u : 0u, ko = kk * 256;
+                    const uint64_t ach = make_desc(a0 + 0 * A_MAT_BYTES + ko, 128, SBO), acl = make_desc(a0 + 1 * A_MAT_BYTES + ko, 128, SBO);
+                    const uint64_t ash = make_desc(a0 + 2 * A_MAT_BYTES + ko, 128, SBO), asl = make_desc(a0 + 3 * A_MAT_BYTES + ko, 128, SBO);
+                    const uint64_t bph = make_desc(b0 + 0 * A_MAT_BYTES + ko, 128, SBO), bpl = make_desc(b0 + 1 * A_MAT_BYTES + ko, 128, SBO);
+                    const uint64_t bmh = make_desc(b0 + 2 * A_MAT_BYTES + ko, 128, SBO), bml = make_desc(b0 + 3 * A_MAT_BYTES + ko, 128, SBO);
+                    umma_f16(d_cos, ach, bph, idesc, acc);
+                    umma_f16(d_sin, ash, bmh, idesc, acc);
+                    umma_f16(e_cos, ach, bpl, idesc, acc);
+                    umma_f16(e_sin, ash, bml, idesc, acc);
+                    umma_f16(e_cos, acl, bph, idesc, 1u);
+                    umma_f16(e_sin, asl, bmh, idesc, 1u);
+                    umma_f16(e_cos, acl, bpl, idesc, 1u);
+                    umma_f16(e_sin, asl, bml, idesc, 1u);
+                }
+                umma_commit(&empty[s]);
+                if (kb == n_kb - 1) umma_commit(&done);
             }
-            umma_commit(&bar);
+            __syncwarp();
         }
-        mbar_wait(&bar, st & 1);           // MMAs of this stage have consumed the shared-memory operands
-        tc_fence_after();
-    }
-
-    // ---- epilogue: thread = bin row (4 warps), sum the partials, rotate, store -------------------
-    if (warp < 4) {
-        const int row = warp * 32 + lane;
-        const uint32_t tl = tmem_base + ((uint32_t)(warp * 32) << 16);
-        float ac[NA], as[NA], v[32];
+    } else {
+        // ================================ builders: thread = (anchor a, 16 pairs of the k-block) ===========
+        const int a = tid & (AN - 1), half16 = tid >> 7;            // half16 in {0, 1}
+        const int ai = first + a;
+        const bool live = ai < n_anch_seg;
+        const long long c = (long long)ai * GF * P.hop;            // segment-relative index of the frame centre
+        const bool aligned = ((sd.pcm_start & 7) == 0) && ((reinterpret_cast<uintptr_t>(pcm) & 15) == 0) && (P.hop % 8 == 0 || (GF * P.hop) % 8 == 0);
+        uint32_t hi_w[8], lo_w[8];          // 16 samples above / below the centre for this thread's pairs, offset binary
+        auto load16 = [&](long long s0, uint32_t (&w)[8]) {         // samples s0 .. s0+15 (segment-relative)
+            if (live && aligned && s0 >= 0 && s0 + 16 <= sd.n_samples) {
+                const int4 *p4 = reinterpret_cast<const int4 *>(pcm + sd.pcm_start + s0);
+                const int4 v0 = __ldg(p4), v1 = __ldg(p4 + 1);
+                w[0] = (uint32_t)v0.x ^ 0x80008000u; w[1] = (uint32_t)v0.y ^ 0x80008000u; w[2] = (uint32_t)v0.z ^ 0x80008000u; w[3] = (uint32_t)v0.w ^ 0x80008000u;
+                w[4] = (uint32_t)v1.x ^ 0x80008000u; w[5] = (uint32_t)v1.y ^ 0x80008000u; w[6] = (uint32_t)v1.z ^ 0x80008000u; w[7] = (uint32_t)v1.w ^ 0x80008000u;
+            } else {
 #pragma unroll
-        for (int i = 0; i < NA; ++i) { ac[i] = 0.f; as[i] = 0.f; }
-        const int used = min(NP, P.n_stages);
-        for (int part = 0; part < used; ++part) {
-            tmem_ld32(tl + part * (2 * NA), v);
+                for (int i = 0; i < 8; ++i) {
+                    uint32_t u[2];
 #pragma unroll
-            for (int i = 0; i < NA; ++i) ac[i] += v[i];
-            tmem_ld32(tl + part * (2 * NA) + NA, v);
+                    for (int h = 0; h < 2; ++h) {
+                        const long long sx = s0 + 2 * i + h;
+                        u[h] = (live && sx >= 0 && sx < sd.n_samples) ? ((uint32_t)(uint16_t)__ldg(pcm + sd.pcm_start + sx) ^ 0x8000u) : 0x8000u;
+                    }
+                    w[i] = u[0] | (u[1] << 16);
+                }
+            }
+        };
+        auto prefetch = [&](int kb) {
+            const int j0 = kb * AKB + 16 * half16;                  // first pair of this thread in the k-block
+            load16(c + j0, hi_w);                                   // pair j <-> sample c + j
+            load16(c - j0 - 16, lo_w);                              //            and sample c - 1 - j
+        };
+        prefetch(0);
+        for (int kb = 0; kb < n_kb; ++kb) {
+            const int s = kb & 1, ph = (kb >> 1) & 1;
+            mbar_wait(&empty[s], ph ^ 1);                           // the MMAs of k-block kb-2 have consumed this stage
+            unsigned char *sA = smem_raw + (size_t)s * A_STAGE_BYTES, *sBm = sA + 4 * A_MAT_BYTES;
+            if (tid == 0) {
+                mbar_expect_tx(&full_a[s], 4 * A_MAT_BYTES);
+                bulk_g2s(sA, reinterpret_cast<const unsigned char *>(P.a_anchor) + ((size_t)range * n_kb + kb) * 4 * A_MAT_BYTES,
+                         4 * A_MAT_BYTES, &full_a[s]);
+            }
+            const int j0 = kb * AKB + 16 * half16;
 #pragma unroll
-            for (int i = 0; i < NA; ++i) as[i] += v[i];
+            for (int u = 0; u < 2; ++u) {                           // two units of 8 pairs
+                uint32_t ph4[4], pl4[4], mh4[4], ml4[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    // pairs j0 + 8u + 2q, +1: above the centre words hi_w[4u + q]; below: mirrored, word 7 - 4u - q reversed
+                    const uint32_t wa = hi_w[4 * u + q], wc = lo_w[7 - 4 * u - q];
+                    const __half2 ah = u32_as_h2(__byte_perm(wa, 0x64646464u, 0x4341)), al = u32_as_h2(__byte_perm(wa, 0x44444444u, 0x4240));
+                    const __half2 ch = u32_as_h2(__byte_perm(wc, 0x64646464u, 0x4143)), cl = u32_as_h2(__byte_perm(wc, 0x44444444u, 0x4042));
+                    // sums: (1024 + ua) + (1024 + uc) - 2304 = xa_h + xc_h (signed high bytes);  (4 + la) + (4 + lc) - 8 = la + lc
+                    uint32_t v0 = h2_as_u32(__hadd2(ah, __hsub2(ch, __float2half2_rn(2304.0f))));
+                    uint32_t v1 = h2_as_u32(__hadd2(al, __hsub2(cl, __float2half2_rn(8.0f))));
+                    uint32_t v2 = h2_as_u32(__hsub2(ah, ch)), v3 = h2_as_u32(__hsub2(al, cl));
+                    const int j = j0 + 8 * u + 2 * q;
+                    const uint32_t keep = (j < P.npN ? 0x0000ffffu : 0u) | (j + 1 < P.npN ? 0xffff0000u : 0u);
+                    ph4[q] = v0 & keep; pl4[q] = v1 & keep; mh4[q] = v2 & keep; ml4[q] = v3 & keep;
+                }
+                const size_t o = umma_off(a, 16 * half16 + 8 * u, AKB);
+                *reinterpret_cast<uint4 *>(sBm + 0 * A_MAT_BYTES + o) = make_uint4(ph4[0], ph4[1], ph4[2], ph4[3]);
+                *reinterpret_cast<uint4 *>(sBm + 1 * A_MAT_BYTES + o) = make_uint4(pl4[0], pl4[1], pl4[2], pl4[3]);
+                *reinterpret_cast<uint4 *>(sBm + 2 * A_MAT_BYTES + o) = make_uint4(mh4[0], mh4[1], mh4[2], mh4[3]);
+                *reinterpret_cast<uint4 *>(sBm + 3 * A_MAT_BYTES + o) = make_uint4(ml4[0], ml4[1], ml4[2], ml4[3]);
+            }
+            if (kb + 1 < n_kb) prefetch(kb + 1);
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_b[s]);
         }
-        const float2 rot = P.rot[range * 128 + row];          // e^{-i theta (N-1)/2} * 2^-12 = (c, -s) form below
+        // ---- epilogue: thread = bin row (warps 0..3), add the two accumulators, rotate, store ---------------
+        if (warp < 4) {
+            mbar_wait(&done, 0);
+            tc_fence_after();
+            const int row = warp * 32 + lane;
+            const uint32_t tl = tmem_base + ((uint32_t)(warp * 32) << 16);
+            const float2 rot = P.rot[range * 128 + row];          // e^{-i theta (N-1)/2} x scale
+            for (int c0 = 0; c0 < AN; c0 += 32) {
+                float ac[32], as[32], v[32];
+                tmem_ld32(tl + c0, ac);
+                tmem_ld32(tl + AN + c0, as);
+                tmem_ld32(tl + 2 * AN + c0, v);
 #pragma unroll
-        for (int a = 0; a < NA; ++a) {
-            const int ai = first + a;
-            if (ai < n_anch_seg) {
-                // R = (c0 - i s0)(A - iB)
-                const float rr = rot.x * ac[a] - rot.y * as[a];
-                const float ri = -(rot.x * as[a] + rot.y * ac[a]);
-                anchors[(anchor_base + ai) * (P.n_ranges * 128) + range * 128 + row] = make_float2(rr, ri);
+                for (int i = 0; i < 32; ++i) ac[i] += v[i];
+                tmem_ld32(tl + 3 * AN + c0, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) as[i] += v[i];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int an = first + c0 + i;
+                    if (an < n_anch_seg) {
+                        // R = (c0 - i s0)(A - iB)
+                        const float rr = rot.x * ac[i] - rot.y * as[i];
+                        const float ri = -(rot.x * as[i] + rot.y * ac[i]);
+                        anchors[(anchor_base + an) * (P.n_ranges * 128) + range * 128 + row] = make_float2(rr, ri);
+                    }
+                }
             }
         }
     }
@@ -334,47 +409,13 @@ anchor_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, const
 constexpr int CF = 32;                      // frames per chain
 constexpr int ST_LD = CF + 2;               // float2 per bin row of the R stage: 272 B pitch, conflict-free STS.128
 constexpr int ROWS_PER_EWARP = 32;          // emit rows per warp
-constexpr int TM_A_COL = 256;               // TMEM: accumulators in [0, 256), twiddles from column 256
+constexpr int TM_ACC_PER_GROUP = 4 * CF;    // big (cos, sin) and small (cos, sin) accumulators
+constexpr int NK_T = 4;                     // k-steps whose twiddles live in TMEM; a fifth is read from shared memory
 constexpr int TM_COLS = 512;
 
-// one lane of the (converged) warp; the compiler treats the guarded region as single-threaded, so warp-uniform
-// operands of tcgen05 instructions need no per-value election loop
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                 : "r"(taddr) : "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint4 &lo, const uint4 &hi) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                 ::"r"(taddr), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// D[tmem] (+)= A[tmem] * B[smem]
-__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
-}
-
 // 8 values -> fp16 hi and lo (= v - hi), each packed as one 16-byte vector
 __device__ __forceinline__ void split8_hl(const float (&v)[8], uint4 &h, uint4 &l) {
     uint32_t hh[4], ll[4];
@@ -389,8 +430,6 @@ __device__ __forceinline__ void split8_hl(const float (&v)[8], uint4 &h, uint4 &
     h = make_uint4(hh[0], hh[1], hh[2], hh[3]);
     l = make_uint4(ll[0], ll[1], ll[2], ll[3]);
 }
-__device__ __forceinline__ __half2 u32_as_h2(uint32_t u) { return *reinterpret_cast<__half2 *>(&u); }
-__device__ __forceinline__ uint32_t h2_as_u32(__half2 h) { return *reinterpret_cast<uint32_t *>(&h); }
 // two offset-binary PCM16 samples packed in one word -> floats 2^9 + u 2^-14 (differences of two such are exact)
 __device__ __forceinline__ void unpack2(uint32_t w, float &f0, float &f1) {
     f0 = __uint_as_float(__byte_perm(w, 0x44000000u, 0x7610));
@@ -459,6 +498,7 @@ slide_ws_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int to
     unsigned char *sB = gbase;                                           // 4 x [32 x KP] fp16
     float2 *stage = reinterpret_cast<float2 *>(gbase + 4 * b_mat);       // [128][ST_LD]
     uint16_t *buf16 = reinterpret_cast<uint16_t *>(stage + 128 * ST_LD); // samples of one chain, offset binary
+    unsigned char *sAt = smem_raw + (size_t)G * grp_bytes;               // twiddles of the k-steps beyond NK_T: 4 x [128 x 16]
 
     if (is_worker) {   // B zeroed once: the K padding columns are never written again
         uint4 *db = reinterpret_cast<uint4 *>(sB);
@@ -478,8 +518,9 @@ slide_ws_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int to
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
-    const uint32_t tmem_a = tmem_base + TM_A_COL;                  // 4 matrices x (KP / 2) columns
-    // ---- twiddles into TMEM: thread = bin row = TMEM lane, 16 fp16 (one k-step) = 8 columns per store ----
+    const uint32_t tmem_a = tmem_base + G * TM_ACC_PER_GROUP;      // 4 matrices x NK_T x 8 columns
+    // ---- twiddles: thread = bin row.  k-steps < NK_T into the row's TMEM lane (16 fp16 = 8 columns per store),
+    //      the rest into shared memory in UMMA K-major layout ---------------------------------------------
     if (warp < 4) {
         const uint4 *grow = reinterpret_cast<const uint4 *>(
             reinterpret_cast<const unsigned char *>(P.a_slide) + ((size_t)range * 128 + gt) * 4 * KP * 2);
@@ -487,9 +528,16 @@ slide_ws_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int to
         for (int m = 0; m < 4; ++m)
             for (int kk = 0; kk < nk; ++kk) {
                 const uint4 lo = __ldg(grow + (m * KP + kk * 16) / 8), hi = __ldg(grow + (m * KP + kk * 16) / 8 + 1);
-                tmem_st8(tl + (uint32_t)(m * (KP / 2) + kk * 8), lo, hi);
+                if (kk < NK_T) {
+                    tmem_st8(tl + (uint32_t)(m * (NK_T * 8) + kk * 8), lo, hi);
+                } else {
+                    unsigned char *d = sAt + (size_t)m * 128 * 16 * 2 * (nk - NK_T);
+                    *reinterpret_cast<uint4 *>(d + umma_off(gt, (kk - NK_T) * 16, 16 * (nk - NK_T))) = lo;
+                    *reinterpret_cast<uint4 *>(d + umma_off(gt, (kk - NK_T) * 16 + 8, 16 * (nk - NK_T))) = hi;
+                }
             }
         tmem_st_wait();
+        fence_async_smem();
     }
     tc_fence_before();
     __syncthreads();
@@ -500,8 +548,6 @@ slide_ws_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int to
     const int n_iters = first < total_chains ? (total_chains - first + cstride - 1) / cstride : 0;
     const uint32_t idesc = make_idesc(128, CF);
     const uint32_t SBO = (uint32_t)(KP / 8) * 128;
-    const uint32_t kp2 = (uint32_t)KP / 2;
-
     if (is_mma_warp) {
         // ================================ MMA issuer (all groups, round robin) =========================
         // b_ready[g] (4 warp arrivals) says: B operand of group g's next chain is in shared memory AND the group
@@ -518,20 +564,39 @@ slide_ws_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int to
                     const uint32_t b0 = smem_u32(smem_raw + (size_t)gg * grp_bytes);
                     const uint64_t dph = make_desc(b0 + 0 * (uint32_t)b_mat, 128, SBO), dpl = make_desc(b0 + 1 * (uint32_t)b_mat, 128, SBO);
                     const uint64_t dmh = make_desc(b0 + 2 * (uint32_t)b_mat, 128, SBO), dml = make_desc(b0 + 3 * (uint32_t)b_mat, 128, SBO);
-                    const uint32_t dcol = tmem_base + (uint32_t)gg * (2 * CF);
+                    // Two accumulators per (cos, sin): the hi x hi products are integers (twiddle x 2^11 times a byte-plane
+                    // value) and fp32 adds them exactly below 2^24; the three small products (2^-8 .. 2^-19 of those) get
+                    // their own accumulator instead of being absorbed, truncated, into the large partial sums.
+                    const uint32_t big_c = tmem_base + (uint32_t)gg * TM_ACC_PER_GROUP, big_s = big_c + CF;
+                    const uint32_t sml_c = big_c + 2 * CF, sml_s = big_c + 3 * CF;
 #pragma unroll 1
                     for (int kk = 0; kk < nk; ++kk) {
                         const uint64_t ko = (uint64_t)(kk * 16);        // 256 B per k-step in the 16-byte address field
-                        const uint32_t acc = kk > 0 ? 1u : 0u, ka = tmem_a + kk * 8;
-                        // (cos_h + cos_l)(p_hi + p_lo) and (sin_h + sin_l)(m_hi + m_lo); the two accumulators alternate
-                        umma_f16_ts(dcol, ka + 0 * kp2, dph + ko, idesc, acc);
-                        umma_f16_ts(dcol + CF, ka + 2 * kp2, dmh + ko, idesc, acc);
-                        umma_f16_ts(dcol, ka + 0 * kp2, dpl + ko, idesc, 1u);
-                        umma_f16_ts(dcol + CF, ka + 2 * kp2, dml + ko, idesc, 1u);
-                        umma_f16_ts(dcol, ka + 1 * kp2, dph + ko, idesc, 1u);
-                        umma_f16_ts(dcol + CF, ka + 3 * kp2, dmh + ko, idesc, 1u);
-                        umma_f16_ts(dcol, ka + 1 * kp2, dpl + ko, idesc, 1u);
-                        umma_f16_ts(dcol + CF, ka + 3 * kp2, dml + ko, idesc, 1u);
+                        const uint32_t acc = kk > 0 ? 1u : 0u;
+                        if (kk < NK_T) {
+                            const uint32_t ka = tmem_a + kk * 8, mt = NK_T * 8;    // cos_h, cos_l, sin_h, sin_l at ka + {0,1,2,3} mt
+                            umma_f16_ts(big_c, ka + 0 * mt, dph + ko, idesc, acc);
+                            umma_f16_ts(big_s, ka + 2 * mt, dmh + ko, idesc, acc);
+                            umma_f16_ts(sml_c, ka + 0 * mt, dpl + ko, idesc, acc);
+                            umma_f16_ts(sml_s, ka + 2 * mt, dml + ko, idesc, acc);
+                            umma_f16_ts(sml_c, ka + 1 * mt, dph + ko, idesc, 1u);
+                            umma_f16_ts(sml_s, ka + 3 * mt, dmh + ko, idesc, 1u);
+                            umma_f16_ts(sml_c, ka + 1 * mt, dpl + ko, idesc, 1u);
+                            umma_f16_ts(sml_s, ka + 3 * mt, dml + ko, idesc, 1u);
+                        } else {
+                            const uint32_t a0 = smem_u32(sAt) + (uint32_t)(kk - NK_T) * 256, am = 128 * 16 * 2 * (uint32_t)(nk - NK_T);
+                            const uint32_t sbo_a = (uint32_t)(16 * (nk - NK_T) / 8) * 128;
+                            const uint64_t ach = make_desc(a0 + 0 * am, 128, sbo_a), acl = make_desc(a0 + 1 * am, 128, sbo_a);
+                            const uint64_t ash = make_desc(a0 + 2 * am, 128, sbo_a), asl = make_desc(a0 + 3 * am, 128, sbo_a);
+                            umma_f16(big_c, ach, dph + ko, idesc, acc);
+                            umma_f16(big_s, ash, dmh + ko, idesc, acc);
+                            umma_f16(sml_c, ach, dpl + ko, idesc, acc);
+                            umma_f16(sml_s, ash, dml + ko, idesc, acc);
+                            umma_f16(sml_c, acl, dph + ko, idesc, 1u);
+                            umma_f16(sml_s, asl, dmh + ko, idesc, 1u);
+                            umma_f16(sml_c, acl, dpl + ko, idesc, 1u);
+                            umma_f16(sml_s, asl, dml + ko, idesc, 1u);
+                        }
                     }
                     umma_commit(&acc_full[gg]);
                 }
@@ -611,7 +676,7 @@ slide_ws_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int to
     const int njg = (P.npH + 7) / 8;
     const int n = gt & 31;                                         // build: frame column of this thread
     const int base = PADF + P.off + n * hop;
-    const uint32_t acc_col = tmem_base + (uint32_t)g * (2 * CF);
+    const uint32_t acc_col = tmem_base + (uint32_t)g * TM_ACC_PER_GROUP;
     const uint32_t lane_sel = (uint32_t)(wq * 32) << 16;
     const float2 cf = P.cf[range * 128 + gt];
     const float2 gF = P.gf[range * 128 + gt], gB = P.gb[range * 128 + gt];
@@ -703,45 +768,55 @@ slide_ws_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int to
         const float2 anc = anc_next;
         if (it + 1 < n_iters) anc_next = anchor_of(chain + cstride);
         WS_MARK(0);
-        // ---- recur: accumulator -> registers -> 32-step recurrence -> stage ---------------------------
+        // ---- recur: accumulators -> registers -> 32-step recurrence -> stage, 16 columns at a time ----------
         {
-            float gc[CF], gs[CF];
             mbar_wait(&acc_full[g], it & 1);
             WS_MARK(1);
             tc_fence_after();
-            tmem_ld32_nowait(acc_col + lane_sel, gc);
-            tmem_ld32_nowait(acc_col + lane_sel + CF, gs);
-            tmem_ld_wait();
-            tc_fence_before();
             float4 *st4 = reinterpret_cast<float4 *>(stage + (size_t)gt * ST_LD);
             float Rr = anc.x, Ri = anc.y;
-            if (fwd) {
-                // frames t0 .. t0+31 ; column i+1 from column i with D_i
-                float pr = Rr, pi = Ri;
+            float pr = Rr, pi = Ri;
 #pragma unroll
-                for (int i = 0; i < CF - 1; ++i) {
-                    const float gr = gF.x * gc[i] + gF.y * gs[i];
-                    const float gi = gF.y * gc[i] - gF.x * gs[i];
-                    const float nr = fmaf(cf.x, Rr, fmaf(-cf.y, Ri, gr));
-                    const float ni = fmaf(cf.x, Ri, fmaf(cf.y, Rr, gi));
-                    Rr = nr; Ri = ni;
-                    if (i & 1) { pr = Rr; pi = Ri; }                       // column i+1 even: first of a pair
-                    else st4[i >> 1] = make_float4(pr, pi, Rr, Ri);       // columns (i, i+1)
-                }
-            } else {
-                // frames t0+31 down to t0 ; column i from column i+1 with D_i ; column 32 is the anchor
-                float pr = 0.f, pi = 0.f;
+            for (int hh = 0; hh < 2; ++hh) {
+                const int c0 = fwd ? 16 * hh : 16 - 16 * hh;             // forward chains walk the columns up, backward ones down
+                float gc[16], gs[16], ec[16], es[16];
+                tmem_ld16_nowait(acc_col + lane_sel + c0, gc);
+                tmem_ld16_nowait(acc_col + lane_sel + CF + c0, gs);
+                tmem_ld16_nowait(acc_col + lane_sel + 2 * CF + c0, ec);
+                tmem_ld16_nowait(acc_col + lane_sel + 3 * CF + c0, es);
+                tmem_ld_wait();
 #pragma unroll
-                for (int i = CF - 1; i >= 0; --i) {
-                    const float gr = gB.y * gs[i] - gB.x * gc[i];
-                    const float gi = gB.x * gs[i] + gB.y * gc[i];
-                    const float nr = fmaf(cf.x, Rr, fmaf(cf.y, Ri, gr));
-                    const float ni = fmaf(cf.x, Ri, fmaf(-cf.y, Rr, gi));
-                    Rr = nr; Ri = ni;
-                    if (i & 1) { pr = Rr; pi = Ri; }                       // odd column: second of a pair
-                    else st4[i >> 1] = make_float4(Rr, Ri, pr, pi);       // columns (i, i+1)
+                for (int i = 0; i < 16; ++i) { gc[i] += ec[i]; gs[i] += es[i]; }
+                if (fwd) {
+                    // frames t0 .. t0+31 ; column c+1 from column c with D_c
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int c = c0 + i;
+                        if (c == CF - 1) break;
+                        const float gr = gF.x * gc[i] + gF.y * gs[i];
+                        const float gi = gF.y * gc[i] - gF.x * gs[i];
+                        const float nr = fmaf(cf.x, Rr, fmaf(-cf.y, Ri, gr));
+                        const float ni = fmaf(cf.x, Ri, fmaf(cf.y, Rr, gi));
+                        Rr = nr; Ri = ni;
+                        if (c & 1) { pr = Rr; pi = Ri; }                       // column c+1 even: first of a pair
+                        else st4[c >> 1] = make_float4(pr, pi, Rr, Ri);       // columns (c, c+1)
+                    }
+                } else {
+                    // frames t0+31 down to t0 ; column c from column c+1 with D_c ; column 32 is the anchor
+#pragma unroll
+                    for (int i = 15; i >= 0; --i) {
+                        const int c = c0 + i;
+                        const float gr = gB.y * gs[i] - gB.x * gc[i];
+                        const float gi = gB.x * gs[i] + gB.y * gc[i];
+                        const float nr = fmaf(cf.x, Rr, fmaf(cf.y, Ri, gr));
+                        const float ni = fmaf(cf.x, Ri, fmaf(-cf.y, Rr, gi));
+                        Rr = nr; Ri = ni;
+                        if (c & 1) { pr = Rr; pi = Ri; }                       // odd column: second of a pair
+                        else st4[c >> 1] = make_float4(Rr, Ri, pr, pi);       // columns (c, c+1)
+                    }
                 }
             }
+            tc_fence_before();
         }
         WS_MARK(2);
         named_bar_sync(bar_id, 128);        // stage complete; accumulator and B operand free (MMA(it) done, D loaded)
@@ -797,14 +872,7 @@ slide_ws_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int to
 using namespace nbm;
 
 namespace {
-// anchor tables: w = h + 2^-11 l   (the B side carries a 2^-11-scaled copy of its hi part)
-inline void put_split(std::vector<__half> &dst, size_t base_elems_h, size_t base_elems_l, size_t off_bytes, double w) {
-    const __half h = __float2half_rn((float)w);
-    const double rem = (w - (double)__half2float(h)) * 2048.0;
-    dst[base_elems_h + off_bytes / 2] = h;
-    dst[base_elems_l + off_bytes / 2] = __float2half_rn((float)rem);
-}
-// slide tables: 2^11 w = H + L, both at the same scale, so (H, L) x (hi, lo) needs no rescaled operand copy
+// twiddle tables: 2^11 w = H + L, both at the same scale, so (H, L) x (hi, lo) needs no rescaled operand copy
 inline void put_split_scaled(std::vector<__half> &dst, size_t base_elems_h, size_t base_elems_l, size_t off_bytes, double w) {
     const double ws = w * 2048.0;
     const __half h = __float2half_rn((float)ws);
@@ -817,7 +885,7 @@ int nbm::tc_plan_create(const nbm_frontend_params &p, TcPlan **out) {
     *out = nullptr;
     const int N = p.n_fft, hop = p.hop;
     const int npH = hop / 2, KP = ((npH + 15) / 16) * 16;
-    const bool ok = (N % 4 == 0) && (hop % 4 == 0) && TM_A_COL + 4 * (KP / 2) <= TM_COLS && hop >= 8 && p.n_bins <= 3 * BINS_PER_RANGE &&
+    const bool ok = (N % 4 == 0) && (hop % 4 == 0) && KP / 16 <= NK_T + 1 && hop >= 8 && p.n_bins <= 3 * BINS_PER_RANGE &&
                     p.low_idx >= 1 && N >= 2 * hop;
     if (!ok) return NBM_ERR_UNSUPPORTED;
     auto *pl = new TcPlan();
@@ -825,19 +893,18 @@ int nbm::tc_plan_create(const nbm_frontend_params &p, TcPlan **out) {
     k.N = N; k.hop = hop; k.low_idx = p.low_idx; k.n_bins = p.n_bins;
     k.n_ranges = (p.n_bins + BINS_PER_RANGE - 1) / BINS_PER_RANGE;
     k.npH = npH; k.KP = KP; k.nk = KP / 16;
-    k.npN = N / 2; k.n_stages = (k.npN + KS * 16 - 1) / (KS * 16);
+    k.npN = N / 2; k.n_stages = (k.npN + AKB - 1) / AKB;
     k.off = (4 - (npH % 4)) % 4;
     k.buf_len = ((PADF + k.off + CF * hop + N + 16 + 7) / 8) * 8;   // +16: masked tail pairs read past the last block
     k.min_level_sq = (float)(p.min_level * p.min_level);
     const int R = k.n_ranges, N2 = 2 * N;
 
     const size_t slide_elems = (size_t)R * 4 * 128 * KP;
-    const size_t anchor_elems = (size_t)R * k.n_stages * 4 * 128 * (KS * 16);
+    const size_t anchor_elems = (size_t)R * k.n_stages * 4 * 128 * AKB;
     std::vector<__half> a_slide(slide_elems, __float2half_rn(0.f)), a_anchor(anchor_elems, __float2half_rn(0.f));
     std::vector<float2> cf(R * 128), gf(R * 128), gb(R * 128), rot(R * 128);
     auto ang = [&](long long q) { return M_PI * (double)(q % N2) / (double)N; };
-    const double s12 = 1.0 / 4096.0;          // anchors: samples / 8, twiddles x 1
-    const double s18 = 1.0 / 262144.0;        // slides: byte planes (ep / 256), twiddles x 2^11
+    const double s18 = 1.0 / 262144.0;        // byte planes (value / 256) x twiddles x 2^11, samples / 32768
     for (int r = 0; r < R; ++r)
         for (int row = 0; row < 128; ++row) {
             const long long kbin = p.low_idx - 1 + (long long)r * BINS_PER_RANGE + row;
@@ -849,14 +916,14 @@ int nbm::tc_plan_create(const nbm_frontend_params &p, TcPlan **out) {
                 put_split_scaled(a_slide, rbase + 0 * KP, rbase + 1 * KP, (size_t)j * 2, cos(a));
                 put_split_scaled(a_slide, rbase + 2 * KP, rbase + 3 * KP, (size_t)j * 2, sin(a));
             }
-            const size_t amat = (size_t)128 * (KS * 16);
+            const size_t amat = (size_t)128 * AKB;
             for (int j = 0; j < k.npN; ++j) {
                 const double a = ang(kbin * (2 * j + 1));
-                const int st = j / (KS * 16), jj = j % (KS * 16);
+                const int st = j / AKB, jj = j % AKB;
                 const size_t base = ((size_t)r * k.n_stages + st) * 4 * amat;
-                const size_t o = umma_off(row, jj, KS * 16);
-                put_split(a_anchor, base + 0 * amat, base + 1 * amat, o, cos(a));
-                put_split(a_anchor, base + 2 * amat, base + 3 * amat, o, sin(a));
+                const size_t o = umma_off(row, jj, AKB);
+                put_split_scaled(a_anchor, base + 0 * amat, base + 1 * amat, o, cos(a));
+                put_split_scaled(a_anchor, base + 2 * amat, base + 3 * amat, o, sin(a));
             }
             const int i = r * 128 + row;
             double a = ang(kbin * 2 * hop);
@@ -866,7 +933,7 @@ int nbm::tc_plan_create(const nbm_frontend_params &p, TcPlan **out) {
             a = ang(kbin * (hop - 1));
             gb[i] = make_float2((float)(cos(a) * s18), (float)(sin(a) * s18));
             a = ang(kbin * (N - 1));
-            rot[i] = make_float2((float)(cos(a) * s12), (float)(sin(a) * s12));
+            rot[i] = make_float2((float)(cos(a) * s18), (float)(sin(a) * s18));
         }
     const size_t b_slide = align_up(slide_elems * 2, 256), b_anchor = align_up(anchor_elems * 2, 256);
     const size_t b_c = align_up((size_t)R * 128 * sizeof(float2), 256);
@@ -885,8 +952,9 @@ int nbm::tc_plan_create(const nbm_frontend_params &p, TcPlan **out) {
     k.gf = reinterpret_cast<const float2 *>(d + b_slide + b_anchor + b_c);
     k.gb = reinterpret_cast<const float2 *>(d + b_slide + b_anchor + 2 * b_c);
     k.rot = reinterpret_cast<const float2 *>(d + b_slide + b_anchor + 3 * b_c);
-    pl->smem_slide = WS_G * ((size_t)4 * CF * KP * 2 + (size_t)128 * ST_LD * 8 + (size_t)k.buf_len * 2);
-    pl->smem_anchor = (size_t)KS * 4 * 128 * 16 * 2 + (size_t)6 * NA * KS * 16 * 2;
+    pl->smem_slide = WS_G * ((size_t)4 * CF * KP * 2 + (size_t)128 * ST_LD * 8 + (size_t)k.buf_len * 2) +
+                     (size_t)4 * 128 * 16 * 2 * std::max(0, k.nk - NK_T);
+    pl->smem_anchor = (size_t)2 * A_STAGE_BYTES + 128;
     int dev = 0, sms = 0, max_smem = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -929,7 +997,7 @@ extern "C" int nbm_debug_ws_timing(unsigned long long *out, int reset) {
 }
 #endif
 
-int nbm::tc_anchor_group() { return NA; }
+int nbm::tc_anchor_group() { return AN; }
 int nbm::tc_n_ranges(const TcPlan *pl) { return pl->p.n_ranges; }
 int nbm::tc_bins_per_range() { return BINS_PER_RANGE; }
 int nbm::tc_chain_frames() { return CF; }
@@ -942,8 +1010,8 @@ int nbm::tc_launch(const TcPlan *pl, const SegDesc *d_segs, int n_segs, int tota
     const TcParams &k = pl->p;
     float2 *anchors = reinterpret_cast<float2 *>(d_anchors);
     dim3 ga((unsigned)n_tasks, (unsigned)k.n_ranges);
-    anchor_tc_kernel<<<ga, TC_THREADS, pl->smem_anchor, stream>>>(k, d_segs, n_segs, d_task_seg, d_task_first, d_pcm,
-                                                                  dtype, channels, anchors);
+    anchor_tc_kernel<<<ga, A_THREADS, pl->smem_anchor, stream>>>(k, d_segs, d_task_seg, d_task_first,
+                                                                 reinterpret_cast<const short *>(d_pcm), anchors);
     const int total_chains = 2 * total_tiles;
     const int grid = std::min(pl->grid_slide, std::max(1, total_chains) * k.n_ranges);
     slide_ws_kernel<<<(grid / k.n_ranges) * k.n_ranges, WS_THREADS, pl->smem_slide, stream>>>(
