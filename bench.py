@@ -29,6 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 BYTES_PER_FRAME = 264 + 1500          # 132 int16 samples in + 375 fp32 bins out
+TRAFFIC_BYTES_PER_FRAME = 1777        # measured DRAM bytes per frame of slide_ws_kernel (profiles/r01_slide_ws_kernel_ncu.txt)
 SAMPLE_RATE = 44100
 
 
@@ -217,7 +218,8 @@ def run_b200(a):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    stft_ms, tile_ms, runs = plan.get_profile()
+    kern_ms, runs = plan.get_profile_kernels()
+    stft_ms, tile_ms = kern_ms["stft"], kern_ms["tile"]
     plan.set_profiling(False)
     clocks = sampler.stop()
 
@@ -227,11 +229,10 @@ def run_b200(a):
         host = torch.empty(pcm.shape, dtype=torch.int16).pin_memory()
         host.copy_(pcm.cpu())
         mm_host = torch.empty((a.clips, 2), dtype=torch.float32).pin_memory()
-        dpcm = torch.empty_like(pcm)
 
         def e2e_step():
-            dpcm.copy_(host, non_blocking=True)
-            _, _, mm = plan.run_batch(dpcm, offs, out=tiles)
+            # public API: pinned host PCM16 -> chunked H2D on a side stream overlapped with the front-end
+            _, _, mm = plan.run_batch_from_host(host, offs, out=tiles)
             mm_host.copy_(mm, non_blocking=True)
 
         for _ in range(max(1, a.warmup // 2)):
@@ -246,7 +247,7 @@ def run_b200(a):
         barrier()
         e2e_ms = f0.elapsed_time(f1) / k
         e2e = (e2e_ms, host.numel() * 2, mm_host.numel() * 4)
-        del host, dpcm
+        del host
 
     # ---- parity spot check on this very data (first clip) against the oracle --------------------
     parity = None
@@ -259,8 +260,8 @@ def run_b200(a):
                   "rms": float(np.sqrt((err ** 2).mean()))}
 
     # ---- gather: max time over ranks, totals (NCCL all_gather of a small vector) ----------------
-    stats = torch.tensor([ms, frames, audio_hours * 1e6, stft_ms, tile_ms, e2e[0] if e2e else 0.0],
-                         dtype=torch.float64, device=dev)
+    stats = torch.tensor([ms, frames, audio_hours * 1e6, stft_ms, tile_ms, e2e[0] if e2e else 0.0,
+                          kern_ms["anchor"], kern_ms["minmax"]], dtype=torch.float64, device=dev)
     if world > 1:
         allst = [torch.empty_like(stats) for _ in range(world)]
         dist.all_gather(allst, stats)
@@ -288,11 +289,18 @@ def run_b200(a):
                    "l2": "inputs (%.1f GB) and outputs (%.1f GB) per step exceed L2 (126 MB); no flush needed"
                          % (pcm.numel() * 2 / 1e9, tiles.numel() * 4 / 1e9),
                    "sharding": "files sharded across ranks, no data-path collective"},
-        "roofline": {"bound": "hbm", "kernel": "stft_db_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "algorithmic_bytes_per_frame": BYTES_PER_FRAME, "frames_per_launch": frames,
-                     "ms_per_launch": stft_per_launch_ms,
-                     "tile_kernel_ms_per_launch": float(allst[0, 4]) / max(runs, 1)},
+        "roofline": {"bound": "hbm", "kernel": "slide_ws_kernel" if plan.impl == "tcgen05" else "stft_db_kernel",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": TRAFFIC_BYTES_PER_FRAME * frames if plan.impl == "tcgen05" else None,
+                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per frame "
+                                       "(profiles/), scaled to this launch",
+                     "peak_source": peak_src,
+                     "algorithmic_bytes_per_frame": BYTES_PER_FRAME, "algorithmic_bytes_per_launch": BYTES_PER_FRAME * frames,
+                     "frames_per_launch": frames, "ms_per_launch": stft_per_launch_ms,
+                     "other_kernels_ms_per_launch": {"anchor_tc_kernel": float(allst[0, 6]) / max(runs, 1),
+                                                     "refine_minmax_kernel": float(allst[0, 7]) / max(runs, 1),
+                                                     "tile_kernel": float(allst[0, 4]) / max(runs, 1)},
+                     "note": "the kernel is instruction-issue / shared-memory bound, not HBM bound (DESIGN.md 3)"},
         "clocks": clocks,
         "gpu_launches": 4 * a.steps,
         "parity": parity,
@@ -301,7 +309,8 @@ def run_b200(a):
         e_ms = float(allst[:, 5].max())
         line["e2e"] = {"value": total_hours / (e_ms / 1e3), "unit": "audio-hours/s", "h2d_bytes_per_step": e2e[1],
                        "d2h_bytes_per_step": e2e[2], "ms_per_step": e_ms,
-                       "note": "pinned host PCM16 -> H2D -> front-end -> tiles stay on the device for the detector; "
+                       "note": "FrontendPlan.run_batch_from_host: pinned host PCM16 -> H2D in 64-file chunks on a side stream, "
+                               "overlapped with the front-end; tiles stay on the device for the detector; "
                                "per-file (s_min, s_max) read back"}
     if not a.no_cpu_baseline:
         cores = os.cpu_count() or 1

@@ -469,8 +469,8 @@ struct nbm_frontend_plan {
     cudaEvent_t staged = nullptr;
     // optional per-kernel timing (nbm_frontend_set_profiling)
     bool profiling = false;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    double acc_ms[2] = {0.0, 0.0};
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // anchors | slides (or the CUDA-core STFT) | min/max | tiles
+    double acc_ms[4] = {0.0, 0.0, 0.0, 0.0};
     long long acc_runs = 0;
     bool ev_pending = false;
 };
@@ -685,11 +685,13 @@ extern "C" int nbm_frontend_spectrogram_view(const nbm_frontend_plan *pl, const 
 // fold the previous profiled run's event pairs into the accumulators (waits for that run)
 static int collect_profile(nbm_frontend_plan *pl) {
     if (!pl->ev_pending) return NBM_OK;
-    NBM_CUDA(cudaEventSynchronize(pl->ev[3]));
-    float a = 0.f, b = 0.f;
-    NBM_CUDA(cudaEventElapsedTime(&a, pl->ev[0], pl->ev[1]));
-    NBM_CUDA(cudaEventElapsedTime(&b, pl->ev[2], pl->ev[3]));
-    pl->acc_ms[0] += a; pl->acc_ms[1] += b; pl->acc_runs += 1;
+    NBM_CUDA(cudaEventSynchronize(pl->ev[4]));
+    for (int i = 0; i < 4; ++i) {
+        float ms = 0.f;
+        NBM_CUDA(cudaEventElapsedTime(&ms, pl->ev[i], pl->ev[i + 1]));
+        pl->acc_ms[i] += ms;
+    }
+    pl->acc_runs += 1;
     pl->ev_pending = false;
     return NBM_OK;
 }
@@ -700,7 +702,8 @@ extern "C" int nbm_frontend_set_profiling(nbm_frontend_plan *pl, int32_t enable)
     if (enable && !pl->ev[0])
         for (auto &e : pl->ev) NBM_CUDA(cudaEventCreate(&e));
     pl->profiling = enable != 0;
-    pl->acc_ms[0] = pl->acc_ms[1] = 0.0; pl->acc_runs = 0; pl->ev_pending = false;
+    for (auto &a : pl->acc_ms) a = 0.0;
+    pl->acc_runs = 0; pl->ev_pending = false;
     return NBM_OK;
 }
 
@@ -709,8 +712,18 @@ extern "C" int nbm_frontend_get_profile(nbm_frontend_plan *pl, double *stft_ms, 
     std::lock_guard<std::mutex> lock(pl->mu);
     int rc = collect_profile(pl);
     if (rc != NBM_OK) return rc;
-    if (stft_ms) *stft_ms = pl->acc_ms[0];
-    if (tile_ms) *tile_ms = pl->acc_ms[1];
+    if (stft_ms) *stft_ms = pl->acc_ms[0] + pl->acc_ms[1] + pl->acc_ms[2];
+    if (tile_ms) *tile_ms = pl->acc_ms[3];
+    if (runs) *runs = pl->acc_runs;
+    return NBM_OK;
+}
+
+extern "C" int nbm_frontend_get_profile_kernels(nbm_frontend_plan *pl, double *ms4, int64_t *runs) {
+    NBM_REQUIRE(pl && ms4, "null argument");
+    std::lock_guard<std::mutex> lock(pl->mu);
+    int rc = collect_profile(pl);
+    if (rc != NBM_OK) return rc;
+    for (int i = 0; i < 4; ++i) ms4[i] = pl->acc_ms[i];
     if (runs) *runs = pl->acc_runs;
     return NBM_OK;
 }
@@ -770,14 +783,17 @@ extern "C" int nbm_frontend_run_batch(const nbm_frontend_plan *cpl, const void *
     // the tensor-core kernels stage mono PCM16; float or multi-channel input takes the CUDA-core kernel
     const bool use_tc = pl->tc && pcm_dtype == NBM_PCM_INT16 && channels == 1;
     if (use_tc) {
-        rc = tc_launch(pl->tc, d_segs, (int)B.segs.size(), B.groups, d_tseg, d_tfirst, (int)B.task_seg.size(), d_pcm,
-                       pcm_dtype, channels, d_spec, d_tile_mm, ws + B.o_anchors, stream);
+        rc = tc_launch_anchors(pl->tc, d_segs, d_tseg, d_tfirst, (int)B.task_seg.size(), d_pcm, ws + B.o_anchors, stream);
+        if (rc != NBM_OK) return rc;
+        if (prof) NBM_CUDA(cudaEventRecord(pl->ev[1], stream));
+        rc = tc_launch_slides(pl->tc, d_segs, (int)B.segs.size(), B.groups, d_pcm, d_spec, d_tile_mm, ws + B.o_anchors, stream);
         if (rc != NBM_OK) return rc;
     } else {
+        if (prof) NBM_CUDA(cudaEventRecord(pl->ev[1], stream));
         stft_db_kernel<<<B.groups, pl->n_threads, pl->smem_bytes, stream>>>(pl->kp, d_segs, (int)B.segs.size(), d_pcm,
                                                                           pcm_dtype, channels, d_spec, d_tile_mm);
     }
-    if (prof) NBM_CUDA(cudaEventRecord(pl->ev[1], stream));
+    if (prof) NBM_CUDA(cudaEventRecord(pl->ev[2], stream));
     {
         RefineParams rp;
         rp.N = p.n_fft; rp.hop = p.hop; rp.low_idx = p.low_idx; rp.n_bins = p.n_bins;
@@ -791,11 +807,11 @@ extern "C" int nbm_frontend_run_batch(const nbm_frontend_plan *cpl, const void *
         refine_minmax_kernel<<<n_files, 256, 0, stream>>>(rp, d_segs, d_files, d_tile_mm, d_spec, d_pcm, pcm_dtype,
                                                          channels, d_minmax);
     }
+    if (prof) NBM_CUDA(cudaEventRecord(pl->ev[3], stream));
     dim3 grid((unsigned)B.tiles, (unsigned)((p.n_bins + TILE_ROWS - 1) / TILE_ROWS));
-    if (prof) NBM_CUDA(cudaEventRecord(pl->ev[2], stream));
     if (p.w_pix % 4 == 0) tile_kernel<true><<<grid, 256, 0, stream>>>(pl->kp, d_files, n_files, d_spec, d_minmax, d_tiles);
     else tile_kernel<false><<<grid, 256, 0, stream>>>(pl->kp, d_files, n_files, d_spec, d_minmax, d_tiles);
-    if (prof) { NBM_CUDA(cudaEventRecord(pl->ev[3], stream)); pl->ev_pending = true; }
+    if (prof) { NBM_CUDA(cudaEventRecord(pl->ev[4], stream)); pl->ev_pending = true; }
     NBM_CUDA(cudaGetLastError());
     return NBM_OK;
 }

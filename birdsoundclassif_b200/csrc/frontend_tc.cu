@@ -1004,18 +1004,25 @@ int nbm::tc_chain_frames() { return CF; }
 int nbm::tc_slots_per_range() { return 4; }
 int nbm::tc_bins_per_slot() { return ROWS_PER_EWARP; }
 
-int nbm::tc_launch(const TcPlan *pl, const SegDesc *d_segs, int n_segs, int total_tiles, const int *d_task_seg,
-                   const int *d_task_first, int n_tasks, const void *d_pcm, int dtype, int channels, float *d_spec,
-                   float2 *d_tile_mm, void *d_anchors, cudaStream_t stream) {
+int nbm::tc_launch_anchors(const TcPlan *pl, const SegDesc *d_segs, const int *d_task_seg, const int *d_task_first,
+                           int n_tasks, const void *d_pcm, void *d_anchors, cudaStream_t stream) {
     const TcParams &k = pl->p;
-    float2 *anchors = reinterpret_cast<float2 *>(d_anchors);
     dim3 ga((unsigned)n_tasks, (unsigned)k.n_ranges);
     anchor_tc_kernel<<<ga, A_THREADS, pl->smem_anchor, stream>>>(k, d_segs, d_task_seg, d_task_first,
-                                                                 reinterpret_cast<const short *>(d_pcm), anchors);
+                                                                 reinterpret_cast<const short *>(d_pcm),
+                                                                 reinterpret_cast<float2 *>(d_anchors));
+    NBM_CUDA(cudaGetLastError());
+    return NBM_OK;
+}
+
+int nbm::tc_launch_slides(const TcPlan *pl, const SegDesc *d_segs, int n_segs, int total_tiles, const void *d_pcm,
+                          float *d_spec, float2 *d_tile_mm, const void *d_anchors, cudaStream_t stream) {
+    const TcParams &k = pl->p;
     const int total_chains = 2 * total_tiles;
     const int grid = std::min(pl->grid_slide, std::max(1, total_chains) * k.n_ranges);
     slide_ws_kernel<<<(grid / k.n_ranges) * k.n_ranges, WS_THREADS, pl->smem_slide, stream>>>(
-        k, d_segs, n_segs, total_chains, reinterpret_cast<const short *>(d_pcm), anchors, d_spec, d_tile_mm);
+        k, d_segs, n_segs, total_chains, reinterpret_cast<const short *>(d_pcm),
+        reinterpret_cast<const float2 *>(d_anchors), d_spec, d_tile_mm);
     NBM_CUDA(cudaGetLastError());
     return NBM_OK;
 }

@@ -31,9 +31,11 @@ int tc_bins_per_range();               // output bins per range
 int tc_chain_frames();
 int tc_slots_per_range();
 int tc_bins_per_slot();
-// anchors (tcgen05 GEMM over N/2 folded pairs) then slides (tcgen05 GEMM over hop/2 pairs + recurrence + Hann + dB)
-int tc_launch(const TcPlan *pl, const SegDesc *d_segs, int n_segs, int total_tiles, const int *d_task_seg,
-              const int *d_task_first, int n_tasks, const void *d_pcm, int dtype, int channels, float *d_spec,
-              float2 *d_tile_mm, void *d_anchors, cudaStream_t stream);
+// anchors: tcgen05 GEMM over the N/2 folded pairs of every 64th frame (mono PCM16 only)
+int tc_launch_anchors(const TcPlan *pl, const SegDesc *d_segs, const int *d_task_seg, const int *d_task_first, int n_tasks,
+                      const void *d_pcm, void *d_anchors, cudaStream_t stream);
+// slides: tcgen05 GEMM over hop/2 pairs + recurrence + Hann + dB for every frame, per-(chain, range, slot) min/max
+int tc_launch_slides(const TcPlan *pl, const SegDesc *d_segs, int n_segs, int total_tiles, const void *d_pcm, float *d_spec,
+                     float2 *d_tile_mm, const void *d_anchors, cudaStream_t stream);
 
 }  // namespace nbm

@@ -122,7 +122,7 @@ class FrontendPlan:
         tiles, _, minmax = self.run_batch(pcm, [0, n], channels=ch, stream=stream, out=out)
         return tiles, minmax[0]
 
-    def run_batch(self, pcm: torch.Tensor, sample_offsets, channels=1, stream=None, out=None):
+    def run_batch(self, pcm: torch.Tensor, sample_offsets, channels=1, stream=None, out=None, minmax_out=None):
         """pcm: flat CUDA tensor holding every file back to back; sample_offsets: n_files+1
         per-channel sample indices.  Returns (tiles [total_tiles,1,n_bins,w_pix],
         tile_offsets list[n_files+1], minmax [n_files, 2])."""
@@ -136,7 +136,8 @@ class FrontendPlan:
         else:
             assert out.is_cuda and out.is_contiguous() and out.dtype == torch.float32 and \
                 out.numel() >= total * self.n_bins * self.w_pix
-        minmax = torch.empty((n_files, 2), dtype=torch.float32, device=self.device)
+        minmax = minmax_out if minmax_out is not None else torch.empty((n_files, 2), dtype=torch.float32, device=self.device)
+        assert minmax.is_contiguous() and minmax.shape == (n_files, 2)
         ws = self._workspace(ws_bytes)
         offs = (C.c_int64 * (n_files + 1))(*[int(v) for v in sample_offsets])
         with torch.cuda.device(self.device):
@@ -155,6 +156,48 @@ class FrontendPlan:
         _lib.check(_lib.lib().nbm_frontend_get_profile(self._h, C.byref(a), C.byref(b), C.byref(n)),
                    "nbm_frontend_get_profile")
         return a.value, b.value, n.value
+
+    def get_profile_kernels(self):
+        """({'anchor': ms, 'stft': ms, 'minmax': ms, 'tile': ms}, runs) accumulated since profiling was enabled."""
+        ms, n = (C.c_double * 4)(), C.c_int64()
+        _lib.check(_lib.lib().nbm_frontend_get_profile_kernels(self._h, ms, C.byref(n)), "nbm_frontend_get_profile_kernels")
+        return dict(zip(("anchor", "stft", "minmax", "tile"), list(ms))), n.value
+
+    def run_batch_from_host(self, host_pcm: torch.Tensor, sample_offsets, out=None, files_per_chunk=64):
+        """run_batch for mono PCM16 in PINNED host memory: the files are copied to the device in chunks on a
+        side stream while the previous chunk is being transformed (two device staging buffers), so the
+        call is bound by max(PCIe, front-end) rather than their sum.  Returns like run_batch."""
+        assert not host_pcm.is_cuda and host_pcm.is_pinned() and host_pcm.dim() == 1
+        n_files = len(sample_offsets) - 1
+        offs = [int(v) for v in sample_offsets]
+        _, tile_off, _ = self.query_batch([offs[i + 1] - offs[i] for i in range(n_files)])
+        if out is None:
+            out = torch.empty((tile_off[-1], 1, self.n_bins, self.w_pix), dtype=torch.float32, device=self.device)
+        minmax = torch.empty((n_files, 2), dtype=torch.float32, device=self.device)
+        chunks = [(f, min(n_files, f + files_per_chunk)) for f in range(0, n_files, files_per_chunk)]
+        need = max(offs[b] - offs[a] for a, b in chunks)
+        st = getattr(self, "_h2d", None)
+        if st is None or st["buf"][0].numel() < need or st["buf"][0].dtype != host_pcm.dtype:
+            st = {"buf": [torch.empty(need, dtype=host_pcm.dtype, device=self.device) for _ in range(2)],
+                  "stream": torch.cuda.Stream(device=self.device),
+                  "ready": [torch.cuda.Event() for _ in range(2)], "done": [torch.cuda.Event() for _ in range(2)]}
+            self._h2d = st
+        cur = torch.cuda.current_stream(self.device)
+        st["stream"].wait_stream(cur)
+        for ci, (fa, fb) in enumerate(chunks):
+            b = ci & 1
+            s0, s1 = offs[fa], offs[fb]
+            with torch.cuda.stream(st["stream"]):
+                if ci >= 2:
+                    st["stream"].wait_event(st["done"][b])          # chunk ci-2 no longer reads this buffer
+                st["buf"][b][:s1 - s0].copy_(host_pcm[s0:s1], non_blocking=True)
+                st["ready"][b].record(st["stream"])
+            cur.wait_event(st["ready"][b])
+            self.run_batch(st["buf"][b][:s1 - s0], [o - s0 for o in offs[fa:fb + 1]],
+                           out=out[tile_off[fa]:tile_off[fb]], minmax_out=minmax[fa:fb])
+            st["done"][b].record(cur)
+        self._last_sizes = None
+        return out, tile_off, minmax
 
     def spectrogram_view(self, file_index: int = 0) -> torch.Tensor:
         """Un-normalised dB band [n_bins, n_frames] of a file from the LAST run (a view into the

@@ -109,6 +109,8 @@ int nbm_frontend_spectrogram_view(const nbm_frontend_plan *plan, const int64_t *
  * profiling was (re-)enabled. */
 int nbm_frontend_set_profiling(nbm_frontend_plan *plan, int32_t enable);
 int nbm_frontend_get_profile(nbm_frontend_plan *plan, double *stft_ms, double *tile_ms, int64_t *runs);
+/* The same, per kernel: ms4 = {anchor GEMM, slide/STFT kernel, whole-file min/max, tiling}. */
+int nbm_frontend_get_profile_kernels(nbm_frontend_plan *plan, double *ms4, int64_t *runs);
 
 /* ------------------------------------------------------------- post-processing --------
  * Anchor table: generate_anchors_frcnn + get_anchor_shifts_frcnn combined as in

@@ -205,3 +205,18 @@ def test_leading_silence_and_exact_minimum(fe):
     t = tiles.cpu().numpy()
     assert t.min() == 0.0 and t.max() == 1.0
     assert_tiles_close(t, np.stack(r.tiles), "leading silence")
+
+
+def test_run_batch_from_host_equals_run_batch(fe):
+    """Pinned-host entry (chunked H2D on a side stream overlapped with the transform) == device entry."""
+    plan = fe.get_plan()
+    pcms = [synth.synth_pcm(s, 70 + i) for i, s in enumerate([1.0, 2.3, 0.2, 3.0, 1.5])]
+    flat = np.concatenate(pcms)
+    offs = np.concatenate([[0], np.cumsum([len(p) for p in pcms])]).tolist()
+    ref_tiles, ref_off, ref_mm = plan.run_batch(torch.from_numpy(flat).cuda(), offs)
+    ref_tiles, ref_mm = ref_tiles.clone(), ref_mm.clone()
+    host = torch.from_numpy(flat).pin_memory()
+    for per_chunk in (2, 64):
+        tiles, off, mm = plan.run_batch_from_host(host, offs, files_per_chunk=per_chunk)
+        torch.cuda.synchronize()
+        assert off == ref_off and torch.equal(tiles, ref_tiles) and torch.equal(mm, ref_mm)
