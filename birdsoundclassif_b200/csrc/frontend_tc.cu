@@ -61,6 +61,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
     return ok != 0;
 }
+// the same for waits that are expected to be long (a whole pipeline stage): sleep between polls so the
+// polling warp does not take issue slots from the working ones
+template <int NS>
+__device__ __forceinline__ void mbar_wait_long(uint64_t *bar, uint32_t parity) {
+    int spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(NS);
+        if (++spins > (1 << 22)) __trap();
+    }
+}
 // bounded wait: a lost arrival traps (launch error) instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     int spins = 0;
@@ -409,8 +419,9 @@ anchor_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, const int *__rest
 constexpr int CF = 32;                      // frames per chain
 constexpr int ST_LD = CF + 2;               // float2 per bin row of the R stage: 272 B pitch, conflict-free STS.128
 constexpr int ROWS_PER_EWARP = 32;          // emit rows per warp
-constexpr int TM_ACC_PER_GROUP = 4 * CF;    // big (cos, sin) and small (cos, sin) accumulators
-constexpr int NK_T = 4;                     // k-steps whose twiddles live in TMEM; a fifth is read from shared memory
+constexpr int TM_ACC_PER_GROUP = 2 * CF;    // (cos, sin) accumulators of a group
+constexpr int NK_T = 5;                     // k-steps whose twiddles fit in TMEM next to the accumulators (any further one is
+                                            // read from shared memory, at 4 KB per MMA)
 constexpr int TM_COLS = 512;
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -557,47 +568,54 @@ slide_ws_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int to
 #pragma unroll 1
             for (int gg = 0; gg < G; ++gg) {
                 if (q0 + (it * G + gg) * qstride >= total_chains) break;
-                mbar_wait(&b_ready[gg], it & 1);
+                mbar_wait_long<256>(&b_ready[gg], it & 1);
                 tc_fence_after();
                 WS_MARK(0);
                 if (elect_one()) {
                     const uint32_t b0 = smem_u32(smem_raw + (size_t)gg * grp_bytes);
                     const uint64_t dph = make_desc(b0 + 0 * (uint32_t)b_mat, 128, SBO), dpl = make_desc(b0 + 1 * (uint32_t)b_mat, 128, SBO);
                     const uint64_t dmh = make_desc(b0 + 2 * (uint32_t)b_mat, 128, SBO), dml = make_desc(b0 + 3 * (uint32_t)b_mat, 128, SBO);
-                    // Two accumulators per (cos, sin): the hi x hi products are integers (twiddle x 2^11 times a byte-plane
-                    // value) and fp32 adds them exactly below 2^24; the three small products (2^-8 .. 2^-19 of those) get
-                    // their own accumulator instead of being absorbed, truncated, into the large partial sums.
-                    const uint32_t big_c = tmem_base + (uint32_t)gg * TM_ACC_PER_GROUP, big_s = big_c + CF;
-                    const uint32_t sml_c = big_c + 2 * CF, sml_s = big_c + 3 * CF;
+                    // fp32 accumulation in TMEM truncates, so order matters: all the small products (2^-8 .. 2^-19 of
+                    // the hi x hi ones) are summed first, while the accumulator is still small and they keep their low
+                    // bits; the integer-valued hi x hi products are added last (5 roundings instead of 40).
+                    const uint32_t d_c = tmem_base + (uint32_t)gg * TM_ACC_PER_GROUP, d_s = d_c + CF;
 #pragma unroll 1
-                    for (int kk = 0; kk < nk; ++kk) {
-                        const uint64_t ko = (uint64_t)(kk * 16);        // 256 B per k-step in the 16-byte address field
-                        const uint32_t acc = kk > 0 ? 1u : 0u;
-                        if (kk < NK_T) {
-                            const uint32_t ka = tmem_a + kk * 8, mt = NK_T * 8;    // cos_h, cos_l, sin_h, sin_l at ka + {0,1,2,3} mt
-                            umma_f16_ts(big_c, ka + 0 * mt, dph + ko, idesc, acc);
-                            umma_f16_ts(big_s, ka + 2 * mt, dmh + ko, idesc, acc);
-                            umma_f16_ts(sml_c, ka + 0 * mt, dpl + ko, idesc, acc);
-                            umma_f16_ts(sml_s, ka + 2 * mt, dml + ko, idesc, acc);
-                            umma_f16_ts(sml_c, ka + 1 * mt, dph + ko, idesc, 1u);
-                            umma_f16_ts(sml_s, ka + 3 * mt, dmh + ko, idesc, 1u);
-                            umma_f16_ts(sml_c, ka + 1 * mt, dpl + ko, idesc, 1u);
-                            umma_f16_ts(sml_s, ka + 3 * mt, dml + ko, idesc, 1u);
-                        } else {
-                            const uint32_t a0 = smem_u32(sAt) + (uint32_t)(kk - NK_T) * 256, am = 128 * 16 * 2 * (uint32_t)(nk - NK_T);
-                            const uint32_t sbo_a = (uint32_t)(16 * (nk - NK_T) / 8) * 128;
-                            const uint64_t ach = make_desc(a0 + 0 * am, 128, sbo_a), acl = make_desc(a0 + 1 * am, 128, sbo_a);
-                            const uint64_t ash = make_desc(a0 + 2 * am, 128, sbo_a), asl = make_desc(a0 + 3 * am, 128, sbo_a);
-                            umma_f16(big_c, ach, dph + ko, idesc, acc);
-                            umma_f16(big_s, ash, dmh + ko, idesc, acc);
-                            umma_f16(sml_c, ach, dpl + ko, idesc, acc);
-                            umma_f16(sml_s, ash, dml + ko, idesc, acc);
-                            umma_f16(sml_c, acl, dph + ko, idesc, 1u);
-                            umma_f16(sml_s, asl, dmh + ko, idesc, 1u);
-                            umma_f16(sml_c, acl, dpl + ko, idesc, 1u);
-                            umma_f16(sml_s, asl, dml + ko, idesc, 1u);
+                    for (int pass = 0; pass < 2; ++pass)
+#pragma unroll 1
+                        for (int kk = 0; kk < nk; ++kk) {
+                            const uint64_t ko = (uint64_t)(kk * 16);    // 256 B per k-step in the 16-byte address field
+                            if (kk < NK_T) {
+                                const uint32_t ka = tmem_a + kk * 8, mt = NK_T * 8;    // cos_h, cos_l, sin_h, sin_l at ka + {0,1,2,3} mt
+                                if (pass == 0) {
+                                    const uint32_t acc = kk > 0 ? 1u : 0u;
+                                    umma_f16_ts(d_c, ka + 1 * mt, dpl + ko, idesc, acc);
+                                    umma_f16_ts(d_s, ka + 3 * mt, dml + ko, idesc, acc);
+                                    umma_f16_ts(d_c, ka + 1 * mt, dph + ko, idesc, 1u);
+                                    umma_f16_ts(d_s, ka + 3 * mt, dmh + ko, idesc, 1u);
+                                    umma_f16_ts(d_c, ka + 0 * mt, dpl + ko, idesc, 1u);
+                                    umma_f16_ts(d_s, ka + 2 * mt, dml + ko, idesc, 1u);
+                                } else {
+                                    umma_f16_ts(d_c, ka + 0 * mt, dph + ko, idesc, 1u);
+                                    umma_f16_ts(d_s, ka + 2 * mt, dmh + ko, idesc, 1u);
+                                }
+                            } else {
+                                const uint32_t a0 = smem_u32(sAt) + (uint32_t)(kk - NK_T) * 256, am = 128 * 16 * 2 * (uint32_t)(nk - NK_T);
+                                const uint32_t sbo_a = (uint32_t)(16 * (nk - NK_T) / 8) * 128;
+                                const uint64_t ach = make_desc(a0 + 0 * am, 128, sbo_a), acl = make_desc(a0 + 1 * am, 128, sbo_a);
+                                const uint64_t ash = make_desc(a0 + 2 * am, 128, sbo_a), asl = make_desc(a0 + 3 * am, 128, sbo_a);
+                                if (pass == 0) {
+                                    umma_f16(d_c, acl, dpl + ko, idesc, 1u);
+                                    umma_f16(d_s, asl, dml + ko, idesc, 1u);
+                                    umma_f16(d_c, acl, dph + ko, idesc, 1u);
+                                    umma_f16(d_s, asl, dmh + ko, idesc, 1u);
+                                    umma_f16(d_c, ach, dpl + ko, idesc, 1u);
+                                    umma_f16(d_s, ash, dml + ko, idesc, 1u);
+                                } else {
+                                    umma_f16(d_c, ach, dph + ko, idesc, 1u);
+                                    umma_f16(d_s, ash, dmh + ko, idesc, 1u);
+                                }
+                            }
                         }
-                    }
                     umma_commit(&acc_full[gg]);
                 }
                 __syncwarp();
@@ -613,8 +631,23 @@ slide_ws_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int to
         ChainWalk cw;
         cw.init(segs, n_segs);
         const int nv = P.buf_len / 8;
+        // pull the PCM of a chain this far ahead into L2, so the register loads below see L2, not HBM, latency
+        auto l2_prefetch = [&](int chain) {
+            ChainWalk w2 = cw;
+            w2.seek(chain);
+            const int t0 = (chain - 2 * w2.sd.group0) * CF;
+            long long a = (long long)t0 * hop - N / 2 - (PADF + P.off), b = a + P.buf_len;
+            a = a < 0 ? 0 : a;
+            b = b > w2.sd.n_samples ? w2.sd.n_samples : b;
+            const long long ga = (w2.sd.pcm_start + a + 7) & ~7ll, gb = (w2.sd.pcm_start + b) & ~7ll;      // 16-byte granules
+            if (gb > ga && elect_one())
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pcm + ga), "r"((uint32_t)((gb - ga) * 2)) : "memory");
+        };
+        constexpr int L2_AHEAD = 3;
+        for (int j = 1; j < L2_AHEAD && j < n_iters; ++j) l2_prefetch(first + j * cstride);
         for (int it = 0; it < n_iters; ++it) {
             const int chain = first + it * cstride;
+            if (it + L2_AHEAD < n_iters) l2_prefetch(chain + L2_AHEAD * cstride);
             cw.seek(chain);
             const int t0 = (chain - 2 * cw.sd.group0) * CF;
             const long long s0 = (long long)t0 * hop - N / 2 - (PADF + P.off);
@@ -635,16 +668,20 @@ slide_ws_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int to
                         if (v >= v_lo && v < v_hi) pre[e] = __ldg(src + 32 * e);
                     }
                     WS_MARK(0);
-                    if (vb == 0 && it > 0) mbar_wait(&s_free[g], (it - 1) & 1);   // every warp is done with chain it-1's samples
+                    if (vb == 0 && it > 0) mbar_wait_long<2048>(&s_free[g], (it - 1) & 1);   // every warp is done with chain it-1's samples
                     WS_MARK(1);
 #pragma unroll
                     for (int e = 0; e < PV; ++e) {
                         const int v = vb + lane + 32 * e;
-                        if (v >= v_lo && v < v_hi) {
+                        if (v >= v_lo && v < v_hi)
                             reinterpret_cast<uint4 *>(buf16)[v] =
                                 make_uint4((uint32_t)pre[e].x ^ 0x80008000u, (uint32_t)pre[e].y ^ 0x80008000u,
                                            (uint32_t)pre[e].z ^ 0x80008000u, (uint32_t)pre[e].w ^ 0x80008000u);
-                        } else if (v < nv) {        // straddles or lies outside the segment: centre padding (first / last chains)
+                    }
+                    if (v_lo > 0 || v_hi < nv) {    // first / last chains of a segment: vectors that straddle or lie outside it
+#pragma unroll 1
+                        for (int v = vb + lane; v < min(nv, vb + 32 * PV); v += 32) {
+                            if (v >= v_lo && v < v_hi) continue;
                             const long long sv = s0 + 8 * v;
                             uint32_t u[8];
 #pragma unroll
@@ -656,7 +693,7 @@ slide_ws_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int to
                     }
                 }
             } else {                                // file start not 16-byte aligned in the batch buffer
-                if (it > 0) mbar_wait(&s_free[g], (it - 1) & 1);
+                if (it > 0) mbar_wait_long<2048>(&s_free[g], (it - 1) & 1);
                 for (int i = lane; i < P.buf_len; i += 32) {
                     const long long sx = s0 + i;
                     buf16[i] = (sx >= 0 && sx < ns) ? (uint16_t)((uint16_t)__ldg(pcm + pcm0 + sx) ^ 0x8000u) : (uint16_t)0x8000u;
@@ -738,7 +775,7 @@ slide_ws_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int to
     };
     // B operand of the group's chain `it`; hands the operand to the MMA warp and the samples back to the fill warp
     auto build = [&](int it) {
-        mbar_wait(&s_full[g], it & 1);
+        mbar_wait_long<32>(&s_full[g], it & 1);
         const int n_full = P.npH / 8;                               // units with all 8 pairs live
         for (int jg = wq; jg < n_full; jg += 4) build_unit(jg);
         if (n_full < njg && wq == (it & 3)) build_tail(n_full);
@@ -770,23 +807,19 @@ slide_ws_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int to
         WS_MARK(0);
         // ---- recur: accumulators -> registers -> 32-step recurrence -> stage, 16 columns at a time ----------
         {
-            mbar_wait(&acc_full[g], it & 1);
+            mbar_wait_long<32>(&acc_full[g], it & 1);
             WS_MARK(1);
             tc_fence_after();
             float4 *st4 = reinterpret_cast<float4 *>(stage + (size_t)gt * ST_LD);
             float Rr = anc.x, Ri = anc.y;
             float pr = Rr, pi = Ri;
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll 1
+            for (int hh = 0; hh < 2; ++hh) {          // not unrolled: the straight-line recurrence is instruction-fetch bound
                 const int c0 = fwd ? 16 * hh : 16 - 16 * hh;             // forward chains walk the columns up, backward ones down
-                float gc[16], gs[16], ec[16], es[16];
+                float gc[16], gs[16];
                 tmem_ld16_nowait(acc_col + lane_sel + c0, gc);
                 tmem_ld16_nowait(acc_col + lane_sel + CF + c0, gs);
-                tmem_ld16_nowait(acc_col + lane_sel + 2 * CF + c0, ec);
-                tmem_ld16_nowait(acc_col + lane_sel + 3 * CF + c0, es);
                 tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) { gc[i] += ec[i]; gs[i] += es[i]; }
                 if (fwd) {
                     // frames t0 .. t0+31 ; column c+1 from column c with D_c
 #pragma unroll
@@ -824,27 +857,42 @@ slide_ws_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int to
         // ---- next chain's B operand: its MMAs run under this chain's emit stage ------------------------
         if (it + 1 < n_iters) build(it + 1);
         WS_MARK(4);
-        // ---- emit: Hann + dB + store, lane = frame, warp = 32 bin rows ----------------------------------
+        // ---- emit: Hann + dB + store.  Warp = 32 bin rows; a thread owns TWO adjacent frames (one LDS.128 /
+        //      STG.64 per row) and the half-warps walk the two 16-row halves, so each row store is one 128-byte line
         {
             float vmin = INFINITY, vmax = -INFINITY;
-            const float2 *st = stage + lane;
-            if (t0 + lane < cw.sd.n_frames && r_lo < r_hi) {
-                float2 pv = st[(r_lo - 1) * ST_LD], cu = st[r_lo * ST_LD];
+            const int hw = lane >> 4, fc = 2 * (lane & 15);             // half-warp, first of the two frame columns
+            const int ra = r_lo + 16 * hw, rb = min(ra + 16, r_hi);
+            const float4 *st = reinterpret_cast<const float4 *>(stage + fc);
+            constexpr int LD4 = ST_LD / 2;                               // row pitch in float4
+            const int nfr = cw.sd.n_frames - (t0 + fc);                 // frames of this thread inside the segment
+            if (nfr > 0 && ra < rb) {
+                float4 pv = st[(ra - 1) * LD4], cu = st[ra * LD4];
                 const int stride = cw.sd.row_stride;
-                float *out = spec + cw.sd.spec_off + (long long)(range * BINS_PER_RANGE + r_lo - 1) * stride + t0 + lane;
+                char *out = reinterpret_cast<char *>(spec + cw.sd.spec_off + (long long)(range * BINS_PER_RANGE + ra - 1) * stride + t0 + fc);
                 const long long stride_b = (long long)stride * 4;
-#pragma unroll 8
-                for (int r = r_lo; r < r_hi; ++r) {
-                    const float2 nx = st[(r + 1) * ST_LD];
+                const bool pair_ok = (cw.sd.spec_off & 1) == 0;          // a later STFT chunk of a long file may start on an odd column
+#pragma unroll 2
+                for (int r = ra; r < rb; ++r) {
+                    const float4 nx = st[(r + 1) * LD4];
                     // 4 X = 2 R[k] - (R[k-1] + R[k+1]);  10 log10(|X|^2) = 10 log10(|4X|^2) - 10 log10(16)
-                    const float xr = fmaf(2.0f, cu.x, -(pv.x + nx.x));
-                    const float xi = fmaf(2.0f, cu.y, -(pv.y + nx.y));
-                    const float pw = fmaxf(fmaf(xr, xr, xi * xi), floor_pw);
-                    const float db = fmaf(fast_log2(pw), 3.0102999566398120f, -12.041199826559248f);
-                    *out = db;
-                    out = reinterpret_cast<float *>(reinterpret_cast<char *>(out) + stride_b);
-                    vmin = fminf(vmin, db);
-                    vmax = fmaxf(vmax, db);
+                    const float xr0 = fmaf(2.0f, cu.x, -(pv.x + nx.x)), xi0 = fmaf(2.0f, cu.y, -(pv.y + nx.y));
+                    const float xr1 = fmaf(2.0f, cu.z, -(pv.z + nx.z)), xi1 = fmaf(2.0f, cu.w, -(pv.w + nx.w));
+                    const float pw0 = fmaxf(fmaf(xr0, xr0, xi0 * xi0), floor_pw);
+                    const float pw1 = fmaxf(fmaf(xr1, xr1, xi1 * xi1), floor_pw);
+                    const float db0 = fmaf(fast_log2(pw0), 3.0102999566398120f, -12.041199826559248f);
+                    const float db1 = fmaf(fast_log2(pw1), 3.0102999566398120f, -12.041199826559248f);
+                    if (nfr > 1) {
+                        if (pair_ok) *reinterpret_cast<float2 *>(out) = make_float2(db0, db1);
+                        else { reinterpret_cast<float *>(out)[0] = db0; reinterpret_cast<float *>(out)[1] = db1; }
+                        vmin = fminf(vmin, fminf(db0, db1));
+                        vmax = fmaxf(vmax, fmaxf(db0, db1));
+                    } else {
+                        *reinterpret_cast<float *>(out) = db0;
+                        vmin = fminf(vmin, db0);
+                        vmax = fmaxf(vmax, db0);
+                    }
+                    out += stride_b;
                     pv = cu; cu = nx;
                 }
             }
@@ -885,7 +933,7 @@ int nbm::tc_plan_create(const nbm_frontend_params &p, TcPlan **out) {
     *out = nullptr;
     const int N = p.n_fft, hop = p.hop;
     const int npH = hop / 2, KP = ((npH + 15) / 16) * 16;
-    const bool ok = (N % 4 == 0) && (hop % 4 == 0) && KP / 16 <= NK_T + 1 && hop >= 8 && p.n_bins <= 3 * BINS_PER_RANGE &&
+    const bool ok = (N % 4 == 0) && (hop % 4 == 0) && KP / 16 <= NK_T && hop >= 8 && p.n_bins <= 3 * BINS_PER_RANGE &&
                     p.low_idx >= 1 && N >= 2 * hop;
     if (!ok) return NBM_ERR_UNSUPPORTED;
     auto *pl = new TcPlan();
