@@ -13,6 +13,7 @@
 // folded about their centre (cos part uses x[c+u]+x[c-u], sin part x[c+u]-x[c-u]) which halves the
 // multiply-adds.  Thread = frequency bin, so the per-frame recurrence is register-resident; the
 // Hann combination uses warp shuffles (each warp computes 32 bins, emits the inner 30).
+#include <algorithm>
 #include <mutex>
 #include <vector>
 #include <cmath>
@@ -69,18 +70,19 @@ __device__ __forceinline__ void fold_idx(int L, int j, int &hi, int &lo) {
 
 __global__ void __launch_bounds__(512, 1)
 stft_db_kernel(KParams P, const SegDesc *__restrict__ segs, int n_segs, const void *__restrict__ pcm,
-               int dtype, int channels, float *__restrict__ spec, float2 *__restrict__ tile_mm) {
+               int dtype, int channels, float *__restrict__ spec, float2 *__restrict__ tile_mm, int group_begin) {
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
 
     // ---- which segment / group -------------------------------------------------------------
+    const int group = (int)blockIdx.x + group_begin;
     int lo_s = 0, hi_s = n_segs - 1;
     while (lo_s < hi_s) {
         int mid = (lo_s + hi_s + 1) >> 1;
-        if (segs[mid].group0 <= (int)blockIdx.x) lo_s = mid; else hi_s = mid - 1;
+        if (segs[mid].group0 <= group) lo_s = mid; else hi_s = mid - 1;
     }
     const SegDesc sd = segs[lo_s];
-    const int t0 = ((int)blockIdx.x - sd.group0) * GF;
+    const int t0 = (group - sd.group0) * GF;
     const int nf = min(GF, sd.n_frames - t0);
     const int a = nf >> 1;                       // anchor frame (local)
     const int N = P.N, hop = P.hop, N2 = 2 * P.N;
@@ -255,7 +257,7 @@ stft_db_kernel(KParams P, const SegDesc *__restrict__ segs, int n_segs, const vo
             vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
             vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
         }
-        if (lane == 0) tile_mm[blockIdx.x] = make_float2(vmin, vmax);     // one slot per group on this path
+        if (lane == 0) tile_mm[group] = make_float2(vmin, vmax);          // one slot per group on this path
     }
 }
 
@@ -290,13 +292,14 @@ __device__ __forceinline__ double block_sum_256(double v, double *red) {
 __global__ void __launch_bounds__(256)
 refine_minmax_kernel(RefineParams R, const SegDesc *__restrict__ segs, const FileDesc *__restrict__ files,
                      const float2 *__restrict__ tile_mm, float *__restrict__ spec, const void *__restrict__ pcm,
-                     int dtype, int channels, float *__restrict__ out) {
+                     int dtype, int channels, float *__restrict__ out, int file_begin) {
     __shared__ float s_red[16];
     __shared__ double d_red[16];
     __shared__ int c_seg[REFINE_CAP], c_bin[REFINE_CAP], c_frame[REFINE_CAP];
     __shared__ int n_cand, n_hot, hot[REFINE_CAP];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const FileDesc fd = files[blockIdx.x];
+    const int file = blockIdx.x + file_begin;
+    const FileDesc fd = files[file];
     const int per_gf = GF / R.mm_frames, n_slots = R.n_ranges * R.slots_per_range;
     const int n_ent = fd.n_groups * per_gf * n_slots;
     const float2 *mm = tile_mm + (size_t)fd.group0 * per_gf * n_slots;
@@ -376,8 +379,8 @@ refine_minmax_kernel(RefineParams R, const SegDesc *__restrict__ segs, const Fil
         // every pixel within the margin was recomputed unless the list overflowed (e.g. digital silence)
         float smin = vmin;
         if (nc > 0) smin = (n_cand > REFINE_CAP || n_hot > REFINE_CAP) ? fminf(vmin, (float)best) : (float)best;
-        out[2 * blockIdx.x] = smin;
-        out[2 * blockIdx.x + 1] = vmax;
+        out[2 * file] = smin;
+        out[2 * file + 1] = vmax;
     }
 }
 
@@ -402,8 +405,8 @@ __device__ __forceinline__ int reflect_src(int c, int width, int period) {
 template <bool VEC4>
 __global__ void __launch_bounds__(256)
 tile_kernel(KParams P, const FileDesc *__restrict__ files, int n_files, const float *__restrict__ spec,
-            const float *__restrict__ minmax, float *__restrict__ tiles) {
-    const long long tile = blockIdx.x;
+            const float *__restrict__ minmax, float *__restrict__ tiles, long long tile_begin) {
+    const long long tile = blockIdx.x + tile_begin;
     int lo_f = 0, hi_f = n_files - 1;
     while (lo_f < hi_f) {
         int mid = (lo_f + hi_f + 1) >> 1;
@@ -469,10 +472,18 @@ struct nbm_frontend_plan {
     cudaEvent_t staged = nullptr;
     // optional per-kernel timing (nbm_frontend_set_profiling)
     bool profiling = false;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // anchors | slides (or the CUDA-core STFT) | min/max | tiles
+    static constexpr int MAX_SUB = 8;          // sub-batches of a run: tiling of sub-batch g overlaps the transform of g+1
+    cudaEvent_t ev[MAX_SUB][5] = {};           // per sub-batch: anchors | slides (or the CUDA-core STFT) | min/max | tiles
+    int ev_subs = 0;
     double acc_ms[4] = {0.0, 0.0, 0.0, 0.0};
     long long acc_runs = 0;
     bool ev_pending = false;
+    // the transform runs on a high-priority side stream so that its persistent CTAs are placed ahead of the
+    // bandwidth-bound tiling kernel of the previous sub-batch, which stays on the caller's stream
+    cudaStream_t s_hi = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_sub[MAX_SUB] = {};
+    bool overlap = false;
+    int sub_groups = 8192;      // least 64-frame groups per sub-batch
 };
 
 namespace {
@@ -625,6 +636,27 @@ extern "C" int nbm_frontend_plan_create(const nbm_frontend_params *p, nbm_fronte
         return rc;
     }
     k.tw = pl->d_tw;
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);             // hi = numerically lowest = greatest priority
+        e = cudaStreamCreateWithPriority(&pl->s_hi, cudaStreamNonBlocking, hi);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_in, cudaEventDisableTiming);
+        for (auto &ev : pl->ev_sub)
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        if (e != cudaSuccess) { int rc = cuda_fail(e, "plan_create(streams)"); nbm_frontend_plan_destroy(pl); return rc; }
+        // Off by default: measured on B200 the two kernels contend for the L1 / LSU data path and the
+        // power cap, and the tiling kernel, squeezed to two CTAs per SM, loses its memory-level parallelism.
+        const char *ov = getenv("NBM_FRONTEND_OVERLAP");
+        pl->overlap = ov && strcmp(ov, "1") == 0;
+        const char *sg = getenv("NBM_FRONTEND_SUB_GROUPS");
+        pl->sub_groups = sg ? std::max(1, atoi(sg)) : 8192;
+        if (pl->overlap) {
+            // to share an SM with the persistent slide kernel (maximum shared-memory carve-out) the tiling kernel
+            // has to ask for the same L1 / shared memory split
+            cudaFuncSetAttribute(tile_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(tile_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        }
+    }
     // tensor-core path unless the parameters do not fit it or NBM_FRONTEND_IMPL=cuda-core asks for the other one
     const char *impl = getenv("NBM_FRONTEND_IMPL");
     if (!(impl && strcmp(impl, "cuda-core") == 0)) {
@@ -640,7 +672,10 @@ extern "C" int nbm_frontend_plan_destroy(nbm_frontend_plan *pl) {
     if (pl->d_tw) cudaFree(pl->d_tw);
     if (pl->h_stage) cudaFreeHost(pl->h_stage);
     if (pl->staged) cudaEventDestroy(pl->staged);
-    for (auto &e : pl->ev) if (e) cudaEventDestroy(e);
+    for (auto &row : pl->ev) for (auto &e : row) if (e) cudaEventDestroy(e);
+    for (auto &e : pl->ev_sub) if (e) cudaEventDestroy(e);
+    if (pl->ev_in) cudaEventDestroy(pl->ev_in);
+    if (pl->s_hi) cudaStreamDestroy(pl->s_hi);
     tc_plan_destroy(pl->tc);
     delete pl;
     return NBM_OK;
@@ -685,11 +720,13 @@ extern "C" int nbm_frontend_spectrogram_view(const nbm_frontend_plan *pl, const 
 // fold the previous profiled run's event pairs into the accumulators (waits for that run)
 static int collect_profile(nbm_frontend_plan *pl) {
     if (!pl->ev_pending) return NBM_OK;
-    NBM_CUDA(cudaEventSynchronize(pl->ev[4]));
-    for (int i = 0; i < 4; ++i) {
-        float ms = 0.f;
-        NBM_CUDA(cudaEventElapsedTime(&ms, pl->ev[i], pl->ev[i + 1]));
-        pl->acc_ms[i] += ms;
+    for (int g = 0; g < pl->ev_subs; ++g) {
+        NBM_CUDA(cudaEventSynchronize(pl->ev[g][4]));
+        for (int i = 0; i < 4; ++i) {
+            float ms = 0.f;
+            NBM_CUDA(cudaEventElapsedTime(&ms, pl->ev[g][i], pl->ev[g][i + 1]));
+            pl->acc_ms[i] += ms;
+        }
     }
     pl->acc_runs += 1;
     pl->ev_pending = false;
@@ -699,8 +736,8 @@ static int collect_profile(nbm_frontend_plan *pl) {
 extern "C" int nbm_frontend_set_profiling(nbm_frontend_plan *pl, int32_t enable) {
     NBM_REQUIRE(pl, "null plan");
     std::lock_guard<std::mutex> lock(pl->mu);
-    if (enable && !pl->ev[0])
-        for (auto &e : pl->ev) NBM_CUDA(cudaEventCreate(&e));
+    if (enable && !pl->ev[0][0])
+        for (auto &row : pl->ev) for (auto &e : row) NBM_CUDA(cudaEventCreate(&e));
     pl->profiling = enable != 0;
     for (auto &a : pl->acc_ms) a = 0.0;
     pl->acc_runs = 0; pl->ev_pending = false;
@@ -779,39 +816,71 @@ extern "C" int nbm_frontend_run_batch(const nbm_frontend_plan *cpl, const void *
         rc = collect_profile(pl);
         if (rc != NBM_OK) return rc;
     }
-    if (prof) NBM_CUDA(cudaEventRecord(pl->ev[0], stream));
     // the tensor-core kernels stage mono PCM16; float or multi-channel input takes the CUDA-core kernel
     const bool use_tc = pl->tc && pcm_dtype == NBM_PCM_INT16 && channels == 1;
-    if (use_tc) {
-        rc = tc_launch_anchors(pl->tc, d_segs, d_tseg, d_tfirst, (int)B.task_seg.size(), d_pcm, ws + B.o_anchors, stream);
-        if (rc != NBM_OK) return rc;
-        if (prof) NBM_CUDA(cudaEventRecord(pl->ev[1], stream));
-        rc = tc_launch_slides(pl->tc, d_segs, (int)B.segs.size(), B.groups, d_pcm, d_spec, d_tile_mm, ws + B.o_anchors, stream);
-        if (rc != NBM_OK) return rc;
-    } else {
-        if (prof) NBM_CUDA(cudaEventRecord(pl->ev[1], stream));
-        stft_db_kernel<<<B.groups, pl->n_threads, pl->smem_bytes, stream>>>(pl->kp, d_segs, (int)B.segs.size(), d_pcm,
-                                                                          pcm_dtype, channels, d_spec, d_tile_mm);
+    RefineParams rp;
+    rp.N = p.n_fft; rp.hop = p.hop; rp.low_idx = p.low_idx; rp.n_bins = p.n_bins;
+    rp.mm_frames = use_tc ? tc_chain_frames() : GF;
+    rp.n_ranges = use_tc ? tc_n_ranges(pl->tc) : 1;
+    rp.slots_per_range = use_tc ? tc_slots_per_range() : 1;
+    rp.bins_per_range = use_tc ? tc_bins_per_range() : p.n_bins;
+    rp.bins_per_slot = use_tc ? tc_bins_per_slot() : p.n_bins;
+    rp.min_level = p.min_level;
+    rp.margin_db = 0.25f;
+
+    // Optional (NBM_FRONTEND_OVERLAP=1): sub-batches of whole files, balanced by 64-frame groups.  Per sub-batch
+    // the transform (anchors, slides, min/max) runs on the plan's high-priority stream and the HBM-bound tiling on
+    // the caller's stream behind an event, so tiling of sub-batch g overlaps the transform of g+1 (the slide kernel
+    // leaves room for two tiling CTAs per SM).  With one sub-batch this degenerates to the plain launch sequence.
+    int n_sub = 1;
+    if (pl->overlap) n_sub = std::max(1, std::min({(int)nbm_frontend_plan::MAX_SUB, n_files, B.groups / pl->sub_groups}));
+    std::vector<int> cut(n_sub + 1, n_files);
+    cut[0] = 0;
+    for (int g = 1, f = 0; g < n_sub; ++g) {
+        const long long want = (long long)B.groups * g / n_sub;
+        while (f < n_files && B.files[f].group0 < want) ++f;
+        cut[g] = std::max(f, cut[g - 1]);
     }
-    if (prof) NBM_CUDA(cudaEventRecord(pl->ev[2], stream));
-    {
-        RefineParams rp;
-        rp.N = p.n_fft; rp.hop = p.hop; rp.low_idx = p.low_idx; rp.n_bins = p.n_bins;
-        rp.mm_frames = use_tc ? tc_chain_frames() : GF;
-        rp.n_ranges = use_tc ? tc_n_ranges(pl->tc) : 1;
-        rp.slots_per_range = use_tc ? tc_slots_per_range() : 1;
-        rp.bins_per_range = use_tc ? tc_bins_per_range() : p.n_bins;
-        rp.bins_per_slot = use_tc ? tc_bins_per_slot() : p.n_bins;
-        rp.min_level = p.min_level;
-        rp.margin_db = 0.25f;
-        refine_minmax_kernel<<<n_files, 256, 0, stream>>>(rp, d_segs, d_files, d_tile_mm, d_spec, d_pcm, pcm_dtype,
-                                                         channels, d_minmax);
+    NBM_CUDA(cudaEventRecord(pl->ev_in, stream));              // inputs and descriptors are ready on the caller's stream
+    NBM_CUDA(cudaStreamWaitEvent(pl->s_hi, pl->ev_in, 0));
+    cudaStream_t sc = pl->s_hi;
+    int sub = 0;
+    for (int g = 0; g < n_sub; ++g) {
+        const int f0 = cut[g], f1 = cut[g + 1];
+        if (f1 <= f0) continue;
+        const FileDesc &fa = B.files[f0], &fz = B.files[f1 - 1];
+        const int seg0 = fa.seg0, seg1 = fz.seg0 + fz.n_segs;
+        const int grp0 = fa.group0, grp1 = fz.group0 + fz.n_groups;
+        const long long tile0 = fa.tile0, tile1 = fz.tile0 + fz.n_tiles;
+        if (prof) NBM_CUDA(cudaEventRecord(pl->ev[sub][0], sc));
+        if (use_tc) {
+            int t0 = 0, t1 = (int)B.task_seg.size();           // anchor tasks of these segments (task_seg is sorted)
+            t0 = (int)(std::lower_bound(B.task_seg.begin(), B.task_seg.end(), seg0) - B.task_seg.begin());
+            t1 = (int)(std::lower_bound(B.task_seg.begin(), B.task_seg.end(), seg1) - B.task_seg.begin());
+            rc = tc_launch_anchors(pl->tc, d_segs, d_tseg + t0, d_tfirst + t0, t1 - t0, d_pcm, ws + B.o_anchors, sc);
+            if (rc != NBM_OK) return rc;
+            if (prof) NBM_CUDA(cudaEventRecord(pl->ev[sub][1], sc));
+            rc = tc_launch_slides(pl->tc, d_segs, (int)B.segs.size(), seg0, grp0, grp1, d_pcm, d_spec, d_tile_mm,
+                                  ws + B.o_anchors, sc);
+            if (rc != NBM_OK) return rc;
+        } else {
+            if (prof) NBM_CUDA(cudaEventRecord(pl->ev[sub][1], sc));
+            stft_db_kernel<<<grp1 - grp0, pl->n_threads, pl->smem_bytes, sc>>>(pl->kp, d_segs, (int)B.segs.size(), d_pcm,
+                                                                               pcm_dtype, channels, d_spec, d_tile_mm, grp0);
+        }
+        if (prof) NBM_CUDA(cudaEventRecord(pl->ev[sub][2], sc));
+        refine_minmax_kernel<<<f1 - f0, 256, 0, sc>>>(rp, d_segs, d_files, d_tile_mm, d_spec, d_pcm, pcm_dtype, channels,
+                                                     d_minmax, f0);
+        NBM_CUDA(cudaEventRecord(pl->ev_sub[sub], sc));
+        NBM_CUDA(cudaStreamWaitEvent(stream, pl->ev_sub[sub], 0));
+        if (prof) NBM_CUDA(cudaEventRecord(pl->ev[sub][3], stream));
+        dim3 grid((unsigned)(tile1 - tile0), (unsigned)((p.n_bins + TILE_ROWS - 1) / TILE_ROWS));
+        if (p.w_pix % 4 == 0) tile_kernel<true><<<grid, 256, 0, stream>>>(pl->kp, d_files, n_files, d_spec, d_minmax, d_tiles, tile0);
+        else tile_kernel<false><<<grid, 256, 0, stream>>>(pl->kp, d_files, n_files, d_spec, d_minmax, d_tiles, tile0);
+        if (prof) NBM_CUDA(cudaEventRecord(pl->ev[sub][4], stream));
+        ++sub;
     }
-    if (prof) NBM_CUDA(cudaEventRecord(pl->ev[3], stream));
-    dim3 grid((unsigned)B.tiles, (unsigned)((p.n_bins + TILE_ROWS - 1) / TILE_ROWS));
-    if (p.w_pix % 4 == 0) tile_kernel<true><<<grid, 256, 0, stream>>>(pl->kp, d_files, n_files, d_spec, d_minmax, d_tiles);
-    else tile_kernel<false><<<grid, 256, 0, stream>>>(pl->kp, d_files, n_files, d_spec, d_minmax, d_tiles);
-    if (prof) { NBM_CUDA(cudaEventRecord(pl->ev[4], stream)); pl->ev_pending = true; }
+    if (prof) { pl->ev_subs = sub; pl->ev_pending = true; }
     NBM_CUDA(cudaGetLastError());
     return NBM_OK;
 }

@@ -452,9 +452,9 @@ struct ChainWalk {
     const SegDesc *segs;
     int n_segs, seg_idx, next_chain0;
     SegDesc sd;
-    __device__ void init(const SegDesc *s, int n) {
-        segs = s; n_segs = n; seg_idx = 0; sd = s[0];
-        next_chain0 = n > 1 ? 2 * s[1].group0 : 0x7fffffff;
+    __device__ void init(const SegDesc *s, int n, int start) {
+        segs = s; n_segs = n; seg_idx = start; sd = s[start];
+        next_chain0 = start + 1 < n ? 2 * s[start + 1].group0 : 0x7fffffff;
     }
     // chains are visited in increasing order
     __device__ __forceinline__ void seek(int chain) {
@@ -485,10 +485,10 @@ __device__ unsigned long long ws_dbg[32];
 //   warps 4G+1 .. +G  one fill warp per group: PCM16 of the group's next chain -> shared memory
 constexpr int WS_G = 3;
 constexpr int WS_THREADS = 32 * (4 * WS_G + 1 + WS_G);
-constexpr int PV = 22;                      // 16-byte PCM vectors per fill lane per round
+constexpr int PV = 11;                      // 16-byte PCM vectors per fill lane per round (two rounds per chain)
 
-__global__ void __launch_bounds__(WS_THREADS, 1)
-slide_ws_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int total_chains,
+__global__ void __maxnreg__(96)
+slide_ws_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int seg_begin, int chain_begin, int total_chains,
                 const short *__restrict__ pcm, const float2 *__restrict__ anchors,
                 float *__restrict__ spec, float2 *__restrict__ chain_mm) {
     constexpr int G = WS_G;
@@ -500,7 +500,7 @@ slide_ws_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int to
     const int g = is_worker ? warp >> 2 : (is_mma_warp ? 0 : warp - 4 * G - 1);    // group served
     const int wq = warp & 3, gt = tid & 127;                       // worker: warp in group (= TMEM lane quarter), thread in group
     const int range = blockIdx.x % P.n_ranges;
-    const int q0 = blockIdx.x / P.n_ranges, qstride = gridDim.x / P.n_ranges;
+    const int q0 = chain_begin + blockIdx.x / P.n_ranges, qstride = gridDim.x / P.n_ranges;   // chains [chain_begin, total_chains)
 
     const int KP = P.KP, nk = P.nk, hop = P.hop, N = P.N;
     const size_t b_mat = (size_t)CF * KP * 2;
@@ -629,7 +629,7 @@ slide_ws_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int to
         // samples), then, once the group has released the buffer, flipped to offset binary and stored.
         WS_T0();
         ChainWalk cw;
-        cw.init(segs, n_segs);
+        cw.init(segs, n_segs, seg_begin);
         const int nv = P.buf_len / 8;
         // pull the PCM of a chain this far ahead into L2, so the register loads below see L2, not HBM, latency
         auto l2_prefetch = [&](int chain) {
@@ -707,7 +707,7 @@ slide_ws_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int to
     } else {
     // ================================ worker group g ======================================================
     ChainWalk cw;
-    cw.init(segs, n_segs);
+    cw.init(segs, n_segs, seg_begin);
     const int bar_id = 1 + g;
     const int half_hop = hop / 2;
     const int njg = (P.npH + 7) / 8;
@@ -1063,13 +1063,13 @@ int nbm::tc_launch_anchors(const TcPlan *pl, const SegDesc *d_segs, const int *d
     return NBM_OK;
 }
 
-int nbm::tc_launch_slides(const TcPlan *pl, const SegDesc *d_segs, int n_segs, int total_tiles, const void *d_pcm,
-                          float *d_spec, float2 *d_tile_mm, const void *d_anchors, cudaStream_t stream) {
+int nbm::tc_launch_slides(const TcPlan *pl, const SegDesc *d_segs, int n_segs, int seg_begin, int group_begin, int group_end,
+                          const void *d_pcm, float *d_spec, float2 *d_tile_mm, const void *d_anchors, cudaStream_t stream) {
     const TcParams &k = pl->p;
-    const int total_chains = 2 * total_tiles;
-    const int grid = std::min(pl->grid_slide, std::max(1, total_chains) * k.n_ranges);
+    const int chain_begin = 2 * group_begin, chain_end = 2 * group_end;
+    const int grid = std::min(pl->grid_slide, std::max(1, chain_end - chain_begin) * k.n_ranges);
     slide_ws_kernel<<<(grid / k.n_ranges) * k.n_ranges, WS_THREADS, pl->smem_slide, stream>>>(
-        k, d_segs, n_segs, total_chains, reinterpret_cast<const short *>(d_pcm),
+        k, d_segs, n_segs, seg_begin, chain_begin, chain_end, reinterpret_cast<const short *>(d_pcm),
         reinterpret_cast<const float2 *>(d_anchors), d_spec, d_tile_mm);
     NBM_CUDA(cudaGetLastError());
     return NBM_OK;

@@ -35,7 +35,8 @@ int tc_bins_per_slot();
 int tc_launch_anchors(const TcPlan *pl, const SegDesc *d_segs, const int *d_task_seg, const int *d_task_first, int n_tasks,
                       const void *d_pcm, void *d_anchors, cudaStream_t stream);
 // slides: tcgen05 GEMM over hop/2 pairs + recurrence + Hann + dB for every frame, per-(chain, range, slot) min/max
-int tc_launch_slides(const TcPlan *pl, const SegDesc *d_segs, int n_segs, int total_tiles, const void *d_pcm, float *d_spec,
-                     float2 *d_tile_mm, const void *d_anchors, cudaStream_t stream);
+// for the 64-frame groups [group_begin, group_end), which start in segment seg_begin
+int tc_launch_slides(const TcPlan *pl, const SegDesc *d_segs, int n_segs, int seg_begin, int group_begin, int group_end,
+                     const void *d_pcm, float *d_spec, float2 *d_tile_mm, const void *d_anchors, cudaStream_t stream);
 
 }  // namespace nbm

@@ -223,3 +223,20 @@ def test_run_batch_from_host_equals_run_batch(fe):
         tiles, off, mm = plan.run_batch_from_host(host, offs, files_per_chunk=per_chunk)
         torch.cuda.synchronize()
         assert off == ref_off and torch.equal(tiles, ref_tiles) and torch.equal(mm, ref_mm)
+
+
+def test_sub_batched_overlap_path_equals_plain(fe, monkeypatch):
+    """NBM_FRONTEND_OVERLAP=1 splits a batch into sub-batches (transform on a priority stream, tiling behind
+    events): same bits as the plain launch sequence, also across an STFT-chunk seam."""
+    pcms = [synth.synth_pcm(s, 80 + i) for i, s in enumerate([3.0, 2.3, 4.1, 3.0, 1.5, 2.2])]
+    flat = torch.from_numpy(np.concatenate(pcms)).cuda()
+    offs = np.concatenate([[0], np.cumsum([len(p) for p in pcms])]).tolist()
+    plain = fe.FrontendPlan(stft_chunk=100_100)
+    ref_tiles, ref_off, ref_mm = plain.run_batch(flat, offs)
+    monkeypatch.setenv("NBM_FRONTEND_OVERLAP", "1")
+    monkeypatch.setenv("NBM_FRONTEND_SUB_GROUPS", "4")
+    sub = fe.FrontendPlan(stft_chunk=100_100)
+    tiles, off, mm = sub.run_batch(flat, offs)
+    torch.cuda.synchronize()
+    assert off == ref_off and torch.equal(tiles, ref_tiles) and torch.equal(mm, ref_mm)
+    plain.close(); sub.close()
