@@ -487,7 +487,7 @@ constexpr int WS_G = 3;
 constexpr int WS_THREADS = 32 * (4 * WS_G + 1 + WS_G);
 constexpr int PV = 11;                      // 16-byte PCM vectors per fill lane per round (two rounds per chain)
 
-__global__ void __maxnreg__(96)
+__global__ void __launch_bounds__(WS_THREADS, 1)
 slide_ws_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int seg_begin, int chain_begin, int total_chains,
                 const short *__restrict__ pcm, const float2 *__restrict__ anchors,
                 float *__restrict__ spec, float2 *__restrict__ chain_mm) {
