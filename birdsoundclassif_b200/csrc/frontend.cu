@@ -384,6 +384,13 @@ refine_minmax_kernel(RefineParams R, const SegDesc *__restrict__ segs, const Fil
     }
 }
 
+// Descriptor upload without the copy engine: a DMA copy on the caller's stream would queue behind whatever large
+// H2D transfer (the next chunk of PCM) is in flight on the same engine and stall the kernels that wait for it.
+// Pinned host memory is device-addressable under UVA, so a few warps simply read it.
+__global__ void upload_kernel(uint4 *__restrict__ dst, const uint4 *__restrict__ src, size_t n16) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
 // Normalise by the file's min/max and cut detector windows (prepare_dataset.py:248-250, 255-294);
 // columns past the file's end mirror numpy's iterated 'reflect' pad of the partial window.
 // (x - s_min) / (s_max - s_min) as reciprocal + one FMA Newton step: correctly rounded for these operands
@@ -796,7 +803,7 @@ extern "C" int nbm_frontend_run_batch(const nbm_frontend_plan *cpl, const void *
         const size_t up = B.upload_bytes;
         if (pl->h_stage_bytes < up) {
             if (pl->h_stage) { NBM_CUDA(cudaEventSynchronize(pl->staged)); cudaFreeHost(pl->h_stage); pl->h_stage = nullptr; }
-            NBM_CUDA(cudaMallocHost(&pl->h_stage, up));
+            NBM_CUDA(cudaMallocHost(&pl->h_stage, up + 16));
             pl->h_stage_bytes = up;
         } else {
             NBM_CUDA(cudaEventSynchronize(pl->staged));     // previous upload has left the staging buffer
@@ -808,7 +815,9 @@ extern "C" int nbm_frontend_run_batch(const nbm_frontend_plan *cpl, const void *
             memcpy(h + B.o_tseg, B.task_seg.data(), B.task_seg.size() * sizeof(int));
             memcpy(h + B.o_tfirst, B.task_first.data(), B.task_first.size() * sizeof(int));
         }
-        NBM_CUDA(cudaMemcpyAsync(ws, pl->h_stage, up, cudaMemcpyHostToDevice, stream));
+        const size_t n16 = (up + 15) / 16;
+        upload_kernel<<<(unsigned)std::min<size_t>(64, (n16 + 255) / 256), 256, 0, stream>>>(
+            reinterpret_cast<uint4 *>(ws), reinterpret_cast<const uint4 *>(pl->h_stage), n16);
         NBM_CUDA(cudaEventRecord(pl->staged, stream));
     }
     const bool prof = pl->profiling;
