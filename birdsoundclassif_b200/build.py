@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnbm_b200.so")
-SOURCES = ["capi.cu", "frontend.cu", "frontend_tc.cu", "postproc.cu"]
+SOURCES = ["capi.cu", "frontend.cu", "frontend_tc.cu", "postproc.cu", "roipool.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

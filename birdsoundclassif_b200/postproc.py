@@ -9,6 +9,7 @@ replace, so they can be patched into ``nbm_model.nets.layers`` / ``nbm_model.run
   ProposalLayer       layers.py:219-303       (parameter-free nn.Module)
   fastrcnn_inference_tail   layers.py:688-778 (the inference branch of FastRCNN.forward)
   merge_images        run_detection.py:163-249
+  ROIPooling          layers.py:399-497       (parameter-free nn.Module)
 
 All arithmetic is done by libnbm_b200.so on the tensors' CUDA device; torch only owns the
 memory.  There is no CPU fallback: CPU tensors raise.
@@ -280,3 +281,54 @@ def merge_images(fp, outputs, num_classes, nms_thresh=0.3):
     kb, ks, kc = merge_flat(boxes, scores, classes, tiles, len(out), fp.W_PIX, fp.HOP_SPECTRO,
                             int(fp.spectrogram_length), nms_thresh)
     return survivors_to_class_dict(kb, ks, kc, num_classes)
+
+
+# ------------------------------------------------------------------------------ RoI pooling ----
+def one_dimension_positional_encoding(length, cn, temp=10000):
+    """position_encoding.py:10-15, restated (computed on the CPU like the reference, then moved)."""
+    pos = torch.arange(1, length + 1, dtype=torch.float32)
+    dt = temp ** (2 * torch.div(torch.arange(cn, dtype=torch.float32), 2, rounding_mode='trunc') / cn)
+    posenc = pos[:, None] / dt[None, :]
+    return torch.stack([posenc[:, 0::2].sin(), posenc[:, 1::2].cos()], dim=2).flatten(start_dim=1)
+
+
+class ROIPooling(nn.Module):
+    """Drop-in for layers.ROIPooling (layers.py:399-497): same forward(rois, conv_out) ->
+    (roi_pool_out [B,R,C,ph,pw], roi_pe_out [B,R,C,ph,pw], level assignment numpy [B,R]), one kernel
+    launch instead of a Python loop over batch x RoIs with .item() syncs.  Holds no parameters."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self._pe = {}
+
+    def _tables(self, device):
+        cfg = self.config
+        key = (int(cfg.img_height), int(cfg.img_width), int(cfg.out_fpn_chan), str(device))
+        if key not in self._pe:
+            self._pe[key] = (one_dimension_positional_encoding(cfg.img_height, cfg.out_fpn_chan // 2).to(device).contiguous(),
+                             one_dimension_positional_encoding(cfg.img_width, cfg.out_fpn_chan // 2).to(device).contiguous())
+        return self._pe[key]
+
+    def forward(self, rois: torch.Tensor, conv_out):
+        cfg = self.config
+        _need_cuda(rois, *conv_out)
+        B, R = rois.shape[:2]
+        n_layers = int(cfg.n_layers)
+        feats = [_f32c(f) for f in conv_out[:n_layers]]
+        Cc = feats[0].shape[1]
+        if Cc != int(cfg.out_fpn_chan):
+            raise _lib.NbmError("feature maps must have out_fpn_chan channels")
+        ph, pw = int(cfg.roi_pool_h), int(cfg.roi_pool_w)
+        pe_f, pe_t = self._tables(rois.device)
+        r = _f32c(rois)
+        pool = torch.empty((B, R, Cc, ph, pw), dtype=torch.float32, device=rois.device)
+        pe = torch.empty_like(pool)
+        lvl = torch.empty((B, R), dtype=torch.int32, device=rois.device)
+        ptrs = (C.c_void_p * n_layers)(*[f.data_ptr() for f in feats])
+        hs = (C.c_int32 * n_layers)(*[f.shape[-2] for f in feats])
+        ws = (C.c_int32 * n_layers)(*[f.shape[-1] for f in feats])
+        _lib.check(_lib.lib().nbm_roi_pool(r.data_ptr(), B, R, ptrs, hs, ws, n_layers, Cc, ph, pw, int(cfg.img_height),
+                                           int(cfg.img_width), pe_f.data_ptr(), pe_t.data_ptr(), pool.data_ptr(),
+                                           pe.data_ptr(), lvl.data_ptr(), _stream()), "nbm_roi_pool")
+        return pool, pe, lvl.cpu().numpy()

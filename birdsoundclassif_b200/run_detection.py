@@ -47,12 +47,17 @@ def patch_reference() -> list[str]:
 
 
 def accelerate_model(model):
-    """Swap the parameter-free ProposalLayer of a reference NbmModel (head.prop_layer,
-    head.py:18) for the fused one; state_dict keys are unaffected."""
+    """Swap the parameter-free ProposalLayer (head.prop_layer, head.py:18) and ROIPooling
+    (head.fast_rcnn.roi_pooling, layers.py:661) of a reference NbmModel for the library-backed ones;
+    state_dict keys are unaffected."""
     head = getattr(model, "head", None)
     if head is not None and hasattr(head, "prop_layer"):
         old = head.prop_layer
         head.prop_layer = postproc.ProposalLayer(old.config, old.n_layers).train(old.training)
+    # second stage: the parameter-free ROIPooling of FastRCNN (layers.py:661) -> one-launch kernel
+    frcnn = getattr(head, "fast_rcnn", None) if head is not None else None
+    if frcnn is not None and hasattr(frcnn, "roi_pooling"):
+        frcnn.roi_pooling = postproc.ROIPooling(frcnn.roi_pooling.config)
     return model
 
 

@@ -113,3 +113,11 @@ def read_wav_pcm16(path: str) -> tuple[np.ndarray, int]:
         sr, ch, n = w.getframerate(), w.getnchannels(), w.getnframes()
         pcm = np.frombuffer(w.readframes(n), dtype="<i2")
     return (pcm if ch == 1 else pcm.reshape(-1, ch)), sr
+
+
+def fpn_features(seed: int, batch: int, channels: int, n_layers: int = 5, img_height: int = 375, img_width: int = 1024):
+    """Seeded stand-in FPN outputs for the second-stage pooling tests: level l is [batch, channels,
+    ceil(img_height / 2^(l+1)), img_width / 2^(l+1)] float32 (strides 2 .. 2^n_layers, layers.py:415)."""
+    rng = np.random.default_rng(seed)
+    return [rng.standard_normal((batch, channels, -(-img_height // 2 ** (l + 1)), img_width // 2 ** (l + 1))).astype(np.float32)
+            for l in range(n_layers)]

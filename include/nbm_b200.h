@@ -187,6 +187,19 @@ int nbm_merge_detections(const float *d_boxes, const float *d_scores, const int3
                          int32_t *d_out_count, void *d_workspace, size_t workspace_bytes,
                          void *stream);
 
+/* ------------------------------------------------------------- second-stage pooling ----
+ * ROIPooling.forward (layers.py:399-497): pyramid-level assignment, adaptive average pooling of the
+ * level's feature-map crop, and the pooled RoI positional encoding, for all B*R RoIs in one launch
+ * (the reference loops in Python with five .item() syncs per RoI).  d_feat: HOST array of n_layers
+ * device pointers to [B, C, heights[l], widths[l]] float32 maps.  d_pe_freq [img_h, C/2] and d_pe_time
+ * [img_w, C/2]: one_dimension_positional_encoding tables (position_encoding.py:10-15).  Outputs:
+ * d_pool_out, d_pe_out [B, R, C, pool_h, pool_w]; d_level_out int32 [B, R].  Averages follow ATen's
+ * summation order, so the result is bit-identical to the reference on the same inputs. */
+int nbm_roi_pool(const float *d_rois, int32_t B, int32_t R, const float *const *d_feat, const int32_t *heights,
+                 const int32_t *widths, int32_t n_layers, int32_t C, int32_t pool_h, int32_t pool_w,
+                 int32_t img_h, int32_t img_w, const float *d_pe_freq, const float *d_pe_time,
+                 float *d_pool_out, float *d_pe_out, int32_t *d_level_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,7 +5,7 @@
 Front-end vectors come from the reference ``File_Processor.process_file`` run unmodified
 through ``oracle.ref_shims`` (only ``librosa.load/stft`` are supplied, see that module);
 post-processing vectors come from the reference ``nms``, ``bbox_reg_to_coord``,
-``ProposalLayer``, the inference branch of ``FastRCNN.forward`` and ``merge_images``.
+``ProposalLayer``, the inference branch of ``FastRCNN.forward``, ``merge_images`` and ``ROIPooling``.
 The fixtures are small (strided pixel samples, not full tiles) and are regenerated
 bit-identically by this script (seeded inputs).
 """
@@ -257,6 +257,30 @@ def merge_golden():
     np.savez_compressed(os.path.join(GOLD, "postproc_merge.npz"), **out)
 
 
+def roipool_golden():
+    """Reference ROIPooling.forward (layers.py:399-497) on seeded feature maps (8 channels; the maps are
+    regenerated from the seed by the tests, only their CRC is stored)."""
+    layers = ref_shims.ref("nbm_model.nets.layers")
+    pos = ref_shims.ref("nbm_model.nets.position_encoding")
+    rng = np.random.default_rng(600)
+    args = _args()
+    args.out_fpn_chan = 8
+    B, R = 2, 14
+    feats = synth.fpn_features(601, B, 8, args.n_layers)
+    rois = np.stack([_rand_boxes(rng, R, max_side=400) for _ in range(B)])
+    rois[0, 0] = [100, 50, 105, 55]          # tiny: grown to 2 x 2 cells
+    rois[0, 1] = [0, 0, 1023, 374]           # whole image: x2 rounds to the map width (python slice clamps)
+    rois[0, 2] = [1000, 360, 1023, 374]      # bottom-right corner
+    rois[1, 0] = [10, 10, 30, 30]            # side 20 -> log2(2.0): level boundary
+    pool, pe, lvl = layers.ROIPooling(args)(torch.from_numpy(rois), [torch.from_numpy(f) for f in feats])
+    out = {"rois": rois, "pool": pool.numpy(), "pe": pe.numpy(), "lvl": np.asarray(lvl, dtype=np.int32),
+           "pe_freq": pos.one_dimension_positional_encoding(args.img_height, 4).numpy(),
+           "pe_time": pos.one_dimension_positional_encoding(args.img_width, 4).numpy(),
+           "feat_crc": np.uint32(zlib.crc32(b"".join(f.tobytes() for f in feats)))}
+    np.savez_compressed(os.path.join(GOLD, "postproc_roipool.npz"), **out)
+    print("roipool", pool.shape, np.bincount(np.asarray(lvl).ravel()))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
@@ -266,6 +290,7 @@ def main():
     proposal_golden()
     tail_golden()
     merge_golden()
+    roipool_golden()
 
 
 if __name__ == "__main__":

@@ -224,3 +224,63 @@ def merge_images(tiles_out: list[dict], *, w_pix=1024, hop_spectro=819, spectrog
     kb, ks, ksp = boxes[keep], scores[keep], species[keep]
     return {str(c): (dict(bbox_coord=kb[ksp == c], scores=ks[ksp == c]) if (ksp == c).any() else empty())
             for c in range(1, num_classes + 1)}
+
+
+# ------------------------------------------------------------------------------ RoI pooling ----
+def positional_encoding_1d(length: int, cn: int, temp=10000) -> np.ndarray:
+    """position_encoding.py:10-15 in float32 numpy (sin/cos may differ from torch by an ulp; tests
+    feed the kernel and this oracle the SAME table)."""
+    pos = np.arange(1, length + 1, dtype=np.float32)
+    dt = (np.float32(temp) ** (2 * (np.arange(cn, dtype=np.float32) // 2) / np.float32(cn))).astype(np.float32)
+    posenc = (pos[:, None] / dt[None, :]).astype(np.float32)
+    pe = np.stack([np.sin(posenc[:, 0::2]), np.cos(posenc[:, 1::2])], axis=2).reshape(length, -1)
+    return pe.astype(np.float32)
+
+
+def _adaptive_avg_pool(x: np.ndarray, ph: int, pw: int) -> np.ndarray:
+    """ATen cpu_adaptive_avg_pool2d on x [C, H, W]: window summed row by row in float32, then / kh / kw."""
+    Cn, H, W = x.shape
+    out = np.zeros((Cn, ph, pw), dtype=np.float32)
+    for oh in range(ph):
+        ih0, ih1 = (oh * H) // ph, -((-(oh + 1) * H) // ph)
+        for ow in range(pw):
+            iw0, iw1 = (ow * W) // pw, -((-(ow + 1) * W) // pw)
+            acc = np.zeros(Cn, dtype=np.float32)
+            for ih in range(ih0, ih1):
+                for iw in range(iw0, iw1):
+                    acc = (acc + x[:, ih, iw]).astype(np.float32)
+            out[:, oh, ow] = (acc / np.float32(ih1 - ih0)).astype(np.float32) / np.float32(iw1 - iw0)
+    return out
+
+
+def roi_pool(rois: np.ndarray, feats: list, pe_freq: np.ndarray, pe_time: np.ndarray, *, n_layers=5, pool_h=2, pool_w=2):
+    """ROIPooling.forward (layers.py:399-497).  rois [B, R, 4] float32, feats: n_layers arrays [B, C, H_l, W_l]."""
+    rois = np.asarray(rois, np.float32)
+    B, R = rois.shape[:2]
+    Cn = feats[0].shape[1]
+    pool = np.zeros((B, R, Cn, pool_h, pool_w), np.float32)
+    pe = np.zeros_like(pool)
+    lvl = np.zeros((B, R), np.int32)
+    ln2 = np.float32(np.log(2))
+    for b in range(B):
+        for i in range(R):
+            x1, y1, x2, y2 = [np.float32(v) for v in rois[b, i]]
+            side = np.sqrt(np.float32(np.float32(x2 - x1) * np.float32(y2 - y1)))
+            with np.errstate(divide="ignore", invalid="ignore"):
+                lv = np.float32(np.log(np.float32(side * np.float32(0.1)))) / ln2
+            level = int(np.clip(int(lv) if np.isfinite(lv) else 0, 0, n_layers - 1))
+            s = 2 ** (level + 1)
+            fx1, fy1, fx2, fy2 = [int(np.rint(np.float32(v) / np.float32(s))) for v in (x1, y1, x2, y2)]
+            H, W = feats[level].shape[-2:]
+            fy2 = min(fy2, H - 1)
+            while fy2 - fy1 + 1 < pool_h:
+                fy1 = max(0, fy1 - 1); fy2 = min(H - 1, fy2 + 1)
+            while fx2 - fx1 + 1 < pool_w:
+                fx1 = max(0, fx1 - 1); fx2 = min(W - 1, fx2 + 1)
+            lvl[b, i] = level
+            pool[b, i] = _adaptive_avg_pool(feats[level][b, :, fy1:fy2 + 1, fx1:fx2 + 1].astype(np.float32), pool_h, pool_w)
+            fpe, tpe = pe_freq[s * fy1:s * fy2], pe_time[:s * (fx2 - fx1)]
+            roi_pe = np.concatenate([np.broadcast_to(fpe[:, None, :], (len(fpe), len(tpe), fpe.shape[1])),
+                                     np.broadcast_to(tpe[None, :, :], (len(fpe), len(tpe), tpe.shape[1]))], axis=-1)
+            pe[b, i] = _adaptive_avg_pool(np.ascontiguousarray(np.transpose(roi_pe, (2, 0, 1))), pool_h, pool_w)
+    return pool, pe, lvl

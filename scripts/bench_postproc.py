@@ -67,6 +67,19 @@ def main():
     with torch.no_grad():
         out["proposal_layer_bs4"] = {"gpu_us": round(gpu_us(lambda: layer(dc, dr), iters=20), 1),
                                      "cpu_oracle_us": round(cpu_us(lambda: po.proposal_layer(cls, reg), iters=2), 1)}
+    # second-stage RoI pooling + positional encoding: bs 4 x 50 RoIs, 256 channels, 2 x 2 bins
+    cfg.n_layers, cfg.out_fpn_chan = 5, 256
+    feats = synth.fpn_features(5, 4, 256, 5)
+    x1 = rng.integers(0, 900, (4, 50)); y1 = rng.integers(0, 330, (4, 50))
+    rois = np.stack([x1, y1, np.minimum(x1 + rng.integers(5, 300, (4, 50)), 1023),
+                     np.minimum(y1 + rng.integers(5, 120, (4, 50)), 374)], -1).astype(np.float32)
+    rp = pp.ROIPooling(cfg)
+    dro, dfe = torch.from_numpy(rois).cuda(), [torch.from_numpy(f).cuda() for f in feats]
+    small = [f[:, :16] for f in feats]
+    pe_f, pe_t = po.positional_encoding_1d(375, 8), po.positional_encoding_1d(1024, 8)
+    c16 = cpu_us(lambda: po.roi_pool(rois, small, pe_f, pe_t), iters=1)
+    out["roi_pooling_bs4_r50_c256"] = {"gpu_us": round(gpu_us(lambda: rp(dro, dfe), iters=20), 1),
+                                       "cpu_oracle_us": round(c16 * 16, 1), "cpu_note": "oracle timed on 16 of 256 channels, x16"}
     print(json.dumps({"postproc_latency": out, "cpu_threads": 1,
                       "note": "GPU: CUDA events over 20-30 calls through the Python mirror (includes its host overhead); "
                               "CPU: oracle port of the reference algorithm, single thread"}))

@@ -203,3 +203,36 @@ def test_cpu_tensors_are_rejected(pp):
     from birdsoundclassif_b200 import _lib
     with pytest.raises(_lib.NbmError):
         pp.nms(torch.zeros(1, 4, 4), torch.zeros(1, 4))
+
+
+def test_roi_pooling_golden_and_oracle(pp):
+    """ROIPooling.forward (layers.py:399-497) in one launch: pyramid levels, pooled features and pooled
+    positional encoding bit-exact against the vectors recorded from the reference class, then a larger
+    random case against the oracle."""
+    import zlib
+    from oracle import postproc_oracle as po
+    g = H.load("postproc_roipool.npz")
+    feats = synth.fpn_features(601, 2, 8, 5)
+    assert np.uint32(zlib.crc32(b"".join(f.tobytes() for f in feats))) == g["feat_crc"]
+    cfg = synth.default_args("cuda")
+    cfg.out_fpn_chan = 8
+    layer = pp.ROIPooling(cfg)
+    np.testing.assert_array_equal(layer._tables(torch.device("cuda"))[0].cpu().numpy(), g["pe_freq"])
+    pool, pe, lvl = layer(_cuda(g["rois"]), [_cuda(f) for f in feats])
+    np.testing.assert_array_equal(lvl, g["lvl"])
+    np.testing.assert_array_equal(pool.cpu().numpy(), g["pool"])
+    np.testing.assert_array_equal(pe.cpu().numpy(), g["pe"])
+    # detector-sized random case: bs 4 x 50 RoIs, 16 channels
+    rng = np.random.default_rng(77)
+    feats = synth.fpn_features(78, 4, 16, 5)
+    x1 = rng.integers(0, 900, (4, 50)); y1 = rng.integers(0, 330, (4, 50))
+    rois = np.stack([x1, y1, np.minimum(x1 + rng.integers(5, 300, (4, 50)), 1023),
+                     np.minimum(y1 + rng.integers(5, 120, (4, 50)), 374)], -1).astype(np.float32)
+    cfg.out_fpn_chan = 16
+    layer = pp.ROIPooling(cfg)
+    pe_f, pe_t = [t.cpu().numpy() for t in layer._tables(torch.device("cuda"))]
+    pool, pe, lvl = layer(_cuda(rois), [_cuda(f) for f in feats])
+    rp, rpe, rl = po.roi_pool(rois, feats, pe_f, pe_t)
+    np.testing.assert_array_equal(lvl, rl)
+    np.testing.assert_array_equal(pool.cpu().numpy(), rp)
+    np.testing.assert_array_equal(pe.cpu().numpy(), rpe)

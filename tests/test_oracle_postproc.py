@@ -125,3 +125,22 @@ def test_default_args_match_reference_parser():
             elif "action" in kw and ast.literal_eval(kw["action"]) == "store_true":
                 found[name] = False
     assert found == synth.DEFAULT_ARGS
+
+
+def _roipool_case():
+    import zlib
+    from birdsoundclassif_b200 import synth
+    g = H.load("postproc_roipool.npz")
+    feats = synth.fpn_features(601, 2, 8, 5)
+    assert np.uint32(zlib.crc32(b"".join(f.tobytes() for f in feats))) == g["feat_crc"], "seeded feature maps not reproducible"
+    return g, feats
+
+
+def test_roi_pool_oracle_matches_reference_golden():
+    """ROIPooling.forward (layers.py:399-497): levels, pooled features and pooled positional encoding bit-exact."""
+    from oracle import postproc_oracle as po
+    g, feats = _roipool_case()
+    pool, pe, lvl = po.roi_pool(g["rois"], feats, g["pe_freq"], g["pe_time"])
+    np.testing.assert_array_equal(lvl, g["lvl"])
+    np.testing.assert_array_equal(pool, g["pool"])
+    np.testing.assert_array_equal(pe, g["pe"])
