@@ -157,6 +157,22 @@ __device__ __forceinline__ int find_seg(const SegDesc *segs, int n_segs, int til
 }
 
 // ------------------------------------------------------------------------- shared helpers -----
+// Re-alignment of 16-bit samples read with aligned 16-byte loads: W holds NW consecutive 32-bit words (two samples
+// each) starting at an aligned address; the wanted run starts `sh` samples (0..7) later.  Returns words [0, NO).
+template <int NW, int NO>
+__device__ __forceinline__ void realign_words(const uint32_t (&W)[NW], int sh, uint32_t (&out)[NO]) {
+    static_assert(NW >= NO + 4, "need four spare words");
+    uint32_t t[NO + 2], u[NO + 1];
+    const bool q2 = (sh & 4) != 0, q1 = (sh & 2) != 0;
+    const int r = (sh & 1) * 16;
+#pragma unroll
+    for (int i = 0; i < NO + 2; ++i) t[i] = q2 ? W[i + 2] : W[i];
+#pragma unroll
+    for (int i = 0; i < NO + 1; ++i) u[i] = q1 ? t[i + 1] : t[i];
+#pragma unroll
+    for (int i = 0; i < NO; ++i) out[i] = __funnelshift_r(u[i], u[i + 1], r);
+}
+
 // one lane of the (converged) warp; the compiler treats the guarded region as single-threaded, so warp-uniform
 // operands of tcgen05 instructions need no per-value election loop
 __device__ __forceinline__ bool elect_one() {
@@ -298,14 +314,27 @@ anchor_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, const int *__rest
         const int ai = first + a;
         const bool live = ai < n_anch_seg;
         const long long c = (long long)ai * GF * P.hop;            // segment-relative index of the frame centre
-        const bool aligned = ((sd.pcm_start & 7) == 0) && ((reinterpret_cast<uintptr_t>(pcm) & 15) == 0) && (P.hop % 8 == 0 || (GF * P.hop) % 8 == 0);
+        // c and the pair offsets are multiples of 8 samples, so every 16-sample run of this CTA starts `sh`
+        // samples after a 16-byte boundary (sh = 0 when the file starts on one)
+        const bool vec_ok = ((reinterpret_cast<uintptr_t>(pcm) & 15) == 0) && (GF * P.hop) % 8 == 0;
+        const int sh = (int)(sd.pcm_start & 7);
         uint32_t hi_w[8], lo_w[8];          // 16 samples above / below the centre for this thread's pairs, offset binary
         auto load16 = [&](long long s0, uint32_t (&w)[8]) {         // samples s0 .. s0+15 (segment-relative)
-            if (live && aligned && s0 >= 0 && s0 + 16 <= sd.n_samples) {
-                const int4 *p4 = reinterpret_cast<const int4 *>(pcm + sd.pcm_start + s0);
+            const long long a0 = s0 - sh;                           // start of the aligned window (segment-relative)
+            if (live && vec_ok && a0 >= 0 && a0 + (sh ? 24 : 16) <= sd.n_samples) {
+                const int4 *p4 = reinterpret_cast<const int4 *>(pcm + sd.pcm_start + a0);
                 const int4 v0 = __ldg(p4), v1 = __ldg(p4 + 1);
-                w[0] = (uint32_t)v0.x ^ 0x80008000u; w[1] = (uint32_t)v0.y ^ 0x80008000u; w[2] = (uint32_t)v0.z ^ 0x80008000u; w[3] = (uint32_t)v0.w ^ 0x80008000u;
-                w[4] = (uint32_t)v1.x ^ 0x80008000u; w[5] = (uint32_t)v1.y ^ 0x80008000u; w[6] = (uint32_t)v1.z ^ 0x80008000u; w[7] = (uint32_t)v1.w ^ 0x80008000u;
+                if (sh == 0) {
+                    w[0] = (uint32_t)v0.x; w[1] = (uint32_t)v0.y; w[2] = (uint32_t)v0.z; w[3] = (uint32_t)v0.w;
+                    w[4] = (uint32_t)v1.x; w[5] = (uint32_t)v1.y; w[6] = (uint32_t)v1.z; w[7] = (uint32_t)v1.w;
+                } else {
+                    const int4 v2 = __ldg(p4 + 2);
+                    const uint32_t W[12] = {(uint32_t)v0.x, (uint32_t)v0.y, (uint32_t)v0.z, (uint32_t)v0.w, (uint32_t)v1.x, (uint32_t)v1.y,
+                                            (uint32_t)v1.z, (uint32_t)v1.w, (uint32_t)v2.x, (uint32_t)v2.y, (uint32_t)v2.z, (uint32_t)v2.w};
+                    realign_words<12, 8>(W, sh, w);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w[i] ^= 0x80008000u;
             } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -653,12 +682,24 @@ slide_ws_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int se
             const long long s0 = (long long)t0 * hop - N / 2 - (PADF + P.off);
             const long long pcm0 = cw.sd.pcm_start, ns = cw.sd.n_samples;
             const long long g0 = pcm0 + s0;
-            const bool fast = (g0 & 7) == 0 && (reinterpret_cast<uintptr_t>(pcm) & 15) == 0;
-            // vector v covers samples s0 + 8v .. +7: fully inside the segment iff v_lo <= v < v_hi
-            const int v_lo = s0 >= 0 ? 0 : (int)((-s0 + 7) >> 3);
-            const long long room = ns - s0;
+            const bool fast = (reinterpret_cast<uintptr_t>(pcm) & 15) == 0;
+            const int sh = (int)(g0 & 7);           // the chain starts sh samples after a 16-byte boundary of the batch buffer
+            // vector v covers samples s0 + 8v .. +7 and is assembled from the aligned 16-byte loads at s0 - sh + 8v
+            // (and the next one when sh != 0): fast iff those lie inside the segment, v_lo <= v < v_hi
+            const long long a0 = s0 - sh;
+            const int v_lo = a0 >= 0 ? 0 : (int)((-a0 + 7) >> 3);
+            const long long room = ns - a0 - (sh ? 8 : 0);
             const int v_hi = room <= 0 ? 0 : (int)(room >> 3 < nv ? room >> 3 : nv);
-            if (fast) {
+            auto slow_vector = [&](int v) {         // straddles or lies outside the segment: centre padding (first / last chains)
+                const long long sv = s0 + 8 * v;
+                uint32_t u[8];
+#pragma unroll
+                for (int el = 0; el < 8; ++el)
+                    u[el] = (sv + el >= 0 && sv + el < ns) ? ((uint32_t)(uint16_t)__ldg(pcm + pcm0 + sv + el) ^ 0x8000u) : 0x8000u;
+                reinterpret_cast<uint4 *>(buf16)[v] =
+                    make_uint4(u[0] | (u[1] << 16), u[2] | (u[3] << 16), u[4] | (u[5] << 16), u[6] | (u[7] << 16));
+            };
+            if (fast && sh == 0) {
                 for (int vb = 0; vb < nv; vb += 32 * PV) {
                     int4 pre[PV];
                     const int4 *src = reinterpret_cast<const int4 *>(pcm + g0) + vb + lane;
@@ -678,21 +719,43 @@ slide_ws_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int se
                                 make_uint4((uint32_t)pre[e].x ^ 0x80008000u, (uint32_t)pre[e].y ^ 0x80008000u,
                                            (uint32_t)pre[e].z ^ 0x80008000u, (uint32_t)pre[e].w ^ 0x80008000u);
                     }
-                    if (v_lo > 0 || v_hi < nv) {    // first / last chains of a segment: vectors that straddle or lie outside it
+                    if (v_lo > 0 || v_hi < nv) {    // first / last chains of a segment
 #pragma unroll 1
-                        for (int v = vb + lane; v < min(nv, vb + 32 * PV); v += 32) {
-                            if (v >= v_lo && v < v_hi) continue;
-                            const long long sv = s0 + 8 * v;
-                            uint32_t u[8];
-#pragma unroll
-                            for (int el = 0; el < 8; ++el)
-                                u[el] = (sv + el >= 0 && sv + el < ns) ? ((uint32_t)(uint16_t)__ldg(pcm + pcm0 + sv + el) ^ 0x8000u) : 0x8000u;
-                            reinterpret_cast<uint4 *>(buf16)[v] =
-                                make_uint4(u[0] | (u[1] << 16), u[2] | (u[3] << 16), u[4] | (u[5] << 16), u[6] | (u[7] << 16));
-                        }
+                        for (int v = vb + lane; v < min(nv, vb + 32 * PV); v += 32)
+                            if (!(v >= v_lo && v < v_hi)) slow_vector(v);
                     }
                 }
-            } else {                                // file start not 16-byte aligned in the batch buffer
+            } else if (fast) {
+                // the file does not start on a 16-byte boundary of the batch buffer: aligned loads, re-aligned in registers
+                constexpr int PS = 4;
+                for (int vb = 0; vb < nv; vb += 32 * PS) {
+                    int4 pa[PS], pb[PS];
+                    const int4 *src = reinterpret_cast<const int4 *>(pcm + g0 - sh) + vb + lane;
+#pragma unroll
+                    for (int e = 0; e < PS; ++e) {
+                        const int v = vb + lane + 32 * e;
+                        if (v >= v_lo && v < v_hi) { pa[e] = __ldg(src + 32 * e); pb[e] = __ldg(src + 32 * e + 1); }
+                    }
+                    if (vb == 0 && it > 0) mbar_wait_long<2048>(&s_free[g], (it - 1) & 1);
+#pragma unroll
+                    for (int e = 0; e < PS; ++e) {
+                        const int v = vb + lane + 32 * e;
+                        if (v >= v_lo && v < v_hi) {
+                            const uint32_t W[8] = {(uint32_t)pa[e].x, (uint32_t)pa[e].y, (uint32_t)pa[e].z, (uint32_t)pa[e].w,
+                                                   (uint32_t)pb[e].x, (uint32_t)pb[e].y, (uint32_t)pb[e].z, (uint32_t)pb[e].w};
+                            uint32_t o[4];
+                            realign_words<8, 4>(W, sh, o);
+                            reinterpret_cast<uint4 *>(buf16)[v] =
+                                make_uint4(o[0] ^ 0x80008000u, o[1] ^ 0x80008000u, o[2] ^ 0x80008000u, o[3] ^ 0x80008000u);
+                        }
+                    }
+                    if (v_lo > 0 || v_hi < nv) {
+#pragma unroll 1
+                        for (int v = vb + lane; v < min(nv, vb + 32 * PS); v += 32)
+                            if (!(v >= v_lo && v < v_hi)) slow_vector(v);
+                    }
+                }
+            } else {                                // the batch buffer itself is not 16-byte aligned
                 if (it > 0) mbar_wait_long<2048>(&s_free[g], (it - 1) & 1);
                 for (int i = lane; i < P.buf_len; i += 32) {
                     const long long sx = s0 + i;
