@@ -29,7 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 BYTES_PER_FRAME = 264 + 1500          # 132 int16 samples in + 375 fp32 bins out
-TRAFFIC_BYTES_PER_FRAME = 1777        # measured DRAM bytes per frame of slide_ws_kernel (profiles/r01_slide_ws_kernel_ncu.txt)
+TRAFFIC_BYTES_PER_FRAME = 1774        # measured DRAM bytes per frame of slide_ws_kernel (profiles/r01_slide_ws_kernel_ncu.txt)
 SAMPLE_RATE = 44100
 
 
@@ -302,7 +302,7 @@ def run_b200(a):
                                                      "tile_kernel": float(allst[0, 4]) / max(runs, 1)},
                      "note": "the kernel is instruction-issue / shared-memory bound, not HBM bound (DESIGN.md 3)"},
         "clocks": clocks,
-        "gpu_launches": 4 * a.steps,
+        "gpu_launches": 5 * a.steps,      # upload, anchor, slide, min/max, tile per step
         "parity": parity,
     }
     if e2e:
