@@ -226,7 +226,9 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
 // K = N/2 pairs, streamed in k-blocks of AKB pairs through a two-stage shared-memory ring:
 //   builder warps (8)  PCM16 straight from global memory (prefetched one k-block ahead) -> byte-plane fp16 B
 //                      operand (same exact hi/lo split as the slide kernel); one elected thread also starts the
-//                      cp.async.bulk of the k-block's pre-laid-out twiddle block (A operand)
+//                      cp.async.bulk of the k-block's pre-laid-out twiddle block (A operand, 32 KB).  (Cluster
+//                      pairs sharing one multicast copy of A were tried: the L2 stream is not the limit and the
+//                      pair's cluster barriers cost more than the halved traffic saved.)
 //   MMA warp (1)       8 x tcgen05.mma per k-step (4 hi/lo products x cos/sin), accumulators in TMEM.  The hi x hi
 //                      products are integers (twiddle x 2^11 times a byte-plane sum) and get an accumulator of
 //                      their own, where fp32 addition is exact up to 2^24; the three small products (2^-8 .. 2^-19
@@ -238,6 +240,7 @@ constexpr int A_BUILD_WARPS = 8;
 constexpr int A_THREADS = 32 * (A_BUILD_WARPS + 1);
 constexpr int A_MAT_BYTES = 128 * AKB * 2;          // one [128 x AKB] fp16 matrix (A: bins, B: anchors)
 constexpr int A_STAGE_BYTES = 8 * A_MAT_BYTES;      // 4 twiddle + 4 sample matrices
+constexpr int A_STAGES = 3;                         // the twiddle block of k-block kb+2 is in flight while kb is multiplied
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -249,14 +252,15 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 
 __global__ void __launch_bounds__(A_THREADS, 1)
 anchor_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, const int *__restrict__ task_seg,
-                 const int *__restrict__ task_first, const short *__restrict__ pcm, float2 *__restrict__ anchors) {
+                 const int *__restrict__ task_first, int n_tasks, const short *__restrict__ pcm, float2 *__restrict__ anchors) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t full_a[2], full_b[2], empty[2], done;
+    __shared__ uint64_t full_a[A_STAGES], full_b[A_STAGES], empty[A_STAGES], done;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int range = blockIdx.y;
-    const int seg_idx = task_seg[blockIdx.x];
-    const int first = task_first[blockIdx.x];          // first anchor (segment-local index) of this task
+    const int task = min((int)blockIdx.x, n_tasks - 1);
+    const int seg_idx = task_seg[task];
+    const int first = task_first[task];                 // first anchor (segment-local index) of this task
     const SegDesc sd = segs[seg_idx];
     const int n_anch_seg = (sd.n_frames + GF - 1) / GF + 1;
     const long long anchor_base = (long long)sd.group0 + seg_idx;      // global index of the segment's anchor 0
@@ -265,7 +269,9 @@ anchor_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, const int *__rest
     if (warp == 0) tmem_alloc(&tmem_base_s, 512);
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) { mbar_init(&full_a[i], 1); mbar_init(&full_b[i], A_BUILD_WARPS); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < A_STAGES; ++i) {
+            mbar_init(&full_a[i], 1); mbar_init(&full_b[i], A_BUILD_WARPS); mbar_init(&empty[i], 1);
+        }
         mbar_init(&done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -279,7 +285,7 @@ anchor_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, const int *__rest
         const uint32_t idesc = make_idesc(128, AN);
         constexpr uint32_t SBO = (AKB / 8) * 128;
         for (int kb = 0; kb < n_kb; ++kb) {
-            const int s = kb & 1, ph = (kb >> 1) & 1;
+            const int s = kb % A_STAGES, ph = (kb / A_STAGES) & 1;
             mbar_wait(&full_a[s], ph);
             mbar_wait(&full_b[s], ph);
             tc_fence_after();
@@ -319,44 +325,56 @@ anchor_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, const int *__rest
         const bool vec_ok = ((reinterpret_cast<uintptr_t>(pcm) & 15) == 0) && (GF * P.hop) % 8 == 0;
         const int sh = (int)(sd.pcm_start & 7);
         uint32_t hi_w[8], lo_w[8];          // 16 samples above / below the centre for this thread's pairs, offset binary
-        auto load16 = [&](long long s0, uint32_t (&w)[8]) {         // samples s0 .. s0+15 (segment-relative)
+        int4 raw_h[3], raw_l[3];            // their raw 16-byte loads, in flight while the previous k-block is built
+        bool fast_h = false, fast_l = false;
+        // issue the loads of samples s0 .. s0+15 (segment-relative); nothing here waits for them
+        auto issue16 = [&](long long s0, int4 (&raw)[3], bool &fastflag, uint32_t (&w)[8]) {
             const long long a0 = s0 - sh;                           // start of the aligned window (segment-relative)
-            if (live && vec_ok && a0 >= 0 && a0 + (sh ? 24 : 16) <= sd.n_samples) {
+            fastflag = live && vec_ok && a0 >= 0 && a0 + (sh ? 24 : 16) <= sd.n_samples;
+            if (fastflag) {
                 const int4 *p4 = reinterpret_cast<const int4 *>(pcm + sd.pcm_start + a0);
-                const int4 v0 = __ldg(p4), v1 = __ldg(p4 + 1);
-                if (sh == 0) {
-                    w[0] = (uint32_t)v0.x; w[1] = (uint32_t)v0.y; w[2] = (uint32_t)v0.z; w[3] = (uint32_t)v0.w;
-                    w[4] = (uint32_t)v1.x; w[5] = (uint32_t)v1.y; w[6] = (uint32_t)v1.z; w[7] = (uint32_t)v1.w;
-                } else {
-                    const int4 v2 = __ldg(p4 + 2);
-                    const uint32_t W[12] = {(uint32_t)v0.x, (uint32_t)v0.y, (uint32_t)v0.z, (uint32_t)v0.w, (uint32_t)v1.x, (uint32_t)v1.y,
-                                            (uint32_t)v1.z, (uint32_t)v1.w, (uint32_t)v2.x, (uint32_t)v2.y, (uint32_t)v2.z, (uint32_t)v2.w};
-                    realign_words<12, 8>(W, sh, w);
-                }
+                raw[0] = __ldg(p4); raw[1] = __ldg(p4 + 1);
+                if (sh) raw[2] = __ldg(p4 + 2);
+            } else if (!live) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) w[i] ^= 0x80008000u;
-            } else {
+                for (int i = 0; i < 8; ++i) w[i] = 0x80008000u;
+            } else {                                                // first / last anchors of a segment: centre padding
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     uint32_t u[2];
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const long long sx = s0 + 2 * i + h;
-                        u[h] = (live && sx >= 0 && sx < sd.n_samples) ? ((uint32_t)(uint16_t)__ldg(pcm + sd.pcm_start + sx) ^ 0x8000u) : 0x8000u;
+                        u[h] = (sx >= 0 && sx < sd.n_samples) ? ((uint32_t)(uint16_t)__ldg(pcm + sd.pcm_start + sx) ^ 0x8000u) : 0x8000u;
                     }
                     w[i] = u[0] | (u[1] << 16);
                 }
             }
         };
+        // first use of the loaded vectors: re-align (file not on a 16-byte boundary) and flip to offset binary
+        auto finish16 = [&](const int4 (&raw)[3], bool fastflag, uint32_t (&w)[8]) {
+            if (!fastflag) return;
+            if (sh == 0) {
+                w[0] = (uint32_t)raw[0].x; w[1] = (uint32_t)raw[0].y; w[2] = (uint32_t)raw[0].z; w[3] = (uint32_t)raw[0].w;
+                w[4] = (uint32_t)raw[1].x; w[5] = (uint32_t)raw[1].y; w[6] = (uint32_t)raw[1].z; w[7] = (uint32_t)raw[1].w;
+            } else {
+                const uint32_t W[12] = {(uint32_t)raw[0].x, (uint32_t)raw[0].y, (uint32_t)raw[0].z, (uint32_t)raw[0].w,
+                                        (uint32_t)raw[1].x, (uint32_t)raw[1].y, (uint32_t)raw[1].z, (uint32_t)raw[1].w,
+                                        (uint32_t)raw[2].x, (uint32_t)raw[2].y, (uint32_t)raw[2].z, (uint32_t)raw[2].w};
+                realign_words<12, 8>(W, sh, w);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] ^= 0x80008000u;
+        };
         auto prefetch = [&](int kb) {
             const int j0 = kb * AKB + 16 * half16;                  // first pair of this thread in the k-block
-            load16(c + j0, hi_w);                                   // pair j <-> sample c + j
-            load16(c - j0 - 16, lo_w);                              //            and sample c - 1 - j
+            issue16(c + j0, raw_h, fast_h, hi_w);                   // pair j <-> sample c + j
+            issue16(c - j0 - 16, raw_l, fast_l, lo_w);              //            and sample c - 1 - j
         };
         prefetch(0);
         for (int kb = 0; kb < n_kb; ++kb) {
-            const int s = kb & 1, ph = (kb >> 1) & 1;
-            mbar_wait(&empty[s], ph ^ 1);                           // the MMAs of k-block kb-2 have consumed this stage
+            const int s = kb % A_STAGES, ph = (kb / A_STAGES) & 1;
+            mbar_wait(&empty[s], ph ^ 1);                           // the MMAs of k-block kb-A_STAGES have consumed this stage
             unsigned char *sA = smem_raw + (size_t)s * A_STAGE_BYTES, *sBm = sA + 4 * A_MAT_BYTES;
             if (tid == 0) {
                 mbar_expect_tx(&full_a[s], 4 * A_MAT_BYTES);
@@ -364,6 +382,8 @@ anchor_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, const int *__rest
                          4 * A_MAT_BYTES, &full_a[s]);
             }
             const int j0 = kb * AKB + 16 * half16;
+            finish16(raw_h, fast_h, hi_w);
+            finish16(raw_l, fast_l, lo_w);
 #pragma unroll
             for (int u = 0; u < 2; ++u) {                           // two units of 8 pairs
                 uint32_t ph4[4], pl4[4], mh4[4], ml4[4];
@@ -1065,7 +1085,7 @@ int nbm::tc_plan_create(const nbm_frontend_params &p, TcPlan **out) {
     k.rot = reinterpret_cast<const float2 *>(d + b_slide + b_anchor + 3 * b_c);
     pl->smem_slide = WS_G * ((size_t)4 * CF * KP * 2 + (size_t)128 * ST_LD * 8 + (size_t)k.buf_len * 2) +
                      (size_t)4 * 128 * 16 * 2 * std::max(0, k.nk - NK_T);
-    pl->smem_anchor = (size_t)2 * A_STAGE_BYTES + 128;
+    pl->smem_anchor = (size_t)A_STAGES * A_STAGE_BYTES + 128;
     int dev = 0, sms = 0, max_smem = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1118,8 +1138,9 @@ int nbm::tc_bins_per_slot() { return ROWS_PER_EWARP; }
 int nbm::tc_launch_anchors(const TcPlan *pl, const SegDesc *d_segs, const int *d_task_seg, const int *d_task_first,
                            int n_tasks, const void *d_pcm, void *d_anchors, cudaStream_t stream) {
     const TcParams &k = pl->p;
+    if (n_tasks <= 0) return NBM_OK;
     dim3 ga((unsigned)n_tasks, (unsigned)k.n_ranges);
-    anchor_tc_kernel<<<ga, A_THREADS, pl->smem_anchor, stream>>>(k, d_segs, d_task_seg, d_task_first,
+    anchor_tc_kernel<<<ga, A_THREADS, pl->smem_anchor, stream>>>(k, d_segs, d_task_seg, d_task_first, n_tasks,
                                                                  reinterpret_cast<const short *>(d_pcm),
                                                                  reinterpret_cast<float2 *>(d_anchors));
     NBM_CUDA(cudaGetLastError());
