@@ -497,23 +497,21 @@ namespace {
 
 // Everything the host derives from the per-file sample counts: STFT chunks (prepare_dataset.py:236),
 // detector windows (:266) with the last window's valid width (:268-278 incl. the seam quirk), the
-// 64-frame groups, the anchor tasks of the tensor-core path, and the workspace carve-up
-//   [segs | files | task_seg | task_first | min/max codes | anchors | dB bands].
+// 64-frame groups, and the workspace carve-up
+//   [segs | files | min/max partials | anchors | dB bands].
 struct BatchLayout {
     std::vector<SegDesc> segs;
     std::vector<FileDesc> files;
-    std::vector<int> task_seg, task_first;
     std::vector<int64_t> n_frames;
     size_t spec_floats = 0;
     long long tiles = 0, n_anchors = 0;
     int groups = 0;
-    size_t o_segs = 0, o_files = 0, o_tseg = 0, o_tfirst = 0, o_mm = 0, o_anchors = 0, o_spec = 0, total = 0;
-    size_t upload_bytes = 0;       // segs .. task_first are uploaded from the host
+    size_t o_segs = 0, o_files = 0, o_mm = 0, o_anchors = 0, o_spec = 0, total = 0;
+    size_t upload_bytes = 0;       // segs and files are uploaded from the host
 };
 
 int build_layout(const nbm_frontend_plan *pl, const int64_t *sizes, const int64_t *offsets, int n_files, BatchLayout &B) {
     const nbm_frontend_params &p = pl->prm;
-    const int na_group = pl->tc ? tc_anchor_group() : 1;
     B.files.resize(n_files);
     B.n_frames.resize(n_files);
     for (int f = 0; f < n_files; ++f) {
@@ -538,8 +536,6 @@ int build_layout(const nbm_frontend_plan *pl, const int64_t *sizes, const int64_
             sd.file = f;
             sd.group0 = B.groups;
             const int tiles_seg = (sd.n_frames + GF - 1) / GF;
-            if (pl->tc)
-                for (int a0 = 0; a0 < tiles_seg + 1; a0 += na_group) { B.task_seg.push_back((int)B.segs.size()); B.task_first.push_back(a0); }
             B.groups += tiles_seg;
             B.n_anchors += tiles_seg + 1;
             B.segs.push_back(sd);
@@ -581,8 +577,6 @@ int build_layout(const nbm_frontend_plan *pl, const int64_t *sizes, const int64_
     auto take = [&](size_t bytes) { const size_t at = o; o = align_up(o + bytes, 256); return at; };
     B.o_segs = take(B.segs.size() * sizeof(SegDesc));
     B.o_files = take(B.files.size() * sizeof(FileDesc));
-    B.o_tseg = take(B.task_seg.size() * sizeof(int));
-    B.o_tfirst = take(B.task_first.size() * sizeof(int));
     B.upload_bytes = o;
     B.o_mm = take((size_t)B.groups * (pl->tc ? (GF / tc_chain_frames()) * tc_n_ranges(pl->tc) * tc_slots_per_range() : 1) *
                   sizeof(float2));                                  // min/max partials
@@ -793,8 +787,6 @@ extern "C" int nbm_frontend_run_batch(const nbm_frontend_plan *cpl, const void *
     char *ws = reinterpret_cast<char *>(d_workspace);
     SegDesc *d_segs = reinterpret_cast<SegDesc *>(ws + B.o_segs);
     FileDesc *d_files = reinterpret_cast<FileDesc *>(ws + B.o_files);
-    const int *d_tseg = reinterpret_cast<const int *>(ws + B.o_tseg);
-    const int *d_tfirst = reinterpret_cast<const int *>(ws + B.o_tfirst);
     float2 *d_tile_mm = reinterpret_cast<float2 *>(ws + B.o_mm);
     float *d_spec = reinterpret_cast<float *>(ws + B.o_spec);
 
@@ -811,10 +803,6 @@ extern "C" int nbm_frontend_run_batch(const nbm_frontend_plan *cpl, const void *
         char *h = reinterpret_cast<char *>(pl->h_stage);
         memcpy(h + B.o_segs, B.segs.data(), B.segs.size() * sizeof(SegDesc));
         memcpy(h + B.o_files, B.files.data(), B.files.size() * sizeof(FileDesc));
-        if (!B.task_seg.empty()) {
-            memcpy(h + B.o_tseg, B.task_seg.data(), B.task_seg.size() * sizeof(int));
-            memcpy(h + B.o_tfirst, B.task_first.data(), B.task_first.size() * sizeof(int));
-        }
         const size_t n16 = (up + 15) / 16;
         upload_kernel<<<(unsigned)std::min<size_t>(64, (n16 + 255) / 256), 256, 0, stream>>>(
             reinterpret_cast<uint4 *>(ws), reinterpret_cast<const uint4 *>(pl->h_stage), n16);
@@ -863,10 +851,9 @@ extern "C" int nbm_frontend_run_batch(const nbm_frontend_plan *cpl, const void *
         const long long tile0 = fa.tile0, tile1 = fz.tile0 + fz.n_tiles;
         if (prof) NBM_CUDA(cudaEventRecord(pl->ev[sub][0], sc));
         if (use_tc) {
-            int t0 = 0, t1 = (int)B.task_seg.size();           // anchor tasks of these segments (task_seg is sorted)
-            t0 = (int)(std::lower_bound(B.task_seg.begin(), B.task_seg.end(), seg0) - B.task_seg.begin());
-            t1 = (int)(std::lower_bound(B.task_seg.begin(), B.task_seg.end(), seg1) - B.task_seg.begin());
-            rc = tc_launch_anchors(pl->tc, d_segs, d_tseg + t0, d_tfirst + t0, t1 - t0, d_pcm, ws + B.o_anchors, sc);
+            // globally numbered anchors of these segments: group0[s] + s .. group0[s] + s + tiles[s]
+            rc = tc_launch_anchors(pl->tc, d_segs, seg0, seg1, (long long)grp0 + seg0, (long long)grp1 + seg1, d_pcm,
+                                   ws + B.o_anchors, sc);
             if (rc != NBM_OK) return rc;
             if (prof) NBM_CUDA(cudaEventRecord(pl->ev[sub][1], sc));
             rc = tc_launch_slides(pl->tc, d_segs, (int)B.segs.size(), seg0, grp0, grp1, d_pcm, d_spec, d_tile_mm,

@@ -251,19 +251,16 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 }
 
 __global__ void __launch_bounds__(A_THREADS, 1)
-anchor_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, const int *__restrict__ task_seg,
-                 const int *__restrict__ task_first, int n_tasks, const short *__restrict__ pcm, float2 *__restrict__ anchors) {
+anchor_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, int seg_lo, int seg_hi, long long anchor_begin,
+                 long long anchor_end, const short *__restrict__ pcm, float2 *__restrict__ anchors) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t full_a[A_STAGES], full_b[A_STAGES], empty[A_STAGES], done;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int range = blockIdx.y;
-    const int task = min((int)blockIdx.x, n_tasks - 1);
-    const int seg_idx = task_seg[task];
-    const int first = task_first[task];                 // first anchor (segment-local index) of this task
-    const SegDesc sd = segs[seg_idx];
-    const int n_anch_seg = (sd.n_frames + GF - 1) / GF + 1;
-    const long long anchor_base = (long long)sd.group0 + seg_idx;      // global index of the segment's anchor 0
+    // Anchors are numbered globally: segment s owns numbers group0[s] + s .. group0[s] + s + tiles[s] (frames 64 i and
+    // the one just past its end), so a CTA's AN anchors may span several segments and every CTA but the last is full.
+    const long long ag0 = anchor_begin + (long long)blockIdx.x * AN;
     const int n_kb = P.n_stages;
 
     if (warp == 0) tmem_alloc(&tmem_base_s, 512);
@@ -317,10 +314,17 @@ anchor_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, const int *__rest
     } else {
         // ================================ builders: thread = (anchor a, 16 pairs of the k-block) ===========
         const int a = tid & (AN - 1), half16 = tid >> 7;            // half16 in {0, 1}
-        const int ai = first + a;
-        const bool live = ai < n_anch_seg;
+        const long long ag = ag0 + a;
+        const bool live = ag < anchor_end;
+        int lo_s = seg_lo, hi_s = seg_hi - 1;                       // this anchor's segment: last s with group0[s] + s <= ag
+        while (lo_s < hi_s) {
+            const int mid = (lo_s + hi_s + 1) >> 1;
+            if ((long long)segs[mid].group0 + mid <= ag) lo_s = mid; else hi_s = mid - 1;
+        }
+        const SegDesc sd = segs[lo_s];
+        const int ai = (int)(ag - ((long long)sd.group0 + lo_s));  // frame 64 ai of the segment
         const long long c = (long long)ai * GF * P.hop;            // segment-relative index of the frame centre
-        // c and the pair offsets are multiples of 8 samples, so every 16-sample run of this CTA starts `sh`
+        // c and the pair offsets are multiples of 8 samples, so every 16-sample run of this thread starts `sh`
         // samples after a 16-byte boundary (sh = 0 when the file starts on one)
         const bool vec_ok = ((reinterpret_cast<uintptr_t>(pcm) & 15) == 0) && (GF * P.hop) % 8 == 0;
         const int sh = (int)(sd.pcm_start & 7);
@@ -431,12 +435,12 @@ anchor_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, const int *__rest
                 for (int i = 0; i < 32; ++i) as[i] += v[i];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    const int an = first + c0 + i;
-                    if (an < n_anch_seg) {
+                    const long long an = ag0 + c0 + i;
+                    if (an < anchor_end) {
                         // R = (c0 - i s0)(A - iB)
                         const float rr = rot.x * ac[i] - rot.y * as[i];
                         const float ri = -(rot.x * as[i] + rot.y * ac[i]);
-                        anchors[(anchor_base + an) * (P.n_ranges * 128) + range * 128 + row] = make_float2(rr, ri);
+                        anchors[an * (P.n_ranges * 128) + range * 128 + row] = make_float2(rr, ri);
                     }
                 }
             }
@@ -1128,19 +1132,18 @@ extern "C" int nbm_debug_ws_timing(unsigned long long *out, int reset) {
 }
 #endif
 
-int nbm::tc_anchor_group() { return AN; }
 int nbm::tc_n_ranges(const TcPlan *pl) { return pl->p.n_ranges; }
 int nbm::tc_bins_per_range() { return BINS_PER_RANGE; }
 int nbm::tc_chain_frames() { return CF; }
 int nbm::tc_slots_per_range() { return 4; }
 int nbm::tc_bins_per_slot() { return ROWS_PER_EWARP; }
 
-int nbm::tc_launch_anchors(const TcPlan *pl, const SegDesc *d_segs, const int *d_task_seg, const int *d_task_first,
-                           int n_tasks, const void *d_pcm, void *d_anchors, cudaStream_t stream) {
+int nbm::tc_launch_anchors(const TcPlan *pl, const SegDesc *d_segs, int seg_lo, int seg_hi, long long anchor_begin,
+                           long long anchor_end, const void *d_pcm, void *d_anchors, cudaStream_t stream) {
     const TcParams &k = pl->p;
-    if (n_tasks <= 0) return NBM_OK;
-    dim3 ga((unsigned)n_tasks, (unsigned)k.n_ranges);
-    anchor_tc_kernel<<<ga, A_THREADS, pl->smem_anchor, stream>>>(k, d_segs, d_task_seg, d_task_first, n_tasks,
+    if (anchor_end <= anchor_begin) return NBM_OK;
+    dim3 ga((unsigned)((anchor_end - anchor_begin + AN - 1) / AN), (unsigned)k.n_ranges);
+    anchor_tc_kernel<<<ga, A_THREADS, pl->smem_anchor, stream>>>(k, d_segs, seg_lo, seg_hi, anchor_begin, anchor_end,
                                                                  reinterpret_cast<const short *>(d_pcm),
                                                                  reinterpret_cast<float2 *>(d_anchors));
     NBM_CUDA(cudaGetLastError());

@@ -23,17 +23,16 @@ int tc_plan_create(const nbm_frontend_params &p, TcPlan **out);
 void tc_plan_destroy(TcPlan *pl);
 // bytes of anchor scratch for `n_anchors` anchor frames (sum over segments of tiles + 1)
 size_t tc_anchor_bytes(const TcPlan *pl, long long n_anchors);
-// anchors per anchor task: the host builds one (segment, first anchor) task per this many anchors of a segment
-int tc_anchor_group();
 int tc_n_ranges(const TcPlan *pl);      // 128-row bin ranges (min/max slots per group)
 int tc_bins_per_range();               // output bins per range
 // min/max partials: one float2 per (32-frame chain, range, slot); slot s of a range covers tc_bins_per_slot() bins
 int tc_chain_frames();
 int tc_slots_per_range();
 int tc_bins_per_slot();
-// anchors: tcgen05 GEMM over the N/2 folded pairs of every 64th frame (mono PCM16 only)
-int tc_launch_anchors(const TcPlan *pl, const SegDesc *d_segs, const int *d_task_seg, const int *d_task_first, int n_tasks,
-                      const void *d_pcm, void *d_anchors, cudaStream_t stream);
+// anchors: tcgen05 GEMM over the N/2 folded pairs of every 64th frame (mono PCM16 only), for the globally numbered
+// anchors [anchor_begin, anchor_end) of segments [seg_lo, seg_hi) (segment s owns group0[s] + s .. + tiles[s])
+int tc_launch_anchors(const TcPlan *pl, const SegDesc *d_segs, int seg_lo, int seg_hi, long long anchor_begin,
+                      long long anchor_end, const void *d_pcm, void *d_anchors, cudaStream_t stream);
 // slides: tcgen05 GEMM over hop/2 pairs + recurrence + Hann + dB for every frame, per-(chain, range, slot) min/max
 // for the 64-frame groups [group_begin, group_end), which start in segment seg_begin
 int tc_launch_slides(const TcPlan *pl, const SegDesc *d_segs, int n_segs, int seg_begin, int group_begin, int group_end,
