@@ -57,11 +57,15 @@ def peaks():
 
 # ------------------------------------------------------------------ clocks sampling ---------
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+    """nvidia-smi polled every 100 ms from BEFORE the warm-up (its start-up takes up to a second on an 8-GPU box);
+    the samples whose timestamps fall inside the timed region are the ones reported, and if the region was too
+    short to catch one, the samples taken under load during warm-up + timed region (the dict says which)."""
+    Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index: int):
         self.rows, self.proc, self.index = [], None, index
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
@@ -75,28 +79,45 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)                     # let the sample that covers the end of the region arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for n, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except Exception:
-                pass
+
+        def summarise(rows):
+            sm, mx, reasons = [], [], set()
+            for _, r in rows:
+                try:
+                    sm.append(float(r[1])); mx.append(float(r[2]))
+                    for n, v in zip(names, r[4:8]):
+                        if v.lower().startswith("active"):
+                            reasons.add(n)
+                except Exception:
+                    pass
+            return sm, mx, reasons
+
+        inside = [x for x in self.rows if self.t0 is not None and self.t0 <= x[0] <= (self.t1 or 1e30) + 0.12]
+        window = "timed region"
+        sm, mx, reasons = summarise(inside)
+        if not sm:                           # region shorter than the polling period: samples under load since warm-up began
+            window = "warm-up + timed region"
+            sm, mx, reasons = summarise(self.rows[1:] if len(self.rows) > 1 else self.rows)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------ synthetic audio ----------
@@ -172,6 +193,29 @@ def run_reference(a):
     print(json.dumps(line))
 
 
+def bind_near_gpu(index: int):
+    """Pin this process to the CPUs of the GPU's NUMA node before the pinned host buffers are allocated, so the
+    H2D copies of the end-to-end leg do not cross sockets (one process per GPU).  Returns the node or None."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------ B200 arm ------------------
 def run_b200(a):
     import torch
@@ -204,19 +248,21 @@ def run_b200(a):
     def step():
         plan.run_batch(pcm, offs, out=tiles)
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(a.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     plan.set_profiling(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     e0.record()
     for _ in range(a.steps):
         step()
     e1.record()
     barrier()
+    sampler.mark_end()
     ms = e0.elapsed_time(e1)
     kern_ms, runs = plan.get_profile_kernels()
     stft_ms, tile_ms = kern_ms["stft"], kern_ms["tile"]
@@ -225,7 +271,10 @@ def run_b200(a):
 
     # ---- end to end: PCM in pinned host memory -> tiles on the device, min/max read back -------
     e2e = None
+    numa = None
     if not a.no_e2e:
+        all_cpus = os.sched_getaffinity(0)
+        numa = bind_near_gpu(local)
         host = torch.empty(pcm.shape, dtype=torch.int16).pin_memory()
         host.copy_(pcm.cpu())
         mm_host = torch.empty((a.clips, 2), dtype=torch.float32).pin_memory()
@@ -248,6 +297,7 @@ def run_b200(a):
         e2e_ms = f0.elapsed_time(f1) / k
         e2e = (e2e_ms, host.numel() * 2, mm_host.numel() * 4)
         del host
+        os.sched_setaffinity(0, all_cpus)
 
     # ---- parity spot check on this very data (first clip) against the oracle --------------------
     parity = None
@@ -308,7 +358,7 @@ def run_b200(a):
     if e2e:
         e_ms = float(allst[:, 5].max())
         line["e2e"] = {"value": total_hours / (e_ms / 1e3), "unit": "audio-hours/s", "h2d_bytes_per_step": e2e[1],
-                       "d2h_bytes_per_step": e2e[2], "ms_per_step": e_ms,
+                       "d2h_bytes_per_step": e2e[2], "ms_per_step": e_ms, "host_numa_node": numa,
                        "note": "FrontendPlan.run_batch_from_host: pinned host PCM16 -> H2D in 64-file chunks on a side stream, "
                                "overlapped with the front-end; tiles stay on the device for the detector; "
                                "per-file (s_min, s_max) read back"}
