@@ -1,19 +1,21 @@
 // Tensor-core front-end for sm_100a: the sliding DFT of frontend.cu with its two contractions
-// moved onto tcgen05.mma (accumulators in TMEM).
+// moved onto tcgen05.mma (accumulators in TMEM).  Mono PCM16 input.
 //
 //   anchors   R_a[k]  = sum_n x[a*hop - N/2 + n] w^(kn)            one frame in 64, K = N/2 folded pairs
 //   slides    D_t[k]  = sum_m (x[s_t+N+m] - x[s_t+m]) w^(km)       every frame, K = hop/2 folded pairs
 //   R_{t+1} = w^(-hop k)(R_t + D_t),   X_t[k] = R_t[k]/2 - (R_t[k-1] + R_t[k+1])/4  (Hann),   dB
 //
 // GEMM orientation: M = 128 frequency bins (TMEM lanes), N = frames (TMEM columns), K = folded sample
-// pairs.  A = twiddles (cos / sin), resident in shared memory for the CTA's whole life; B = folded
-// samples built by the CTA from int16 PCM.  After tcgen05.ld each thread owns ONE bin and a run of
-// consecutive frames in registers, so the per-frame recurrence is a register chain with no shuffles.
+// pairs.  A = twiddles (cos / sin): resident in TMEM for the slide kernel, streamed through shared
+// memory by cp.async.bulk for the anchor kernel.  B = folded samples built from int16 PCM.  After
+// tcgen05.ld each thread owns ONE bin and a run of consecutive frames in registers, so the per-frame
+// recurrence is a register chain with no shuffles.
 //
-// Precision: PCM sums are 18-bit integers, exact as fp16 hi + lo (scaled by 1/8); twiddles are
-// hi + 2^-11 lo'.  Three fp16 products (hi*hi, lo*hi, hi'*lo' with hi' = 2^-11 hi kept normal) reproduce
-// the fp32 product to ~2^-24; accumulation is fp32 in TMEM.  The anchor contraction (K = 662) is split
-// over 8 TMEM accumulators summed in the epilogue to keep fp32 accumulation chains short.
+// Precision: everything fed to the tensor core is exact.  Twiddles are 2^11 w = H + L (two fp16 at the
+// same scale); samples are split into BYTE PLANES (a folded sum or difference of int16 samples is formed
+// separately on the high and low bytes in packed half arithmetic, value / 256 = hi + lo), so the four
+// products (H + L)(hi + lo) reproduce the fp32 product; accumulation is fp32 in TMEM, which truncates:
+// the integer-valued H x hi products get their own accumulator (anchors) or are added last (slides).
 //
 // Shared-memory operands use the canonical K-major, no-swizzle UMMA layout: 8x8 core matrices of
 // 128 contiguous bytes, K-adjacent core matrices contiguous (LBO = 128 B), 8-row groups SBO apart.
@@ -25,18 +27,17 @@
 
 namespace nbm {
 
-constexpr int TC_THREADS = 256;
 constexpr int BINS_PER_RANGE = 126;     // rows 1..126 of each 128-row range are emitted, 0 and 127 are Hann halos
-constexpr int PADF = 8;                 // front padding (floats) of the sample buffer
+constexpr int PADF = 8;                 // front padding (samples) of the sample buffer
 
 struct TcParams {
     int N, hop, low_idx, n_bins, n_ranges;
     int npH, KP, nk;            // hop/2 pairs, padded K of the slide GEMM, k-steps
     int npN, n_stages;          // N/2 pairs, anchor k-blocks of AKB pairs
     int off;                    // sample-buffer offset making the 8-pair vectors 16 B aligned
-    int buf_len;                // floats in the sample buffer
+    int buf_len;                // samples in the per-chain sample buffer
     float min_level_sq;
-    const __half *a_slide;      // [n_ranges][4][128 x KP]  (cos_h, cos_l, sin_h, sin_l) UMMA layout
+    const __half *a_slide;      // [n_ranges][128 rows][cos_h, cos_l, sin_h, sin_l][KP], row-contiguous (copied into TMEM lanes)
     const __half *a_anchor;     // [n_ranges][n_stages][cos_h, cos_l, sin_h, sin_l][128 x AKB] UMMA layout
     const float2 *cf, *gf, *gb, *rot;   // [n_ranges*128] per-bin constants
 };
@@ -109,16 +110,6 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 __host__ __device__ constexpr uint32_t make_idesc(int M, int Ncols) {
     return (1u << 4) | ((uint32_t)(Ncols >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                 : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
@@ -147,14 +138,6 @@ __host__ __device__ inline size_t umma_off(int row, int k, int kext) {
 
 
 
-__device__ __forceinline__ int find_seg(const SegDesc *segs, int n_segs, int tile) {
-    int lo = 0, hi = n_segs - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (segs[mid].group0 <= tile) lo = mid; else hi = mid - 1;
-    }
-    return lo;
-}
 
 // ------------------------------------------------------------------------- shared helpers -----
 // Re-alignment of 16-bit samples read with aligned 16-byte loads: W holds NW consecutive 32-bit words (two samples
@@ -185,18 +168,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 }
 __device__ __forceinline__ __half2 u32_as_h2(uint32_t u) { return *reinterpret_cast<__half2 *>(&u); }
 __device__ __forceinline__ uint32_t h2_as_u32(__half2 h) { return *reinterpret_cast<uint32_t *>(&h); }
-__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                 : "r"(taddr) : "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -479,25 +450,6 @@ constexpr int TM_COLS = 512;
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-// 8 values -> fp16 hi and lo (= v - hi), each packed as one 16-byte vector
-__device__ __forceinline__ void split8_hl(const float (&v)[8], uint4 &h, uint4 &l) {
-    uint32_t hh[4], ll[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const __half2 hp = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-        const float2 hf = __half22float2(hp);
-        const __half2 lp = __floats2half2_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
-        hh[i] = *reinterpret_cast<const uint32_t *>(&hp);
-        ll[i] = *reinterpret_cast<const uint32_t *>(&lp);
-    }
-    h = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-    l = make_uint4(ll[0], ll[1], ll[2], ll[3]);
-}
-// two offset-binary PCM16 samples packed in one word -> floats 2^9 + u 2^-14 (differences of two such are exact)
-__device__ __forceinline__ void unpack2(uint32_t w, float &f0, float &f1) {
-    f0 = __uint_as_float(__byte_perm(w, 0x44000000u, 0x7610));
-    f1 = __uint_as_float(__byte_perm(w, 0x44000000u, 0x7632));
 }
 
 // Chain -> segment bookkeeping kept in registers; the descriptor is re-read only when the segment changes.
