@@ -911,7 +911,8 @@ slide_ws_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int se
                 char *out = reinterpret_cast<char *>(spec + cw.sd.spec_off + (long long)(range * BINS_PER_RANGE + ra - 1) * stride + t0 + fc);
                 const long long stride_b = (long long)stride * 4;
                 const bool pair_ok = (cw.sd.spec_off & 1) == 0;          // a later STFT chunk of a long file may start on an odd column
-#pragma unroll 2
+                // unroll 4 measured best: 2 lacks ILP, 8 (or a fixed-trip fully unrolled loop) loses more to instruction fetch
+#pragma unroll 4
                 for (int r = ra; r < rb; ++r) {
                     const float4 nx = st[(r + 1) * LD4];
                     // 4 X = 2 R[k] - (R[k-1] + R[k+1]);  10 log10(|X|^2) = 10 log10(|4X|^2) - 10 log10(16)
