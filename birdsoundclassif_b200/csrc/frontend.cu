@@ -19,6 +19,9 @@
 #include <cmath>
 
 #include <cstdlib>
+#include <type_traits>
+
+#include <cuda.h>
 
 #include "common.cuh"
 #include "frontend_tc.cuh"
@@ -39,6 +42,7 @@ struct FileDesc {
     int last_width;        // valid columns of the last tile (rest is reflect padding)
     int group0, n_groups;  // the file's 64-frame groups (contiguous)
     int seg0, n_segs;      // the file's STFT chunks (contiguous)
+    unsigned int done_target;   // units the slide kernel publishes for this file (fused tiling), 0 otherwise
 };
 
 struct KParams {
@@ -289,16 +293,15 @@ __device__ __forceinline__ double block_sum_256(double v, double *red) {
     return t;
 }
 
-__global__ void __launch_bounds__(256)
-refine_minmax_kernel(RefineParams R, const SegDesc *__restrict__ segs, const FileDesc *__restrict__ files,
-                     const float2 *__restrict__ tile_mm, float *__restrict__ spec, const void *__restrict__ pcm,
-                     int dtype, int channels, float *__restrict__ out, int file_begin) {
+__device__ __forceinline__ void
+refine_file(const RefineParams &R, const SegDesc *__restrict__ segs, const FileDesc *__restrict__ files,
+            const float2 *__restrict__ tile_mm, float *__restrict__ spec, const void *__restrict__ pcm,
+            int dtype, int channels, float *__restrict__ out, int file) {
     __shared__ float s_red[16];
     __shared__ double d_red[16];
     __shared__ int c_seg[REFINE_CAP], c_bin[REFINE_CAP], c_frame[REFINE_CAP];
     __shared__ int n_cand, n_hot, hot[REFINE_CAP];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int file = blockIdx.x + file_begin;
     const FileDesc fd = files[file];
     const int per_gf = GF / R.mm_frames, n_slots = R.n_ranges * R.slots_per_range;
     const int n_ent = fd.n_groups * per_gf * n_slots;
@@ -384,6 +387,13 @@ refine_minmax_kernel(RefineParams R, const SegDesc *__restrict__ segs, const Fil
     }
 }
 
+__global__ void __launch_bounds__(256)
+refine_minmax_kernel(RefineParams R, const SegDesc *__restrict__ segs, const FileDesc *__restrict__ files,
+                     const float2 *__restrict__ tile_mm, float *__restrict__ spec, const void *__restrict__ pcm,
+                     int dtype, int channels, float *__restrict__ out, int file_begin) {
+    refine_file(R, segs, files, tile_mm, spec, pcm, dtype, channels, out, blockIdx.x + file_begin);
+}
+
 // Descriptor upload without the copy engine: a DMA copy on the caller's stream would queue behind whatever large
 // H2D transfer (the next chunk of PCM) is in flight on the same engine and stall the kernels that wait for it.
 // Pinned host memory is device-addressable under UVA, so a few warps simply read it.
@@ -409,29 +419,55 @@ __device__ __forceinline__ int reflect_src(int c, int width, int period) {
     return r < width ? r : period - r;
 }
 
-template <bool VEC4>
-__global__ void __launch_bounds__(256)
-tile_kernel(KParams P, const FileDesc *__restrict__ files, int n_files, const float *__restrict__ spec,
-            const float *__restrict__ minmax, float *__restrict__ tiles, long long tile_begin) {
-    const long long tile = blockIdx.x + tile_begin;
-    int lo_f = 0, hi_f = n_files - 1;
-    while (lo_f < hi_f) {
-        int mid = (lo_f + hi_f + 1) >> 1;
-        if (files[mid].tile0 <= tile) lo_f = mid; else hi_f = mid - 1;
-    }
-    const FileDesc fd = files[lo_f];
+template <bool VEC4, bool L2_ONLY>
+__device__ __forceinline__ void
+tile_block(const KParams &P, const FileDesc &fd, long long tile, int row_block, float smin, float smax,
+           const float *__restrict__ spec, float *__restrict__ tiles) {
     const int kt = (int)(tile - fd.tile0);
     const int start = kt * P.hop_spectro;
     const int width = (kt == fd.n_tiles - 1) ? fd.last_width : P.w_pix;
-    const float smin = minmax[2 * lo_f], smax = minmax[2 * lo_f + 1];
     const float range = smax - smin;
     const float inv = 1.0f / range;
-    const int r0 = blockIdx.y * TILE_ROWS;
+    const int r0 = row_block * TILE_ROWS;
     const int r1 = min(r0 + TILE_ROWS, P.n_bins);
     const int period = 2 * (width - 1);
     const float *sbase = spec + fd.spec_off + start;
     float *tbase = tiles + (tile * P.n_bins) * P.w_pix;
-    if (VEC4) {
+    // L2_ONLY: the band was written by other SMs during this very launch; read it from L2, never through L1
+    auto ld = [](const float *p) { return L2_ONLY ? __ldcg(p) : *p; };
+    if (VEC4 && L2_ONLY && width == P.w_pix) {
+        // Full tile read from L2: four scalar loads per thread would each fetch a quarter of every 32-byte sector they
+        // touch (4x the L2 -> SM traffic once L1 is bypassed).  Rows are 128-byte aligned (row_stride % 32 == 0), so
+        // the tile's misalignment is start & 3 for every row: two aligned 16-byte loads, re-aligned in registers.
+        const int sh = start & 3;
+        auto rows = [&](auto SH) {
+            constexpr int S = decltype(SH)::value;
+            for (int c = 4 * threadIdx.x; c < P.w_pix; c += 4 * blockDim.x) {
+#pragma unroll 5
+                for (int r = r0; r < r1; ++r) {
+                    const float4 *q = reinterpret_cast<const float4 *>(sbase + (long long)r * fd.row_stride + c - S);
+                    const float4 a = __ldcg(q);
+                    float4 b = a;
+                    if (S != 0) b = __ldcg(q + 1);
+                    float4 v;
+                    if (S == 0) v = a;
+                    else if (S == 1) v = make_float4(a.y, a.z, a.w, b.x);
+                    else if (S == 2) v = make_float4(a.z, a.w, b.x, b.y);
+                    else v = make_float4(a.w, b.x, b.y, b.z);
+                    float4 o;
+                    o.x = norm_div(v.x - smin, range, inv);
+                    o.y = norm_div(v.y - smin, range, inv);
+                    o.z = norm_div(v.z - smin, range, inv);
+                    o.w = norm_div(v.w - smin, range, inv);
+                    __stcs(reinterpret_cast<float4 *>(tbase + (long long)r * P.w_pix + c), o);
+                }
+            }
+        };
+        if (sh == 0) rows(std::integral_constant<int, 0>{});
+        else if (sh == 1) rows(std::integral_constant<int, 1>{});
+        else if (sh == 2) rows(std::integral_constant<int, 2>{});
+        else rows(std::integral_constant<int, 3>{});
+    } else if (VEC4) {
         for (int c = 4 * threadIdx.x; c < P.w_pix; c += 4 * blockDim.x) {
             int src[4];
             if (c + 3 < width) { src[0] = c; src[1] = c + 1; src[2] = c + 2; src[3] = c + 3; }
@@ -443,10 +479,10 @@ tile_kernel(KParams P, const FileDesc *__restrict__ files, int n_files, const fl
             for (int r = r0; r < r1; ++r) {
                 const float *sp = sbase + (long long)r * fd.row_stride;
                 float4 o;
-                o.x = norm_div(sp[src[0]] - smin, range, inv);
-                o.y = norm_div(sp[src[1]] - smin, range, inv);
-                o.z = norm_div(sp[src[2]] - smin, range, inv);
-                o.w = norm_div(sp[src[3]] - smin, range, inv);
+                o.x = norm_div(ld(sp + src[0]) - smin, range, inv);
+                o.y = norm_div(ld(sp + src[1]) - smin, range, inv);
+                o.z = norm_div(ld(sp + src[2]) - smin, range, inv);
+                o.w = norm_div(ld(sp + src[3]) - smin, range, inv);
                 __stcs(reinterpret_cast<float4 *>(tbase + (long long)r * P.w_pix + c), o);
             }
         }
@@ -454,9 +490,120 @@ tile_kernel(KParams P, const FileDesc *__restrict__ files, int n_files, const fl
         for (int c = threadIdx.x; c < P.w_pix; c += blockDim.x) {
             const int src = reflect_src(c, width, period);
             for (int r = r0; r < r1; ++r)
-                tbase[(long long)r * P.w_pix + c] = norm_div(sbase[(long long)r * fd.row_stride + src] - smin, range, inv);
+                tbase[(long long)r * P.w_pix + c] = norm_div(ld(sbase + (long long)r * fd.row_stride + src) - smin, range, inv);
         }
     }
+}
+
+__device__ __forceinline__ int file_of_tile(const FileDesc *__restrict__ files, int n_files, long long tile) {
+    int lo_f = 0, hi_f = n_files - 1;
+    while (lo_f < hi_f) {
+        int mid = (lo_f + hi_f + 1) >> 1;
+        if (files[mid].tile0 <= tile) lo_f = mid; else hi_f = mid - 1;
+    }
+    return lo_f;
+}
+
+template <bool VEC4>
+__global__ void __launch_bounds__(256)
+tile_kernel(KParams P, const FileDesc *__restrict__ files, int n_files, const float *__restrict__ spec,
+            const float *__restrict__ minmax, float *__restrict__ tiles, long long tile_begin) {
+    const long long tile = blockIdx.x + tile_begin;
+    const int f = file_of_tile(files, n_files, tile);
+    tile_block<VEC4, false>(P, files[f], tile, blockIdx.y, minmax[2 * f], minmax[2 * f + 1], spec, tiles);
+}
+
+// Tiling that FOLLOWS the transform inside one launch window (tensor-core path): blocks run in file order, two per SM
+// beside the 96-register slide kernel.  The first block of a file waits until the slide kernel has published all of the
+// file's units (file_done), computes the file's exact min / max (refine_file) and raises mm_ready; the file's other
+// blocks wait for that flag.  The dB band is then read while it is still in L2, one file behind the transform, so the
+// pass costs HBM only its tile writes.  Waits are bounded: a lost flag traps instead of hanging the device.
+__device__ __forceinline__ void wait_flag_ge(const unsigned int *flag, unsigned int target) {
+    if (threadIdx.x == 0) {
+        unsigned int v;
+        long long spins = 0;
+        while (true) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            if (v >= target) break;
+            __nanosleep(1000);
+            if (++spins > 20000000ll) __trap();
+        }
+    }
+    __syncthreads();
+}
+
+#ifdef NBM_WS_TIMING
+__device__ unsigned long long follow_dbg[8];   // [0] first block start, [1] file 0 ready, [2] middle file ready, [3] last block end
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ unsigned long long follow_files[2][2048];   // per file: min/max block scheduled | file complete (seen by it)
+extern "C" int nbm_debug_follow_timing(unsigned long long *out) {
+    return cudaMemcpyFromSymbol(out, follow_dbg, sizeof(follow_dbg)) == cudaSuccess ? 0 : -1;
+}
+extern "C" int nbm_debug_follow_files(unsigned long long *out) {
+    return cudaMemcpyFromSymbol(out, follow_files, sizeof(follow_files)) == cudaSuccess ? 0 : -1;
+}
+#endif
+
+template <bool VEC4>
+__global__ void __launch_bounds__(256, 8)
+tile_follow_kernel(KParams P, RefineParams R, const SegDesc *__restrict__ segs, const FileDesc *__restrict__ files, int n_files,
+                   const float2 *__restrict__ tile_mm, float *__restrict__ spec, const void *__restrict__ pcm,
+                   float *__restrict__ minmax, float *__restrict__ tiles, const unsigned int *__restrict__ file_done,
+                   unsigned int *__restrict__ mm_ready, int row_blocks, int ahead) {
+    // Block order (file-major): `lead` min/max blocks for files 0 .. lead-1, then per file f the min/max block of file
+    // f + lead followed by f's tiling blocks.  A file's min/max (tens of microseconds of float64 refinement) is thus
+    // under way `lead` files before its tiling blocks reach the SMs instead of in front of them -- only about one
+    // file's blocks are resident at a time, so a min/max placed directly before its tiles serialises per file.
+    const int lead = min(ahead, n_files);
+    const int b = blockIdx.x;
+    int refine_f = -1, f = 0, rb = 0;
+    long long tile = 0;
+    if (b < lead) {
+        refine_f = b;
+    } else {
+        auto group_start = [&](int g) { return (long long)lead + (long long)row_blocks * files[g].tile0 + min(g, n_files - lead); };
+        int lo_f = 0, hi_f = n_files - 1;
+        while (lo_f < hi_f) {
+            const int mid = (lo_f + hi_f + 1) >> 1;
+            if (group_start(mid) <= b) lo_f = mid; else hi_f = mid - 1;
+        }
+        f = lo_f;
+        int r = (int)(b - group_start(f));
+        const int has_ref = (f + lead < n_files) ? 1 : 0;
+        if (has_ref && r == 0) {
+            refine_f = f + lead;
+        } else {
+            r -= has_ref;
+            tile = files[f].tile0 + r / row_blocks;
+            rb = r % row_blocks;
+        }
+    }
+#ifdef NBM_WS_TIMING
+    if (b == 0 && threadIdx.x == 0) follow_dbg[0] = gtime();
+#endif
+    if (refine_f >= 0) {
+#ifdef NBM_WS_TIMING
+        if (threadIdx.x == 0 && refine_f < 2048) follow_files[0][refine_f] = gtime();
+#endif
+        wait_flag_ge(file_done + refine_f, files[refine_f].done_target);
+#ifdef NBM_WS_TIMING
+        if (threadIdx.x == 0 && refine_f < 2048) follow_files[1][refine_f] = gtime();
+        if (threadIdx.x == 0 && (refine_f == 0 || refine_f == n_files / 2)) follow_dbg[refine_f == 0 ? 1 : 2] = gtime();
+#endif
+        refine_file(R, segs, files, tile_mm, spec, pcm, NBM_PCM_INT16, 1, minmax, refine_f);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(mm_ready + refine_f), "r"(1u) : "memory");
+        }
+        return;
+    }
+    wait_flag_ge(mm_ready + f, 1u);
+    const float smin = __ldcg(minmax + 2 * f), smax = __ldcg(minmax + 2 * f + 1);
+    tile_block<VEC4, true>(P, files[f], tile, rb, smin, smax, spec, tiles);
+#ifdef NBM_WS_TIMING
+    if (b == gridDim.x - 1 && threadIdx.x == 0) follow_dbg[3] = gtime();
+#endif
 }
 
 }  // namespace nbm
@@ -490,6 +637,9 @@ struct nbm_frontend_plan {
     cudaStream_t s_hi = nullptr;
     cudaEvent_t ev_in = nullptr, ev_sub[MAX_SUB] = {};
     bool overlap = false;
+    int fused_ahead = 4;        // files by which a file's min/max block runs ahead of its tiling blocks (fused tiling)
+    bool fused = false;         // NBM_FRONTEND_FUSED=1: tiling follows the transform file by file inside one launch window
+    CUresult (*wait_value32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
     int sub_groups = 8192;      // least 64-frame groups per sub-batch
 };
 
@@ -506,7 +656,7 @@ struct BatchLayout {
     size_t spec_floats = 0;
     long long tiles = 0, n_anchors = 0;
     int groups = 0;
-    size_t o_segs = 0, o_files = 0, o_mm = 0, o_anchors = 0, o_spec = 0, total = 0;
+    size_t o_segs = 0, o_files = 0, o_flags = 0, o_mm = 0, o_anchors = 0, o_spec = 0, total = 0;
     size_t upload_bytes = 0;       // segs and files are uploaded from the host
 };
 
@@ -564,6 +714,7 @@ int build_layout(const nbm_frontend_plan *pl, const int64_t *sizes, const int64_
             last_width = (int)(edge + B.segs[i].n_frames - start);
         }
         fd.n_groups = B.groups - fd.group0;
+        fd.done_target = pl->tc ? (unsigned int)(fd.n_groups * 2 * tc_units_per_chain(pl->tc)) : 0u;
         fd.n_segs = (int)B.segs.size() - fd.seg0;
         fd.row_stride = (int)stride;
         fd.n_tiles = (int)nt;
@@ -578,10 +729,11 @@ int build_layout(const nbm_frontend_plan *pl, const int64_t *sizes, const int64_
     B.o_segs = take(B.segs.size() * sizeof(SegDesc));
     B.o_files = take(B.files.size() * sizeof(FileDesc));
     B.upload_bytes = o;
+    B.o_flags = take(((size_t)n_files * 2 + 1) * sizeof(unsigned int));  // file_done | mm_ready | slide CTAs started (fused tiling)
     B.o_mm = take((size_t)B.groups * (pl->tc ? (GF / tc_chain_frames()) * tc_n_ranges(pl->tc) * tc_slots_per_range() : 1) *
                   sizeof(float2));                                  // min/max partials
     B.o_anchors = take(pl->tc ? tc_anchor_bytes(pl->tc, B.n_anchors) : 0);
-    B.o_spec = take(B.spec_floats * sizeof(float));
+    B.o_spec = take(B.spec_floats * sizeof(float) + 16);         // + one vector: the fused tiling pass reads aligned 16-byte pairs
     B.total = o;
     return NBM_OK;
 }
@@ -651,6 +803,24 @@ extern "C" int nbm_frontend_plan_create(const nbm_frontend_params *p, nbm_fronte
         pl->overlap = ov && strcmp(ov, "1") == 0;
         const char *sg = getenv("NBM_FRONTEND_SUB_GROUPS");
         pl->sub_groups = sg ? std::max(1, atoi(sg)) : 8192;
+        const char *fu = getenv("NBM_FRONTEND_FUSED");
+        pl->fused = fu && strcmp(fu, "1") == 0;
+        const char *fa = getenv("NBM_FRONTEND_FUSED_AHEAD");
+        if (fa) pl->fused_ahead = std::max(1, atoi(fa));
+        if (pl->fused) {
+            void *fn = nullptr;
+            cudaDriverEntryPointQueryResult qr;
+            if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn ||
+                qr != cudaDriverEntryPointSuccess) {
+                cudaGetLastError();
+                pl->fused = false;          // no stream memory operations on this driver: keep the plain launch sequence
+            }
+            pl->wait_value32 = reinterpret_cast<CUresult (*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int)>(fn);
+        }
+        if (pl->fused) {
+            cudaFuncSetAttribute(tile_follow_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(tile_follow_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        }
         if (pl->overlap) {
             // to share an SM with the persistent slide kernel (maximum shared-memory carve-out) the tiling kernel
             // has to ask for the same L1 / shared memory split
@@ -841,6 +1011,45 @@ extern "C" int nbm_frontend_run_batch(const nbm_frontend_plan *cpl, const void *
     NBM_CUDA(cudaEventRecord(pl->ev_in, stream));              // inputs and descriptors are ready on the caller's stream
     NBM_CUDA(cudaStreamWaitEvent(pl->s_hi, pl->ev_in, 0));
     cudaStream_t sc = pl->s_hi;
+    if (use_tc && pl->fused) {
+        // anchors -> slide kernel (96 registers, publishes per-file completion) on the priority stream; the tiling
+        // kernel starts on the caller's stream as soon as the anchors are done and follows the transform file by file
+        unsigned int *d_flags = reinterpret_cast<unsigned int *>(ws + B.o_flags);
+        NBM_CUDA(cudaMemsetAsync(d_flags, 0, ((size_t)n_files * 2 + 1) * sizeof(unsigned int), sc));
+        if (prof) NBM_CUDA(cudaEventRecord(pl->ev[0][0], sc));
+        rc = tc_launch_anchors(pl->tc, d_segs, 0, (int)B.segs.size(), 0, B.n_anchors, d_pcm, ws + B.o_anchors, sc);
+        if (rc != NBM_OK) return rc;
+        if (prof) NBM_CUDA(cudaEventRecord(pl->ev[0][1], sc));
+        NBM_CUDA(cudaEventRecord(pl->ev_sub[1], sc));
+        NBM_CUDA(cudaStreamWaitEvent(stream, pl->ev_sub[1], 0));
+        int slide_grid = 0;
+        rc = tc_launch_slides(pl->tc, d_segs, (int)B.segs.size(), 0, 0, B.groups, d_pcm, d_spec, d_tile_mm, ws + B.o_anchors,
+                              d_flags, d_flags + 2 * n_files, &slide_grid, sc);
+        if (rc != NBM_OK) return rc;
+        // the caller's stream waits (in hardware) until every slide CTA is resident; only then may tiling blocks be
+        // placed -- they fill what is left of each SM (two per SM) instead of taking the SMs first
+        {
+            const CUresult cr = pl->wait_value32((CUstream)stream, (CUdeviceptr)(uintptr_t)(d_flags + 2 * n_files),
+                                                 (cuuint32_t)slide_grid, CU_STREAM_WAIT_VALUE_GEQ);
+            if (cr != CUDA_SUCCESS) { set_error("cuStreamWaitValue32 failed (%d)", (int)cr); return NBM_ERR_CUDA; }
+        }
+        // profile: anchors | slide kernel | 0 | what is left of the tiling pass after the slide kernel has ended
+        if (prof) { NBM_CUDA(cudaEventRecord(pl->ev[0][2], sc)); NBM_CUDA(cudaEventRecord(pl->ev[0][3], sc)); }
+        const int row_blocks = (p.n_bins + TILE_ROWS - 1) / TILE_ROWS;
+        const unsigned int blocks = (unsigned int)(B.tiles * row_blocks + n_files);
+        const int ahead = pl->fused_ahead;
+        if (p.w_pix % 4 == 0)
+            tile_follow_kernel<true><<<blocks, 256, 0, stream>>>(pl->kp, rp, d_segs, d_files, n_files, d_tile_mm, d_spec, d_pcm,
+                                                                 d_minmax, d_tiles, d_flags, d_flags + n_files, row_blocks, ahead);
+        else
+            tile_follow_kernel<false><<<blocks, 256, 0, stream>>>(pl->kp, rp, d_segs, d_files, n_files, d_tile_mm, d_spec, d_pcm,
+                                                                  d_minmax, d_tiles, d_flags, d_flags + n_files, row_blocks, ahead);
+        if (prof) { NBM_CUDA(cudaEventRecord(pl->ev[0][4], stream)); pl->ev_subs = 1; pl->ev_pending = true; }
+        NBM_CUDA(cudaEventRecord(pl->ev_sub[0], sc));
+        NBM_CUDA(cudaStreamWaitEvent(stream, pl->ev_sub[0], 0));
+        NBM_CUDA(cudaGetLastError());
+        return NBM_OK;
+    }
     int sub = 0;
     for (int g = 0; g < n_sub; ++g) {
         const int f0 = cut[g], f1 = cut[g + 1];
@@ -857,7 +1066,7 @@ extern "C" int nbm_frontend_run_batch(const nbm_frontend_plan *cpl, const void *
             if (rc != NBM_OK) return rc;
             if (prof) NBM_CUDA(cudaEventRecord(pl->ev[sub][1], sc));
             rc = tc_launch_slides(pl->tc, d_segs, (int)B.segs.size(), seg0, grp0, grp1, d_pcm, d_spec, d_tile_mm,
-                                  ws + B.o_anchors, sc);
+                                  ws + B.o_anchors, nullptr, nullptr, nullptr, sc);
             if (rc != NBM_OK) return rc;
         } else {
             if (prof) NBM_CUDA(cudaEventRecord(pl->ev[sub][1], sc));

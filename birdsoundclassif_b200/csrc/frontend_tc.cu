@@ -448,8 +448,12 @@ constexpr int NK_T = 5;                     // k-steps whose twiddles fit in TME
                                             // read from shared memory, at 4 KB per MMA)
 constexpr int TM_COLS = 512;
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+// group-local barrier of 128 threads.  The id must be a literal: with a register id the compiler reserves all 16
+// hardware barriers for the CTA, and a kernel that needs a barrier of its own can then no longer share the SM.
+__device__ __forceinline__ void named_bar_sync(int id, int /*nthreads = 128*/) {
+    if (id == 1) asm volatile("bar.sync 1, 128;" ::: "memory");
+    else if (id == 2) asm volatile("bar.sync 2, 128;" ::: "memory");
+    else asm volatile("bar.sync 3, 128;" ::: "memory");
 }
 
 // Chain -> segment bookkeeping kept in registers; the descriptor is re-read only when the segment changes.
@@ -492,10 +496,13 @@ constexpr int WS_G = 3;
 constexpr int WS_THREADS = 32 * (4 * WS_G + 1 + WS_G);
 constexpr int PV = 11;                      // 16-byte PCM vectors per fill lane per round (two rounds per chain)
 
-__global__ void __launch_bounds__(WS_THREADS, 1)
-slide_ws_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int seg_begin, int chain_begin, int total_chains,
-                const short *__restrict__ pcm, const float2 *__restrict__ anchors,
-                float *__restrict__ spec, float2 *__restrict__ chain_mm) {
+// file_done (optional): per-file count of finished (chain, range, emit warp) units, published with release semantics
+// when a warp moves on to another file -- the tiling kernel that follows the transform file by file waits on it.
+template <int PS>                           // shifted-path vectors per fill lane per round (register budget)
+__device__ __forceinline__ void
+slide_ws_body(const TcParams &P, const SegDesc *__restrict__ segs, int n_segs, int seg_begin, int chain_begin, int total_chains,
+              const short *__restrict__ pcm, const float2 *__restrict__ anchors,
+              float *__restrict__ spec, float2 *__restrict__ chain_mm, unsigned int *__restrict__ file_done) {
     constexpr int G = WS_G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t acc_full[G], b_ready[G], s_full[G], s_free[G];
@@ -703,7 +710,6 @@ slide_ws_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int se
                 }
             } else if (fast) {
                 // the file does not start on a 16-byte boundary of the batch buffer: aligned loads, re-aligned in registers
-                constexpr int PS = 4;
                 for (int vb = 0; vb < nv; vb += 32 * PS) {
                     int4 pa[PS], pb[PS];
                     const int4 *src = reinterpret_cast<const int4 *>(pcm + g0 - sh) + vb + lane;
@@ -834,10 +840,20 @@ slide_ws_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int se
         anc_next = anchor_of(first);
         build(0);
     }
+    int pub_file = -1;                      // units finished for this file and not yet published
+    unsigned int pub_cnt = 0;
+    auto publish = [&]() {
+        if (file_done != nullptr && pub_file >= 0 && pub_cnt > 0) {
+            __syncwarp();
+            if (lane == 0) { __threadfence(); atomicAdd(file_done + pub_file, pub_cnt); }
+        }
+        pub_cnt = 0;
+    };
     WS_T0();
     for (int it = 0; it < n_iters; ++it) {
         const int chain = first + it * cstride;
         cw.seek(chain);
+        if (cw.sd.file != pub_file) { publish(); pub_file = cw.sd.file; }
         const int lc = chain - 2 * cw.sd.group0;
         const int t0 = lc * CF;
         const bool fwd = (lc & 1) == 0;
@@ -942,16 +958,45 @@ slide_ws_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int se
                 vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
             }
             if (lane == 0) chain_mm[((size_t)chain * P.n_ranges + range) * 4 + wq] = make_float2(vmin, vmax);
+            ++pub_cnt;
         }
         WS_MARK(5);
         named_bar_sync(bar_id, 128);        // stage free for the next recurrence
         WS_MARK(6);
     }
+    publish();
     WS_FLUSH(0);
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, TM_COLS);
+}
+
+__global__ void __launch_bounds__(WS_THREADS, 1)
+slide_ws_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int seg_begin, int chain_begin, int total_chains,
+                const short *__restrict__ pcm, const float2 *__restrict__ anchors,
+                float *__restrict__ spec, float2 *__restrict__ chain_mm) {
+    slide_ws_body<4>(P, segs, n_segs, seg_begin, chain_begin, total_chains, pcm, anchors, spec, chain_mm, nullptr);
+}
+
+#ifdef NBM_WS_TIMING
+#define WS_STAMP(i) if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); ws_dbg[i] = t; }
+#else
+#define WS_STAMP(i)
+#endif
+
+// The same kernel held to 96 registers, so that two CTAs of the tiling kernel fit on the SM beside it.
+__global__ void __maxnreg__(96)
+slide_ws_kernel_shared_sm(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int seg_begin, int chain_begin, int total_chains,
+                          const short *__restrict__ pcm, const float2 *__restrict__ anchors,
+                          float *__restrict__ spec, float2 *__restrict__ chain_mm, unsigned int *__restrict__ file_done,
+                          unsigned int *__restrict__ started) {
+    // the tiling kernel is released (stream wait on this counter) only once every CTA of this grid is resident:
+    // if its blocks took the SMs first, they would wait forever for files these CTAs could then never produce
+    if (threadIdx.x == 0) atomicAdd(started, 1u);
+    WS_STAMP(24);
+    slide_ws_body<1>(P, segs, n_segs, seg_begin, chain_begin, total_chains, pcm, anchors, spec, chain_mm, file_done);
+    WS_STAMP(25);
 }
 
 }  // namespace nbm
@@ -1059,6 +1104,13 @@ int nbm::tc_plan_create(const nbm_frontend_params &p, TcPlan **out) {
     // per-function attribute (not per plan): allow the device maximum minus the kernel's static shared memory
     if (e == cudaSuccess) e = cudaFuncSetAttribute(slide_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    max_smem - (int)fa_s.sharedSizeBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(slide_ws_kernel_shared_sm, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   max_smem - (int)fa_s.sharedSizeBytes);
+    // Without this the driver runs the CTA under the smallest shared-memory split that holds it (196 KB), the CTA fills
+    // that split, and no block of another kernel can join it on the SM however small it is (measured with a probe and
+    // in the pipeline: the tiling kernel ran on the one SM this grid leaves free).  Under the 228 KB split ~30 KB stay free.
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(slide_ws_kernel_shared_sm, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                   cudaSharedmemCarveoutMaxShared);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(anchor_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    max_smem - (int)fa_a.sharedSizeBytes);
     if (e != cudaSuccess) { tc_plan_destroy(pl); return cuda_fail(e, "tc_plan_create"); }
@@ -1088,6 +1140,7 @@ extern "C" int nbm_debug_ws_timing(unsigned long long *out, int reset) {
 int nbm::tc_n_ranges(const TcPlan *pl) { return pl->p.n_ranges; }
 int nbm::tc_bins_per_range() { return BINS_PER_RANGE; }
 int nbm::tc_chain_frames() { return CF; }
+int nbm::tc_units_per_chain(const TcPlan *pl) { return pl->p.n_ranges * 4; }
 int nbm::tc_slots_per_range() { return 4; }
 int nbm::tc_bins_per_slot() { return ROWS_PER_EWARP; }
 
@@ -1104,13 +1157,20 @@ int nbm::tc_launch_anchors(const TcPlan *pl, const SegDesc *d_segs, int seg_lo, 
 }
 
 int nbm::tc_launch_slides(const TcPlan *pl, const SegDesc *d_segs, int n_segs, int seg_begin, int group_begin, int group_end,
-                          const void *d_pcm, float *d_spec, float2 *d_tile_mm, const void *d_anchors, cudaStream_t stream) {
+                          const void *d_pcm, float *d_spec, float2 *d_tile_mm, const void *d_anchors,
+                          unsigned int *d_file_done, unsigned int *d_started, int *grid_out, cudaStream_t stream) {
     const TcParams &k = pl->p;
     const int chain_begin = 2 * group_begin, chain_end = 2 * group_end;
     const int grid = std::min(pl->grid_slide, std::max(1, chain_end - chain_begin) * k.n_ranges);
-    slide_ws_kernel<<<(grid / k.n_ranges) * k.n_ranges, WS_THREADS, pl->smem_slide, stream>>>(
-        k, d_segs, n_segs, seg_begin, chain_begin, chain_end, reinterpret_cast<const short *>(d_pcm),
-        reinterpret_cast<const float2 *>(d_anchors), d_spec, d_tile_mm);
+    if (grid_out) *grid_out = (grid / k.n_ranges) * k.n_ranges;
+    if (d_file_done)
+        slide_ws_kernel_shared_sm<<<(grid / k.n_ranges) * k.n_ranges, WS_THREADS, pl->smem_slide, stream>>>(
+            k, d_segs, n_segs, seg_begin, chain_begin, chain_end, reinterpret_cast<const short *>(d_pcm),
+            reinterpret_cast<const float2 *>(d_anchors), d_spec, d_tile_mm, d_file_done, d_started);
+    else
+        slide_ws_kernel<<<(grid / k.n_ranges) * k.n_ranges, WS_THREADS, pl->smem_slide, stream>>>(
+            k, d_segs, n_segs, seg_begin, chain_begin, chain_end, reinterpret_cast<const short *>(d_pcm),
+            reinterpret_cast<const float2 *>(d_anchors), d_spec, d_tile_mm);
     NBM_CUDA(cudaGetLastError());
     return NBM_OK;
 }

@@ -35,7 +35,13 @@ int tc_launch_anchors(const TcPlan *pl, const SegDesc *d_segs, int seg_lo, int s
                       long long anchor_end, const void *d_pcm, void *d_anchors, cudaStream_t stream);
 // slides: tcgen05 GEMM over hop/2 pairs + recurrence + Hann + dB for every frame, per-(chain, range, slot) min/max
 // for the 64-frame groups [group_begin, group_end), which start in segment seg_begin
+// d_file_done (optional, zeroed by the caller): per-file count of finished (chain, range, emit warp) units, published
+// with release semantics; a file is complete at 2 * groups(file) * tc_units_per_chain().  Given it, the 96-register
+// build of the kernel runs, which leaves room on the SM for two CTAs of the tiling kernel that follows it; every
+// CTA bumps *d_started on entry and *grid_out is the number of CTAs launched (the follower waits for all of them).
 int tc_launch_slides(const TcPlan *pl, const SegDesc *d_segs, int n_segs, int seg_begin, int group_begin, int group_end,
-                     const void *d_pcm, float *d_spec, float2 *d_tile_mm, const void *d_anchors, cudaStream_t stream);
+                     const void *d_pcm, float *d_spec, float2 *d_tile_mm, const void *d_anchors,
+                     unsigned int *d_file_done, unsigned int *d_started, int *grid_out, cudaStream_t stream);
+int tc_units_per_chain(const TcPlan *pl);
 
 }  // namespace nbm

@@ -255,3 +255,20 @@ def test_tiny_files(fe, n):
     ref = np.stack(r.tiles)
     if np.isfinite(ref).all():
         assert_tiles_close(tiles.cpu().numpy(), ref, f"n={n}")
+
+
+def test_fused_tiling_follows_transform_equals_plain(fe, monkeypatch):
+    """NBM_FRONTEND_FUSED=1: the tiling kernel runs beside the slide kernel and follows it file by file through
+    release/acquire flags (min/max refinement inside): same bits as the plain launch sequence."""
+    pcms = [synth.synth_pcm(s, 85 + i) for i, s in enumerate([3.0, 2.3, 0.4, 4.1, 3.0, 1.5, 2.2, 6.0])]
+    flat = torch.from_numpy(np.concatenate(pcms)).cuda()
+    offs = np.concatenate([[0], np.cumsum([len(p) for p in pcms])]).tolist()
+    plain = fe.FrontendPlan(stft_chunk=100_100)
+    ref_tiles, ref_off, ref_mm = plain.run_batch(flat, offs)
+    monkeypatch.setenv("NBM_FRONTEND_FUSED", "1")
+    fused = fe.FrontendPlan(stft_chunk=100_100)
+    for _ in range(3):
+        tiles, off, mm = fused.run_batch(flat, offs)
+        torch.cuda.synchronize()
+        assert off == ref_off and torch.equal(mm, ref_mm) and torch.equal(tiles, ref_tiles)
+    plain.close(); fused.close()
