@@ -21,29 +21,44 @@ from . import sharding
 
 
 def detect_directory(model, model_args, audio_dir, bird_dict="bird_dict.json", min_score=0.2, bs=4,
-                     rank=0, world=1, skip_done=False, verbose=True) -> dict:
+                     rank=0, world=1, skip_done=False, verbose=True, pipelined=True, group_tiles=1024) -> dict:
+    """This rank's share of ``audio_dir/*.wav`` -> sibling ``.txt`` files (nbm_detect.py:23-29).  ``pipelined``: wav
+    decoding, the batched front-end and the detector overlap across files (pipeline.DetectionPipeline); otherwise the
+    reference's one-file-at-a-time loop through ``run_detection``.  Same outputs either way."""
     files = sharding.shard_files(glob.glob(os.path.join(audio_dir, "*.wav")), rank, world)
+    if skip_done:
+        files = [f for f in files if not os.path.exists(f.replace(".wav", ".txt"))]
     counts = dict.fromkeys(sharding.COUNT_FIELDS, 0)
     t_wall = time.perf_counter()
-    for wav_path in files:
-        out_path = wav_path.replace(".wav", ".txt")
-        if skip_done and os.path.exists(out_path):
-            continue
-        tm = {}
-        try:
-            output = rd.run_detection(model, model_args, wav_path, bird_dicts_path=bird_dict, min_score=min_score,
-                                      bs=bs, timings=tm)
-        except Exception as e:          # per-file failure isolation (the reference crashes)
-            print(f"[rank {rank}] {wav_path}: FAILED: {e}")
-            continue
-        with open(out_path, "w") as f:
+
+    def done(wav_path, output):
+        with open(wav_path.replace(".wav", ".txt"), "w") as f:
             f.write(str(output))
-        counts["files"] += 1
-        counts["tiles"] += tm["tiles"]; counts["frames"] += tm["frames"]; counts["detections"] += tm["detections"]
-        counts["t_front_us"] += int(tm["frontend_s"] * 1e6); counts["t_model_us"] += int(tm["model_s"] * 1e6)
-        counts["t_post_us"] += int(tm["post_s"] * 1e6)
         if verbose:
             print(f"~~~~~ File {os.path.basename(wav_path).replace('.wav', '')} done ~~~~~")
+
+    if pipelined:
+        from .pipeline import DetectionPipeline
+        pipe = DetectionPipeline(model, model_args, bird_dict, min_score=min_score, bs=bs, max_group_tiles=group_tiles)
+        for wav_path, output in pipe.run(files):
+            done(wav_path, output)
+        for wav_path, why in pipe.failed:       # per-file failure isolation (the reference crashes, SURVEY 5)
+            print(f"[rank {rank}] {wav_path}: FAILED: {why}")
+        counts.update(pipe.counts)
+    else:
+        for wav_path in files:
+            tm = {}
+            try:
+                output = rd.run_detection(model, model_args, wav_path, bird_dicts_path=bird_dict, min_score=min_score,
+                                          bs=bs, timings=tm)
+            except Exception as e:
+                print(f"[rank {rank}] {wav_path}: FAILED: {e}")
+                continue
+            done(wav_path, output)
+            counts["files"] += 1
+            counts["tiles"] += tm["tiles"]; counts["frames"] += tm["frames"]; counts["detections"] += tm["detections"]
+            counts["t_front_us"] += int(tm["frontend_s"] * 1e6); counts["t_model_us"] += int(tm["model_s"] * 1e6)
+            counts["t_post_us"] += int(tm["post_s"] * 1e6)
     torch.cuda.synchronize()
     counts["t_wall_us"] = int((time.perf_counter() - t_wall) * 1e6)
     return counts
@@ -57,6 +72,8 @@ def main(argv=None):
     parser.add_argument("--batch", dest="bs", type=int, default=4)
     parser.add_argument("--bird_dict", type=str, default="bird_dict.json")
     parser.add_argument("--skip_done", action="store_true", help="skip wavs that already have a .txt")
+    parser.add_argument("--no_pipeline", action="store_true", help="one file at a time, as the reference loops")
+    parser.add_argument("--group_tiles", type=int, default=1024, help="detector tiles per front-end batch (pipelined)")
     args = parser.parse_args(argv)
     assert os.path.isfile(args.bird_dict), "Missing dictionary of bird species names --> bird_dict.json."
 
@@ -74,7 +91,7 @@ def main(argv=None):
     rd.patch_reference()
     rd.accelerate_model(model)
     counts = detect_directory(model, model_args, args.audio_dirp, args.bird_dict, args.min_score, args.bs,
-                              rank, world, args.skip_done)
+                              rank, world, args.skip_done, pipelined=not args.no_pipeline, group_tiles=args.group_tiles)
     per_rank = sharding.gather_counts(counts, device=torch.device("cuda", local))
     if rank == 0:
         print(json.dumps({"per_rank": per_rank, "totals": sharding.totals(per_rank)}))

@@ -1,0 +1,251 @@
+"""Pipelined multi-file host driver around the reference's per-file loop.
+
+The reference handles a directory one file at a time (nbm_detect.py:23-29 -> run_detection.py:40-67):
+decode the wav, transform it, run the detector batch by batch, merge, write -- every stage waiting
+for the one before.  Here the same per-file results come out of three overlapped stages:
+
+  reader threads   wav -> int16 straight into a slice of a PINNED group buffer (no float conversion,
+                   no per-file allocation); groups of whole files, sized by detector tiles
+  front-end stream one H2D copy + ONE batched front-end call per group (nbm_frontend_run_batch: the
+                   kernels are sized for thousands of tiles, a single 30 s file leaves them
+                   launch-bound), into one of two device tile buffers
+  caller's stream  the detector over the previous group's tiles in the reference's batching (bs, order,
+                   partial last batch PER FILE: nms / ProposalLayer are batch-coupled),
+                   the per-file merge, the output dictionary
+
+Group g+1 is read and transformed while group g is in the detector; events hand the tile buffers back
+and forth.  A file is never split across groups (its normalisation is file-global), so every tile, and
+therefore every box, equals what ``run_detection.run_detection`` returns for that file alone (tested).
+
+Not done here: a CUDA graph of the detector forward.  The reference network's forward reads sizes back to
+the host (proposal counts, ``.item()`` / ``.tolist()`` in its second stage), so its launch sequence is
+data-dependent and cannot be captured unmodified; the north star keeps that network as it is.
+"""
+from __future__ import annotations
+
+import json
+import queue
+import threading
+import time
+import wave
+from concurrent.futures import ThreadPoolExecutor
+from dataclasses import dataclass, field
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from . import postproc
+from .frontend import LONG_FILE_SAMPLES, STFT_CHUNK, derive_constants, get_plan
+from .run_detection import detect_tiles
+
+
+# ------------------------------------------------------------------ pure host arithmetic ------
+def count_frames_tiles(n_samples: int, hop_length: int, w_pix: int, hop_spectro: int, stft_chunk: int = STFT_CHUNK):
+    """(frames, tiles) of a file: prepare_dataset.py:234-237 (one STFT per <= stft_chunk samples, each
+    1 + len // hop frames, `range(int(len / max_l) + 1)` chunks) and :255-266 (tiles)."""
+    frames = 0
+    for c in range(n_samples // stft_chunk + 1):
+        length = max(0, min(n_samples, (c + 1) * stft_chunk) - c * stft_chunk)
+        frames += 1 + length // hop_length
+    tiles = 1 if frames <= w_pix else 1 + -(-(frames - w_pix) // hop_spectro)
+    return frames, tiles
+
+
+@dataclass
+class WavInfo:
+    path: str
+    n_samples: int = 0          # per channel
+    channels: int = 1
+    sample_rate: int = 0
+    error: str | None = None
+
+
+def probe_wav(path: str) -> WavInfo:
+    """Header only (no sample data is read)."""
+    try:
+        with wave.open(path, "rb") as w:
+            if w.getsampwidth() != 2 or w.getcomptype() != "NONE":
+                return WavInfo(path, error="only uncompressed PCM16 wav is supported")
+            return WavInfo(path, w.getnframes(), w.getnchannels(), w.getframerate())
+    except Exception as e:          # the reference prints 'File loading failed' and returns None (prepare_dataset.py:163-165)
+        return WavInfo(path, error=f"File loading failed ({e})")
+
+
+@dataclass
+class Group:
+    files: list = field(default_factory=list)      # WavInfo
+    tiles: list = field(default_factory=list)      # tiles per file
+    frames: list = field(default_factory=list)
+    channels: int = 1
+
+    @property
+    def n_tiles(self):
+        return sum(self.tiles)
+
+    @property
+    def n_values(self):                             # int16 values in the group buffer
+        return sum(f.n_samples * f.channels for f in self.files)
+
+
+def plan_groups(infos, const, max_group_tiles: int, stft_chunk: int = STFT_CHUNK):
+    """Contiguous groups of whole files in the given order, at most `max_group_tiles` detector tiles
+    each (a single larger file forms its own group) and one channel count per group.
+    Returns (groups, rejected) -- rejected = [(WavInfo, reason)] for unreadable / unsupported files."""
+    groups, rejected = [], []
+    cur = None
+    for info in infos:
+        if info.error:
+            rejected.append((info, info.error)); continue
+        if info.sample_rate != 44100:
+            rejected.append((info, f"sample rate {info.sample_rate} != 44100; resample first (no ffmpeg path)")); continue
+        if info.n_samples > LONG_FILE_SAMPLES:
+            rejected.append((info, f"{info.n_samples} samples > {LONG_FILE_SAMPLES}; split the recording first")); continue
+        fr, nt = count_frames_tiles(info.n_samples, const["HOP_LENGTH"], const["W_PIX"], const["HOP_SPECTRO"], stft_chunk)
+        if cur is None or cur.channels != info.channels or (cur.files and cur.n_tiles + nt > max_group_tiles):
+            cur = Group(channels=info.channels)
+            groups.append(cur)
+        cur.files.append(info); cur.tiles.append(nt); cur.frames.append(fr)
+    return groups, rejected
+
+
+def read_into(info: WavInfo, dst: np.ndarray) -> None:
+    """Decode one wav's int16 samples (interleaved if multi-channel) into `dst` (a slice of the pinned buffer)."""
+    with wave.open(info.path, "rb") as w:
+        raw = w.readframes(info.n_samples)
+    a = np.frombuffer(raw, dtype="<i2")
+    if a.size != dst.size:
+        raise IOError(f"{info.path}: header promised {dst.size} values, file holds {a.size}")
+    dst[:] = a
+
+
+# ------------------------------------------------------------------------- the pipeline -------
+class DetectionPipeline:
+    """``run(paths)`` yields ``(path, output_dict)`` in input order, the dictionaries equal to
+    ``run_detection.run_detection(model, config, path, ...)``."""
+
+    def __init__(self, model, config, bird_dicts_path, min_score=0.5, bs=10, max_group_tiles=1024, readers=4,
+                 freq_accuracy=33.3, dt=0.003, overlap_spectro=0.2, w_pix=1024):
+        if not torch.cuda.is_available():
+            raise RuntimeError("the detection pipeline needs a CUDA device (no CPU fallback)")
+        self.model, self.config, self.min_score, self.bs = model, config, min_score, bs
+        self.max_group_tiles, self.readers = int(max_group_tiles), int(readers)
+        self.fe_args = (freq_accuracy, dt, overlap_spectro, w_pix)
+        self.const = derive_constants(*self.fe_args)
+        with open(bird_dicts_path, "r") as f:
+            birds = json.load(f)
+        birds.update({"Non bird sound": 0})                       # run_detection.py:71
+        self.reverse_dict = {idx: name for name, idx in birds.items()}
+        self.counts = dict(files=0, tiles=0, detections=0, frames=0, t_front_us=0, t_model_us=0, t_post_us=0)
+        self.failed: list = []
+
+    # reader side: fills pinned buffers, two groups ahead at most
+    def _reader(self, groups, out_q: queue.Queue, free_q: queue.Queue, pool: ThreadPoolExecutor):
+        try:
+            for g in groups:
+                buf = free_q.get()
+                if buf is None:
+                    return
+                arr = buf.numpy()
+                offs, futs, o = [0], [], 0
+                for info in g.files:
+                    n = info.n_samples * info.channels
+                    futs.append(pool.submit(read_into, info, arr[o:o + n]))
+                    o += n
+                    offs.append(o)
+                bad = {}
+                for i, fu in enumerate(futs):
+                    try:
+                        fu.result()
+                    except Exception as e:
+                        arr[offs[i]:offs[i + 1]] = 0
+                        bad[i] = f"File loading failed ({e})"
+                out_q.put((g, buf, offs, bad))
+            out_q.put(None)
+        except BaseException as e:          # surfaces in run(), never a silent short result
+            out_q.put(e)
+
+    def run(self, paths):
+        plan = get_plan(*self.fe_args)
+        dev = plan.device
+        infos = [probe_wav(p) for p in paths]
+        groups, rejected = plan_groups(infos, self.const, self.max_group_tiles)
+        for info, why in rejected:
+            self.failed.append((info.path, why))
+        if not groups:
+            return
+        cap_tiles = max(g.n_tiles for g in groups)
+        cap_vals = max(g.n_values for g in groups)
+        n_buf = 2
+        tiles_buf = [torch.empty((cap_tiles, 1, plan.n_bins, plan.w_pix), dtype=torch.float32, device=dev) for _ in range(n_buf)]
+        pcm_dev = [torch.empty(cap_vals, dtype=torch.int16, device=dev) for _ in range(n_buf)]
+        fe_stream = torch.cuda.Stream(device=dev)
+        fe_start = [torch.cuda.Event(enable_timing=True) for _ in range(n_buf)]
+        fe_done = [torch.cuda.Event(enable_timing=True) for _ in range(n_buf)]
+        det_done = [None] * n_buf
+        out_q: queue.Queue = queue.Queue()
+        free_q: queue.Queue = queue.Queue()
+        for _ in range(n_buf + 1):                                 # one being filled, one in flight, one being consumed
+            free_q.put(torch.empty(cap_vals, dtype=torch.int16).pin_memory())
+        pool = ThreadPoolExecutor(max_workers=self.readers)
+        th = threading.Thread(target=self._reader, args=(groups, out_q, free_q, pool), daemon=True)
+        th.start()
+        cur = torch.cuda.current_stream(dev)
+
+        def enqueue_frontend(slot, item):
+            g, host, offs, bad = item
+            with torch.cuda.stream(fe_stream):
+                if det_done[slot] is not None:
+                    fe_stream.wait_event(det_done[slot])            # the detector has finished with this tile buffer
+                fe_start[slot].record(fe_stream)
+                d = pcm_dev[slot][:g.n_values]
+                d.copy_(host[:g.n_values], non_blocking=True)
+                ch = g.channels                                     # interleaved; offsets are per-channel sample indices
+                _, tile_off, _ = plan.run_batch(d, [o // ch for o in offs], channels=ch, stream=fe_stream,
+                                                out=tiles_buf[slot][:g.n_tiles])
+                fe_done[slot].record(fe_stream)
+            assert [tile_off[i + 1] - tile_off[i] for i in range(len(g.files))] == g.tiles, "host tile count != library"
+            return tile_off
+
+        def next_group():
+            item = out_q.get()
+            if isinstance(item, BaseException):
+                raise item
+            return item
+
+        try:
+            nxt = next_group()
+            pending = None if nxt is None else (0, nxt, enqueue_frontend(0, nxt))
+            while pending is not None:
+                slot, item, tile_off = pending
+                g, host, offs, bad = item
+                nxt = next_group()                                  # next group's PCM (read while we were busy)
+                pending = None if nxt is None else ((slot + 1) % n_buf, nxt, enqueue_frontend((slot + 1) % n_buf, nxt))
+                cur.wait_event(fe_done[slot])
+                fe_done[slot].synchronize()
+                free_q.put(host)                                    # H2D done: the pinned buffer can be refilled
+                self.counts["t_front_us"] += int(fe_start[slot].elapsed_time(fe_done[slot]) * 1e3)
+                for i, info in enumerate(g.files):
+                    if i in bad:
+                        self.failed.append((info.path, bad[i])); continue
+                    t0 = time.perf_counter()
+                    tiles = tiles_buf[slot][tile_off[i]:tile_off[i + 1], 0]
+                    outputs = detect_tiles(self.model, tiles, self.min_score, self.bs)
+                    t1 = time.perf_counter()
+                    fp = SimpleNamespace(W_PIX=self.const["W_PIX"], HOP_SPECTRO=self.const["HOP_SPECTRO"],
+                                         spectrogram_length=g.frames[i])
+                    class_bbox = postproc.merge_images(fp, outputs, self.config.num_classes)
+                    output = {self.reverse_dict[idx]: {k: v.cpu().numpy().tolist() for k, v in class_bbox[str(idx)].items()}
+                              for idx in range(1, len(class_bbox) + 1) if len(class_bbox[str(idx)]["bbox_coord"]) > 0}
+                    t2 = time.perf_counter()
+                    c = self.counts
+                    c["files"] += 1; c["tiles"] += g.tiles[i]; c["frames"] += g.frames[i]
+                    c["detections"] += sum(len(v["scores"]) for v in output.values())
+                    c["t_model_us"] += int((t1 - t0) * 1e6); c["t_post_us"] += int((t2 - t1) * 1e6)
+                    yield info.path, output
+                det_done[slot] = torch.cuda.Event()
+                det_done[slot].record(cur)
+        finally:
+            free_q.put(None)                                        # unblock the reader if we stop early
+            pool.shutdown(wait=False, cancel_futures=True)
+            torch.cuda.synchronize(dev)

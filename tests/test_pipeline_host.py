@@ -1,0 +1,110 @@
+"""Host logic of the pipelined multi-file driver: frame / tile arithmetic against the
+oracle's restatement of prepare_dataset.py:234-266, grouping invariants, wav probing and decoding
+into a shared buffer.  No GPU."""
+import wave
+
+import numpy as np
+import pytest
+
+from birdsoundclassif_b200 import pipeline as pl
+from birdsoundclassif_b200 import synth
+from birdsoundclassif_b200.frontend import LONG_FILE_SAMPLES, derive_constants
+from oracle import frontend_oracle as fo
+
+CONST = derive_constants()
+
+
+@pytest.mark.parametrize("n,frames,tiles", [(441_000, 3341, 4), (1_323_000, 10_023, 12), (2_646_000, 20_046, 25),
+                                            (26_460_000, 200_455, 245), (149_984_100, 1_136_244, 1388)])
+def test_counts_match_survey_table(n, frames, tiles):
+    assert pl.count_frames_tiles(n, CONST["HOP_LENGTH"], CONST["W_PIX"], CONST["HOP_SPECTRO"]) == (frames, tiles)
+
+
+def test_counts_match_oracle_on_ragged_sizes():
+    p = fo.derive_params()
+    rng = np.random.default_rng(5)
+    sizes = [0, 1, 131, 132, 133, 1323, 1324, 135_167, 135_168, 135_300, 243_275, 243_276, 243_407, 243_408] + \
+        rng.integers(0, 3_000_000, 40).tolist()
+    for n in sizes:
+        T = fo.n_frames(n, p)
+        assert pl.count_frames_tiles(n, p.hop, p.w_pix, p.hop_spectro) == (T, fo.n_tiles(T, p)), n
+    # several STFT chunks per file (prepare_dataset.py:234-237), at a small chunk size
+    for n in [99_999, 100_000, 100_001, 250_000, 300_000]:
+        frames = sum(1 + max(0, min(n, (c + 1) * 100_000) - c * 100_000) // p.hop for c in range(n // 100_000 + 1))
+        assert pl.count_frames_tiles(n, p.hop, p.w_pix, p.hop_spectro, stft_chunk=100_000)[0] == frames
+
+
+def _info(i, seconds, ch=1, sr=44100, error=None):
+    return pl.WavInfo(f"f{i:03d}.wav", int(seconds * 44100), ch, sr, error)
+
+
+def test_plan_groups_invariants():
+    rng = np.random.default_rng(9)
+    infos = [_info(i, s) for i, s in enumerate(rng.uniform(0.5, 90, 60))]
+    for budget in (1, 7, 40, 10_000):
+        groups, rejected = pl.plan_groups(infos, CONST, budget)
+        assert not rejected
+        assert [f.path for g in groups for f in g.files] == [f.path for f in infos]        # order kept, nothing split or lost
+        for g in groups:
+            assert g.n_tiles <= budget or len(g.files) == 1                                  # an over-budget file stands alone
+            assert g.n_values == sum(f.n_samples for f in g.files)
+            for f, nt, fr in zip(g.files, g.tiles, g.frames):
+                assert (fr, nt) == pl.count_frames_tiles(f.n_samples, CONST["HOP_LENGTH"], CONST["W_PIX"], CONST["HOP_SPECTRO"])
+        if budget == 10_000:
+            assert len(groups) == 1
+        # greedy: a group is closed only when the next file would not fit
+        for a, b in zip(groups, groups[1:]):
+            assert a.n_tiles + b.tiles[0] > budget
+
+
+def test_plan_groups_channels_and_rejects():
+    infos = [_info(0, 3), _info(1, 3), _info(2, 3, ch=2), _info(3, 3, ch=2), _info(4, 3),
+             _info(5, 3, sr=48000), _info(6, 0, error="File loading failed (x)"),
+             pl.WavInfo("long.wav", LONG_FILE_SAMPLES + 1, 1, 44100)]
+    groups, rejected = pl.plan_groups(infos, CONST, 1000)
+    assert [[f.path for f in g.files] for g in groups] == [["f000.wav", "f001.wav"], ["f002.wav", "f003.wav"], ["f004.wav"]]
+    assert [g.channels for g in groups] == [1, 2, 1]
+    assert groups[1].n_values == 2 * 2 * 3 * 44100
+    assert [r[0].path for r in rejected] == ["f005.wav", "f006.wav", "long.wav"]
+    assert "48000" in rejected[0][1] and "split the recording" in rejected[2][1]
+
+
+def test_probe_and_read_into(tmp_path):
+    mono = synth.synth_pcm(1.5, 3)
+    stereo = np.stack([synth.synth_pcm(0.7, 4), synth.synth_pcm(0.7, 5)], axis=1)
+    pm, ps = str(tmp_path / "m.wav"), str(tmp_path / "s.wav")
+    synth.write_wav(pm, mono)
+    synth.write_wav(ps, stereo)
+    im, is_ = pl.probe_wav(pm), pl.probe_wav(ps)
+    assert (im.n_samples, im.channels, im.sample_rate, im.error) == (len(mono), 1, 44100, None)
+    assert (is_.n_samples, is_.channels) == (len(stereo), 2)
+    buf = np.full(len(mono) + 2 * len(stereo) + 8, 7, dtype=np.int16)
+    pl.read_into(im, buf[:len(mono)])
+    pl.read_into(is_, buf[len(mono):len(mono) + 2 * len(stereo)])
+    assert np.array_equal(buf[:len(mono)], mono)
+    assert np.array_equal(buf[len(mono):len(mono) + 2 * len(stereo)].reshape(-1, 2), stereo)
+    assert (buf[-8:] == 7).all()
+    # failures: not a wav, 8-bit wav, truncated data
+    bad = tmp_path / "bad.wav"
+    bad.write_bytes(b"not a wav at all")
+    assert "File loading failed" in pl.probe_wav(str(bad)).error
+    with wave.open(str(tmp_path / "u8.wav"), "wb") as w:
+        w.setnchannels(1); w.setsampwidth(1); w.setframerate(44100); w.writeframes(bytes(100))
+    assert "PCM16" in pl.probe_wav(str(tmp_path / "u8.wav")).error
+    raw = open(pm, "rb").read()
+    (tmp_path / "cut.wav").write_bytes(raw[:len(raw) // 2])
+    ic = pl.probe_wav(str(tmp_path / "cut.wav"))
+    if ic.error is None:
+        with pytest.raises(Exception):
+            pl.read_into(ic, np.zeros(ic.n_samples, dtype=np.int16))
+
+
+def test_pipeline_needs_cuda(tmp_path):
+    import json
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    d = tmp_path / "bird_dict.json"
+    d.write_text(json.dumps({"A": 1}))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pl.DetectionPipeline(None, synth.default_args("cpu"), str(d))
