@@ -251,8 +251,9 @@ class File_Processor:
         if sr != self.FREQ:
             # the reference shells out to ffmpeg here (prepare_dataset.py:166-182)
             raise ValueError(f"{self.filepath}: sample rate {sr} != {self.FREQ}; resample first (no ffmpeg path)")
-        t = torch.from_numpy(np.ascontiguousarray(pcm))
-        return t.pin_memory() if torch.cuda.is_available() else t
+        t = torch.empty(pcm.shape, dtype=torch.int16, pin_memory=torch.cuda.is_available())
+        t.numpy()[...] = pcm            # one copy, decoded bytes -> pinned memory
+        return t
 
     def process_file(self, freq_accuracy=33.3, dt=0.003, overlap_spectro=0.2, w_pix=1024):
         data = self.load()

@@ -88,9 +88,17 @@ class Group:
         return sum(f.n_samples * f.channels for f in self.files)
 
 
-def plan_groups(infos, const, max_group_tiles: int, stft_chunk: int = STFT_CHUNK):
-    """Contiguous groups of whole files in the given order, at most `max_group_tiles` detector tiles
-    each (a single larger file forms its own group) and one channel count per group.
+def group_budget(index: int, max_group_tiles: int, first_group_tiles: int | None) -> int:
+    """Tile budget of the index-th group: the first group is small so that the detector starts after a few files
+    have been read rather than after a whole batch (nothing overlaps the first read), then budgets double."""
+    if not first_group_tiles:
+        return max_group_tiles
+    return min(max_group_tiles, first_group_tiles << min(index, 30))
+
+
+def plan_groups(infos, const, max_group_tiles: int, stft_chunk: int = STFT_CHUNK, first_group_tiles: int | None = None):
+    """Contiguous groups of whole files in the given order, group i holding at most
+    `group_budget(i, ...)` detector tiles (a single larger file forms its own group) and one channel count per group.
     Returns (groups, rejected) -- rejected = [(WavInfo, reason)] for unreadable / unsupported files."""
     groups, rejected = [], []
     cur = None
@@ -102,7 +110,8 @@ def plan_groups(infos, const, max_group_tiles: int, stft_chunk: int = STFT_CHUNK
         if info.n_samples > LONG_FILE_SAMPLES:
             rejected.append((info, f"{info.n_samples} samples > {LONG_FILE_SAMPLES}; split the recording first")); continue
         fr, nt = count_frames_tiles(info.n_samples, const["HOP_LENGTH"], const["W_PIX"], const["HOP_SPECTRO"], stft_chunk)
-        if cur is None or cur.channels != info.channels or (cur.files and cur.n_tiles + nt > max_group_tiles):
+        if cur is None or cur.channels != info.channels or \
+                (cur.files and cur.n_tiles + nt > group_budget(len(groups) - 1, max_group_tiles, first_group_tiles)):
             cur = Group(channels=info.channels)
             groups.append(cur)
         cur.files.append(info); cur.tiles.append(nt); cur.frames.append(fr)
@@ -124,12 +133,12 @@ class DetectionPipeline:
     """``run(paths)`` yields ``(path, output_dict)`` in input order, the dictionaries equal to
     ``run_detection.run_detection(model, config, path, ...)``."""
 
-    def __init__(self, model, config, bird_dicts_path, min_score=0.5, bs=10, max_group_tiles=1024, readers=4,
+    def __init__(self, model, config, bird_dicts_path, min_score=0.5, bs=10, max_group_tiles=1024, readers=4, first_group_tiles=64,
                  freq_accuracy=33.3, dt=0.003, overlap_spectro=0.2, w_pix=1024):
         if not torch.cuda.is_available():
             raise RuntimeError("the detection pipeline needs a CUDA device (no CPU fallback)")
         self.model, self.config, self.min_score, self.bs = model, config, min_score, bs
-        self.max_group_tiles, self.readers = int(max_group_tiles), int(readers)
+        self.max_group_tiles, self.readers, self.first_group_tiles = int(max_group_tiles), int(readers), first_group_tiles
         self.fe_args = (freq_accuracy, dt, overlap_spectro, w_pix)
         self.const = derive_constants(*self.fe_args)
         with open(bird_dicts_path, "r") as f:
@@ -169,7 +178,7 @@ class DetectionPipeline:
         plan = get_plan(*self.fe_args)
         dev = plan.device
         infos = [probe_wav(p) for p in paths]
-        groups, rejected = plan_groups(infos, self.const, self.max_group_tiles)
+        groups, rejected = plan_groups(infos, self.const, self.max_group_tiles, first_group_tiles=self.first_group_tiles)
         for info, why in rejected:
             self.failed.append((info.path, why))
         if not groups:

@@ -57,6 +57,17 @@ def test_plan_groups_invariants():
             assert a.n_tiles + b.tiles[0] > budget
 
 
+def test_plan_groups_ramp():
+    infos = [_info(i, 30) for i in range(200)]                      # 12 tiles each
+    groups, _ = pl.plan_groups(infos, CONST, 1024, first_group_tiles=64)
+    assert [f.path for g in groups for f in g.files] == [f.path for f in infos]
+    budgets = [pl.group_budget(i, 1024, 64) for i in range(len(groups))]
+    assert budgets[:6] == [64, 128, 256, 512, 1024, 1024]
+    assert all(g.n_tiles <= b for g, b in zip(groups, budgets))
+    assert [len(g.files) for g in groups[:4]] == [5, 10, 21, 42]
+    assert pl.group_budget(3, 100, None) == 100 and pl.group_budget(50, 1 << 20, 64) == 1 << 20
+
+
 def test_plan_groups_channels_and_rejects():
     infos = [_info(0, 3), _info(1, 3), _info(2, 3, ch=2), _info(3, 3, ch=2), _info(4, 3),
              _info(5, 3, sr=48000), _info(6, 0, error="File loading failed (x)"),
