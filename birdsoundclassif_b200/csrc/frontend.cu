@@ -606,6 +606,19 @@ tile_follow_kernel(KParams P, RefineParams R, const SegDesc *__restrict__ segs, 
 #endif
 }
 
+// Dataset images (prepare_dataset.py:85: np.round(img * 255).astype(np.uint8)): round-half-even of the normalised
+// tile value times 255.  Pure streaming pass, 4 B read + 1 B written per pixel.
+__global__ void __launch_bounds__(256)
+tiles_to_u8_kernel(const float4 *__restrict__ src, uchar4 *__restrict__ dst, long long n4,
+                   const float *__restrict__ tail_src, unsigned char *__restrict__ tail_dst, int n_tail) {
+    auto q = [](float v) { return (unsigned char)__float2int_rn(fminf(fmaxf(v, 0.0f), 1.0f) * 255.0f); };
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldcs(src + i);
+        dst[i] = make_uchar4(q(v.x), q(v.y), q(v.z), q(v.w));
+    }
+    if (blockIdx.x == 0 && (int)threadIdx.x < n_tail) tail_dst[threadIdx.x] = q(tail_src[threadIdx.x]);
+}
+
 }  // namespace nbm
 
 // ------------------------------------------------------------------------------ host side ------
@@ -1096,4 +1109,24 @@ extern "C" int nbm_frontend_run(const nbm_frontend_plan *pl, const void *d_pcm, 
     int64_t off[2] = {0, n_samples};
     return nbm_frontend_run_batch(pl, d_pcm, pcm_dtype, channels, off, 1, d_tiles, d_minmax, d_workspace,
                                   workspace_bytes, stream);
+}
+
+extern "C" int nbm_tiles_to_u8(const float *d_tiles, int64_t n_values, uint8_t *d_out, void *stream_) {
+    NBM_REQUIRE(n_values >= 0, "bad argument");
+    if (n_values == 0) return NBM_OK;
+    NBM_REQUIRE(d_tiles && d_out, "bad argument");
+    NBM_REQUIRE((reinterpret_cast<uintptr_t>(d_tiles) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 3) == 0,
+                "tile buffers must be 16-byte (float) / 4-byte (uint8) aligned");
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    const long long n4 = n_values / 4;
+    const int n_tail = (int)(n_values - 4 * n4);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long want = (n4 + 255) / 256;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)sms * 8));
+    nbm::tiles_to_u8_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4 *>(d_tiles), reinterpret_cast<uchar4 *>(d_out), n4,
+                                                      d_tiles + 4 * n4, d_out + 4 * n4, n_tail);
+    NBM_CUDA(cudaGetLastError());
+    return NBM_OK;
 }

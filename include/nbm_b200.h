@@ -112,6 +112,11 @@ int nbm_frontend_get_profile(nbm_frontend_plan *plan, double *stft_ms, double *t
 /* The same, per kernel: ms4 = {anchor GEMM, slide/STFT kernel, whole-file min/max, tiling}. */
 int nbm_frontend_get_profile_kernels(nbm_frontend_plan *plan, double *ms4, int64_t *runs);
 
+/* Dataset images from detector tiles: out = uint8(round_half_even(tile * 255)), the quantisation
+ * prepare_dataset() applies before writing a PNG (prepare_dataset.py:85).  d_tiles 16-byte aligned,
+ * n_values = number of pixels (any count), asynchronous on `stream`. */
+int nbm_tiles_to_u8(const float *d_tiles, int64_t n_values, uint8_t *d_out, void *stream);
+
 /* ------------------------------------------------------------- post-processing --------
  * Anchor table: generate_anchors_frcnn + get_anchor_shifts_frcnn combined as in
  * ProposalLayer.forward (nets_utils.py:35-59, layers.py:252-258).  Host arithmetic;
