@@ -243,9 +243,7 @@ class DetectionPipeline:
                     t1 = time.perf_counter()
                     fp = SimpleNamespace(W_PIX=self.const["W_PIX"], HOP_SPECTRO=self.const["HOP_SPECTRO"],
                                          spectrogram_length=g.frames[i])
-                    class_bbox = postproc.merge_images(fp, outputs, self.config.num_classes)
-                    output = {self.reverse_dict[idx]: {k: v.cpu().numpy().tolist() for k, v in class_bbox[str(idx)].items()}
-                              for idx in range(1, len(class_bbox) + 1) if len(class_bbox[str(idx)]["bbox_coord"]) > 0}
+                    output = postproc.merge_to_output(fp, outputs, self.config.num_classes, self.reverse_dict)
                     t2 = time.perf_counter()
                     c = self.counts
                     c["files"] += 1; c["tiles"] += g.tiles[i]; c["frames"] += g.frames[i]

@@ -180,22 +180,41 @@ def final_detections_flat(bbox_reg, bbox_classes, rois, num_classes, img_width, 
     return boxes, scores, classes, counts
 
 
+class TileDetections(dict):
+    """The reference's per-image dictionary plus the flat record it was built from (boxes [n,4], scores [n],
+    classes int32 [n], device tensors in surviving order), so that the per-file merge can take the records as
+    they are instead of re-collecting them from 150 dictionary entries per tile.  ``flat`` describes the
+    dictionary as it was built; code that edits the entries afterwards must set it to None."""
+    __slots__ = ("flat",)
+
+
 def records_to_dicts(boxes, scores, classes, counts, num_classes, proposal_number=None):
     """Flat records -> the reference's list(B) of {str(c): {'bbox_coord': [n,4], 'scores': [1,n]}}
-    (layers.py:750-775); empty classes are CPU ``torch.Tensor()`` like the reference."""
-    cnt = counts.tolist()
-    cls_host = classes.cpu()
+    (layers.py:750-775); empty classes are CPU ``torch.Tensor()`` like the reference.  One stable sort by class
+    for the whole batch and one device-to-host copy; the per-class entries are views of the sorted rows (the
+    reference spends 150 iterations with a nonzero + sync each per image, layers.py:757-775)."""
+    B, R = classes.shape
+    dev = boxes.device
+    invalid = int(num_classes) + 1
+    key = torch.where(torch.arange(R, device=dev)[None] < counts[:, None], classes, invalid)
+    skey, order = torch.sort(key, dim=1, stable=True)               # per-class order = surviving order
+    sb = torch.gather(boxes, 1, order[..., None].expand(-1, -1, 4))
+    ss = torch.gather(scores, 1, order)
+    skey_h = skey.cpu().numpy()
     out = []
-    for b, n in enumerate(cnt):
-        d = {str(c): dict(bbox_coord=torch.Tensor(), scores=torch.Tensor()) for c in range(1, num_classes + 1)}
+    for b in range(B):
+        row = skey_h[b]
+        n = int((row < invalid).sum())
+        d = TileDetections((str(c), dict(bbox_coord=torch.Tensor(), scores=torch.Tensor())) for c in range(1, num_classes + 1))
+        truncated = False
         if n:
-            cb = cls_host[b, :n]
-            for c in torch.unique(cb).tolist():
-                w = torch.nonzero(cb == c)[:, 0]
-                if proposal_number is not None:
-                    w = w[:proposal_number]
-                w = w.to(boxes.device)
-                d[str(c)] = dict(bbox_coord=boxes[b, w], scores=scores[b, w][None])
+            starts = [0] + (np.flatnonzero(row[1:n] != row[:n - 1]) + 1).tolist() + [n]
+            for s0, s1 in zip(starts[:-1], starts[1:]):
+                if proposal_number is not None and s1 - s0 > proposal_number:
+                    s1 = s0 + proposal_number
+                    truncated = True
+                d[str(int(row[s0]))] = dict(bbox_coord=sb[b, s0:s1], scores=ss[b, s0:s1][None])
+        d.flat = None if truncated else (boxes[b, :n], scores[b, :n], classes[b, :n])
         out.append(d)
     return out
 
@@ -238,6 +257,12 @@ def flatten_tile_dicts(out: list, num_classes: int, device):
     """list of per-tile dicts (the model's output format) -> flat (boxes, scores, classes, tiles),
     tile-major, per tile class-major (any within-tile order works: merge sorts by class stably and
     the per-class order inside a tile is preserved)."""
+    if out and all(isinstance(d, TileDetections) and d.flat is not None for d in out):
+        # the records the dictionaries were built from: three concatenations instead of 150 x n_tiles look-ups
+        counts = torch.tensor([len(d.flat[1]) for d in out], dtype=torch.int64)
+        tt = torch.repeat_interleave(torch.arange(len(out), dtype=torch.int32), counts).to(device, non_blocking=True)
+        return (torch.cat([d.flat[0] for d in out]).to(device), torch.cat([d.flat[1] for d in out]).to(device),
+                torch.cat([d.flat[2] for d in out]).to(device), tt)
     bb, ss, cc, tt = [], [], [], []
     for i, d in enumerate(out):
         for c in range(1, num_classes + 1):
@@ -270,17 +295,34 @@ def survivors_to_class_dict(boxes, scores, classes, num_classes):
     return out
 
 
-def merge_images(fp, outputs, num_classes, nms_thresh=0.3):
-    """Drop-in for run_detection.merge_images: `outputs` is the list of per-batch lists of per-tile
-    dicts the model returned; `fp` carries W_PIX, HOP_SPECTRO, spectrogram_length."""
+def _merge_survivors(fp, outputs, num_classes, nms_thresh):
     out = []
     for b in outputs:
         out.extend(b)
     dev = torch.device("cuda", torch.cuda.current_device())
     boxes, scores, classes, tiles = flatten_tile_dicts(out, num_classes, dev)
-    kb, ks, kc = merge_flat(boxes, scores, classes, tiles, len(out), fp.W_PIX, fp.HOP_SPECTRO,
-                            int(fp.spectrogram_length), nms_thresh)
+    return merge_flat(boxes, scores, classes, tiles, len(out), fp.W_PIX, fp.HOP_SPECTRO, int(fp.spectrogram_length), nms_thresh)
+
+
+def merge_images(fp, outputs, num_classes, nms_thresh=0.3):
+    """Drop-in for run_detection.merge_images: `outputs` is the list of per-batch lists of per-tile
+    dicts the model returned; `fp` carries W_PIX, HOP_SPECTRO, spectrogram_length."""
+    kb, ks, kc = _merge_survivors(fp, outputs, num_classes, nms_thresh)
     return survivors_to_class_dict(kb, ks, kc, num_classes)
+
+
+def merge_to_output(fp, outputs, num_classes, reverse_dict, nms_thresh=0.3) -> dict:
+    """merge_images followed by run_detection.py:69-77 in one step: the per-file output dictionary
+    ``{species: {'bbox_coord': [[x1,y1,x2,y2],...], 'scores': [...]}}`` (classes ascending, empty ones left out)
+    from ONE device-to-host copy of the survivors instead of two per detected class."""
+    kb, ks, kc = _merge_survivors(fp, outputs, num_classes, nms_thresh)
+    kb, ks, kc = kb.cpu().numpy(), ks.cpu().numpy(), kc.cpu().numpy()
+    output = {}
+    for idx in sorted(set(kc.tolist())):
+        if 1 <= idx <= num_classes:
+            w = kc == idx
+            output[reverse_dict[idx]] = {"bbox_coord": kb[w].tolist(), "scores": ks[w].tolist()}
+    return output
 
 
 # ------------------------------------------------------------------------------ RoI pooling ----

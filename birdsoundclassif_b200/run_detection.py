@@ -93,9 +93,8 @@ def run_detection(model, config, wav_path, bird_dicts_path, min_score=0.5, bs=10
     birds_dict.update({"Non bird sound": 0})
     reverse_dict = {idx: name for name, idx in birds_dict.items()}
 
-    class_bbox = postproc.merge_images(fp, outputs, config.num_classes)
-    output = {reverse_dict[idx]: {k: v.cpu().numpy().tolist() for k, v in class_bbox[str(idx)].items()}
-              for idx in range(1, len(class_bbox) + 1) if len(class_bbox[str(idx)]["bbox_coord"]) > 0}
+    # == merge_images + the dictionary comprehension of run_detection.py:69-77 (tested equal)
+    output = postproc.merge_to_output(fp, outputs, config.num_classes, reverse_dict)
     if timings is not None:
         t3 = time.perf_counter()
         timings.update(frontend_s=t1 - t0, model_s=t2 - t1, post_s=t3 - t2, tiles=len(img_db),

@@ -236,3 +236,43 @@ def test_roi_pooling_golden_and_oracle(pp):
     np.testing.assert_array_equal(lvl, rl)
     np.testing.assert_array_equal(pool.cpu().numpy(), rp)
     np.testing.assert_array_equal(pe.cpu().numpy(), rpe)
+
+
+def test_flat_record_fast_paths_equal_dictionary_paths(pp):
+    """records_to_dicts attaches the flat record to each per-image dictionary; the per-file merge taking those records
+    (three concatenations) and merge_to_output (one D2H copy) must equal the dictionary walk + the reference's output
+    comprehension (run_detection.py:69-77) bit for bit."""
+    rng = np.random.default_rng(33)
+    B, R, ncls = 7, 50, 150
+    x1 = rng.integers(0, 900, (B, R)); y1 = rng.integers(0, 300, (B, R))
+    boxes = np.stack([x1, y1, np.minimum(x1 + rng.integers(6, 220, (B, R)), 1023),
+                      np.minimum(y1 + rng.integers(6, 70, (B, R)), 374)], -1).astype(np.float32)
+    scores = np.sort(rng.random((B, R)).astype(np.float32), axis=1)[:, ::-1].copy()
+    classes = rng.integers(1, 9, (B, R)).astype(np.int32)
+    counts = np.array([50, 0, 17, 50, 1, 33, 50], np.int32)
+    dicts = pp.records_to_dicts(_cuda(boxes), _cuda(scores), _cuda(classes), _cuda(counts), ncls, 50)
+    assert all(isinstance(d, pp.TileDetections) and d.flat is not None for d in dicts)
+    dev = torch.device("cuda")
+    fast = pp.flatten_tile_dicts(dicts, ncls, dev)
+    plain = [dict(d) for d in dicts]                                   # ordinary dicts: the 150 x n_tiles walk
+    slow = pp.flatten_tile_dicts(plain, ncls, dev)
+    # same multiset per (tile, class) in the same relative order -> compare after the stable class sort merge applies
+    def canon(t):
+        b, s, c, ti = [x.cpu().numpy() for x in t]
+        o = np.lexsort((np.arange(len(c)), c, ti))                     # tile-major, class-major, original order
+        return b[o], s[o], c[o], ti[o]
+    for a, b in zip(canon(fast), canon(slow)):
+        np.testing.assert_array_equal(a, b)
+    fp = types.SimpleNamespace(W_PIX=1024, HOP_SPECTRO=819, spectrogram_length=(B - 1) * 819 + 700)
+    batches_fast = [dicts[i:i + 3] for i in range(0, B, 3)]
+    batches_slow = [plain[i:i + 3] for i in range(0, B, 3)]
+    rev = {i: f"Species {i}" for i in range(0, ncls + 1)}
+    class_bbox = pp.merge_images(fp, batches_slow, ncls)
+    want = {rev[idx]: {k: v.cpu().numpy().tolist() for k, v in class_bbox[str(idx)].items()}
+            for idx in range(1, len(class_bbox) + 1) if len(class_bbox[str(idx)]["bbox_coord"]) > 0}
+    got = pp.merge_to_output(fp, batches_fast, ncls, rev)
+    assert got == want and list(got) == list(want) and len(got) > 0
+    # a per-class truncation (more than proposal_number rows of one class) invalidates the record
+    d2 = pp.records_to_dicts(_cuda(boxes), _cuda(scores), _cuda(np.ones_like(classes)), _cuda(counts), ncls, 10)
+    assert d2[0].flat is None and len(d2[0]["1"]["bbox_coord"]) == 10
+    assert d2[4].flat is not None
