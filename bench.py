@@ -328,6 +328,9 @@ def run_b200(a):
     peak, peak_src = peaks()
     stft_per_launch_ms = float(allst[0, 3]) / max(runs, 1)
     achieved = frames * BYTES_PER_FRAME / (stft_per_launch_ms / 1e3) / 1e9
+    tile_ms = float(allst[0, 4]) / max(runs, 1)
+    tile_bytes = frames * 375 * 4 + tiles.numel() * 4
+    tile_gbs = tile_bytes / (tile_ms / 1e3) / 1e9 if tile_ms > 0 else 0.0
     line = {
         "metric": "audio-hours/sec", "value": value, "unit": "audio-hours/s", "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": t_ms / a.steps, "higher_is_better": True, "scaling": "weak",
@@ -350,6 +353,9 @@ def run_b200(a):
                      "other_kernels_ms_per_launch": {"anchor_tc_kernel": float(allst[0, 6]) / max(runs, 1),
                                                      "refine_minmax_kernel": float(allst[0, 7]) / max(runs, 1),
                                                      "tile_kernel": float(allst[0, 4]) / max(runs, 1)},
+                     "tile_kernel": {"bound": "hbm", "achieved": tile_gbs, "peak": peak, "unit": "GB/s", "frac": tile_gbs / peak,
+                                     "algorithmic_bytes_per_launch": tile_bytes,
+                                     "note": "second pass: dB band read once (4 B x 375 x frames) + tiles written once"},
                      "note": "the kernel is instruction-issue / shared-memory bound, not HBM bound (DESIGN.md 3)"},
         "clocks": clocks,
         "gpu_launches": 5 * a.steps,      # upload, anchor, slide, min/max, tile per step

@@ -927,29 +927,49 @@ slide_ws_body(const TcParams &P, const SegDesc *__restrict__ segs, int n_segs, i
                 char *out = reinterpret_cast<char *>(spec + cw.sd.spec_off + (long long)(range * BINS_PER_RANGE + ra - 1) * stride + t0 + fc);
                 const long long stride_b = (long long)stride * 4;
                 const bool pair_ok = (cw.sd.spec_off & 1) == 0;          // a later STFT chunk of a long file may start on an odd column
-                // unroll 4 measured best: 2 lacks ILP, 8 (or a fixed-trip fully unrolled loop) loses more to instruction fetch
-#pragma unroll 4
-                for (int r = ra; r < rb; ++r) {
-                    const float4 nx = st[(r + 1) * LD4];
-                    // 4 X = 2 R[k] - (R[k-1] + R[k+1]);  10 log10(|X|^2) = 10 log10(|4X|^2) - 10 log10(16)
+                // 4 X = 2 R[k] - (R[k-1] + R[k+1]);  10 log10(|X|^2) = 10 log10(|4X|^2) - 10 log10(16)
+                auto row_db = [&](const float4 &nx, float &db0, float &db1) {
                     const float xr0 = fmaf(2.0f, cu.x, -(pv.x + nx.x)), xi0 = fmaf(2.0f, cu.y, -(pv.y + nx.y));
                     const float xr1 = fmaf(2.0f, cu.z, -(pv.z + nx.z)), xi1 = fmaf(2.0f, cu.w, -(pv.w + nx.w));
                     const float pw0 = fmaxf(fmaf(xr0, xr0, xi0 * xi0), floor_pw);
                     const float pw1 = fmaxf(fmaf(xr1, xr1, xi1 * xi1), floor_pw);
-                    const float db0 = fmaf(fast_log2(pw0), 3.0102999566398120f, -12.041199826559248f);
-                    const float db1 = fmaf(fast_log2(pw1), 3.0102999566398120f, -12.041199826559248f);
-                    if (nfr > 1) {
-                        if (pair_ok) *reinterpret_cast<float2 *>(out) = make_float2(db0, db1);
-                        else { reinterpret_cast<float *>(out)[0] = db0; reinterpret_cast<float *>(out)[1] = db1; }
+                    db0 = fmaf(fast_log2(pw0), 3.0102999566398120f, -12.041199826559248f);
+                    db1 = fmaf(fast_log2(pw1), 3.0102999566398120f, -12.041199826559248f);
+                };
+                if (nfr > 1 && pair_ok) {
+                    // The common case on its own loop: with the width / alignment tests inside the loop the compiler
+                    // merged the 8-byte store with the scalar fallback into predicated 4-byte stores (three STG and four
+                    // predicated min/max per row instead of one STG.64 and two FMNMX3).
+                    // unroll 4 measured best: 2 lacks ILP, 8 (or a fixed-trip fully unrolled loop) loses more to instruction fetch
+#pragma unroll 4
+                    for (int r = ra; r < rb; ++r) {
+                        const float4 nx = st[(r + 1) * LD4];
+                        float db0, db1;
+                        row_db(nx, db0, db1);
+                        *reinterpret_cast<float2 *>(out) = make_float2(db0, db1);
                         vmin = fminf(vmin, fminf(db0, db1));
                         vmax = fmaxf(vmax, fmaxf(db0, db1));
-                    } else {
-                        *reinterpret_cast<float *>(out) = db0;
+                        out += stride_b;
+                        pv = cu; cu = nx;
+                    }
+                } else {
+                    // last (odd) frame column of a segment, or a later STFT chunk of a long file that starts on an odd column
+#pragma unroll 1
+                    for (int r = ra; r < rb; ++r) {
+                        const float4 nx = st[(r + 1) * LD4];
+                        float db0, db1;
+                        row_db(nx, db0, db1);
+                        reinterpret_cast<float *>(out)[0] = db0;
                         vmin = fminf(vmin, db0);
                         vmax = fmaxf(vmax, db0);
+                        if (nfr > 1) {
+                            reinterpret_cast<float *>(out)[1] = db1;
+                            vmin = fminf(vmin, db1);
+                            vmax = fmaxf(vmax, db1);
+                        }
+                        out += stride_b;
+                        pv = cu; cu = nx;
                     }
-                    out += stride_b;
-                    pv = cu; cu = nx;
                 }
             }
 #pragma unroll
