@@ -435,9 +435,9 @@ tile_block(const KParams &P, const FileDesc &fd, long long tile, int row_block, 
     float *tbase = tiles + (tile * P.n_bins) * P.w_pix;
     // L2_ONLY: the band was written by other SMs during this very launch; read it from L2, never through L1
     auto ld = [](const float *p) { return L2_ONLY ? __ldcg(p) : *p; };
-    if (VEC4 && L2_ONLY && width == P.w_pix) {
-        // Full tile read from L2: four scalar loads per thread would each fetch a quarter of every 32-byte sector they
-        // touch (4x the L2 -> SM traffic once L1 is bypassed).  Rows are 128-byte aligned (row_stride % 32 == 0), so
+    if (VEC4 && width == P.w_pix) {
+        // Full tile: four scalar loads per thread would each touch a quarter of every 32-byte sector (4x the L1 look-ups,
+        // and 4x the L2 -> SM traffic where L1 is bypassed).  Rows are 128-byte aligned (row_stride % 32 == 0), so
         // the tile's misalignment is start & 3 for every row: two aligned 16-byte loads, re-aligned in registers.
         const int sh = start & 3;
         auto rows = [&](auto SH) {
@@ -446,9 +446,9 @@ tile_block(const KParams &P, const FileDesc &fd, long long tile, int row_block, 
 #pragma unroll 5
                 for (int r = r0; r < r1; ++r) {
                     const float4 *q = reinterpret_cast<const float4 *>(sbase + (long long)r * fd.row_stride + c - S);
-                    const float4 a = __ldcg(q);
+                    const float4 a = L2_ONLY ? __ldcg(q) : __ldg(q);
                     float4 b = a;
-                    if (S != 0) b = __ldcg(q + 1);
+                    if (S != 0) b = L2_ONLY ? __ldcg(q + 1) : __ldg(q + 1);
                     float4 v;
                     if (S == 0) v = a;
                     else if (S == 1) v = make_float4(a.y, a.z, a.w, b.x);
