@@ -505,7 +505,7 @@ __device__ __forceinline__ int file_of_tile(const FileDesc *__restrict__ files, 
 }
 
 template <bool VEC4>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 tile_kernel(KParams P, const FileDesc *__restrict__ files, int n_files, const float *__restrict__ spec,
             const float *__restrict__ minmax, float *__restrict__ tiles, long long tile_begin) {
     const long long tile = blockIdx.x + tile_begin;
