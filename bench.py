@@ -29,7 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 BYTES_PER_FRAME = 264 + 1500          # 132 int16 samples in + 375 fp32 bins out
-TRAFFIC_BYTES_PER_FRAME = 1774        # measured DRAM bytes per frame of slide_ws_kernel (profiles/r01_slide_ws_kernel_ncu.txt)
+TRAFFIC_BYTES_PER_FRAME = 1771        # measured DRAM bytes per frame of slide_ws_kernel (profiles/r01_slide_ws_kernel_ncu.txt)
 SAMPLE_RATE = 44100
 
 

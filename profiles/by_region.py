@@ -13,7 +13,7 @@ root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 src = open(os.path.join(root, "birdsoundclassif_b200/csrc/frontend_tc.cu")).read().splitlines()
 pat = r"MMA issuer \(all|fill warp of group|worker group g ====|auto planes|auto build_unit|auto build_tail|auto build = |auto anchor_of|// ---- recur|// ---- next chain|// ---- emit|stage free for the next|float2 anc_next"
 marks = [(i + 1, l.strip()[:34]) for i, l in enumerate(src) if re.search(pat, l)]
-k0 = next(i + 1 for i, l in enumerate(src) if "slide_ws_kernel(TcParams" in l)
+k0 = next(i + 1 for i, l in enumerate(src) if "slide_ws_body(const TcParams" in l)
 def region(ln):
     name = "setup"
     for m, t in marks:
