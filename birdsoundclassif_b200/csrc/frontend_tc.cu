@@ -189,6 +189,13 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+// the same with the accumulate flag known at compile time (no predicate register to set up per instruction)
+template <bool ACC>
+__device__ __forceinline__ void umma_f16_ts_c(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "n"(ACC ? 1 : 0) : "memory");
+}
 
 
 // ------------------------------------------------------------------------- anchor kernel -------
@@ -591,43 +598,37 @@ slide_ws_body(const TcParams &P, const SegDesc *__restrict__ segs, int n_segs, i
                     // the hi x hi ones) are summed first, while the accumulator is still small and they keep their low
                     // bits; the integer-valued hi x hi products are added last (5 roundings instead of 40).
                     const uint32_t d_c = tmem_base + (uint32_t)gg * TM_ACC_PER_GROUP, d_s = d_c + CF;
-#pragma unroll 1
-                    for (int pass = 0; pass < 2; ++pass)
-#pragma unroll 1
-                        for (int kk = 0; kk < nk; ++kk) {
+                    // Fully unrolled (nk <= NK_T is a condition of tc_plan_create, so every twiddle block is in TMEM): rolled,
+                    // each MMA cost ~45 cycles of dependent uniform-datapath address arithmetic and branches, and this one
+                    // warp, which serves all three groups, was busy 81 % of the time -- the groups queued for it.
+                    constexpr uint32_t mt = NK_T * 8;                   // cos_h, cos_l, sin_h, sin_l at ka + {0,1,2,3} mt
+#pragma unroll
+                    for (int kk = 0; kk < NK_T; ++kk) {
+                        if (kk < nk) {
                             const uint64_t ko = (uint64_t)(kk * 16);    // 256 B per k-step in the 16-byte address field
-                            if (kk < NK_T) {
-                                const uint32_t ka = tmem_a + kk * 8, mt = NK_T * 8;    // cos_h, cos_l, sin_h, sin_l at ka + {0,1,2,3} mt
-                                if (pass == 0) {
-                                    const uint32_t acc = kk > 0 ? 1u : 0u;
-                                    umma_f16_ts(d_c, ka + 1 * mt, dpl + ko, idesc, acc);
-                                    umma_f16_ts(d_s, ka + 3 * mt, dml + ko, idesc, acc);
-                                    umma_f16_ts(d_c, ka + 1 * mt, dph + ko, idesc, 1u);
-                                    umma_f16_ts(d_s, ka + 3 * mt, dmh + ko, idesc, 1u);
-                                    umma_f16_ts(d_c, ka + 0 * mt, dpl + ko, idesc, 1u);
-                                    umma_f16_ts(d_s, ka + 2 * mt, dml + ko, idesc, 1u);
-                                } else {
-                                    umma_f16_ts(d_c, ka + 0 * mt, dph + ko, idesc, 1u);
-                                    umma_f16_ts(d_s, ka + 2 * mt, dmh + ko, idesc, 1u);
-                                }
+                            const uint32_t ka = tmem_a + kk * 8;
+                            if (kk == 0) {
+                                umma_f16_ts_c<false>(d_c, ka + 1 * mt, dpl + ko, idesc);
+                                umma_f16_ts_c<false>(d_s, ka + 3 * mt, dml + ko, idesc);
                             } else {
-                                const uint32_t a0 = smem_u32(sAt) + (uint32_t)(kk - NK_T) * 256, am = 128 * 16 * 2 * (uint32_t)(nk - NK_T);
-                                const uint32_t sbo_a = (uint32_t)(16 * (nk - NK_T) / 8) * 128;
-                                const uint64_t ach = make_desc(a0 + 0 * am, 128, sbo_a), acl = make_desc(a0 + 1 * am, 128, sbo_a);
-                                const uint64_t ash = make_desc(a0 + 2 * am, 128, sbo_a), asl = make_desc(a0 + 3 * am, 128, sbo_a);
-                                if (pass == 0) {
-                                    umma_f16(d_c, acl, dpl + ko, idesc, 1u);
-                                    umma_f16(d_s, asl, dml + ko, idesc, 1u);
-                                    umma_f16(d_c, acl, dph + ko, idesc, 1u);
-                                    umma_f16(d_s, asl, dmh + ko, idesc, 1u);
-                                    umma_f16(d_c, ach, dpl + ko, idesc, 1u);
-                                    umma_f16(d_s, ash, dml + ko, idesc, 1u);
-                                } else {
-                                    umma_f16(d_c, ach, dph + ko, idesc, 1u);
-                                    umma_f16(d_s, ash, dmh + ko, idesc, 1u);
-                                }
+                                umma_f16_ts_c<true>(d_c, ka + 1 * mt, dpl + ko, idesc);
+                                umma_f16_ts_c<true>(d_s, ka + 3 * mt, dml + ko, idesc);
                             }
+                            umma_f16_ts_c<true>(d_c, ka + 1 * mt, dph + ko, idesc);
+                            umma_f16_ts_c<true>(d_s, ka + 3 * mt, dmh + ko, idesc);
+                            umma_f16_ts_c<true>(d_c, ka + 0 * mt, dpl + ko, idesc);
+                            umma_f16_ts_c<true>(d_s, ka + 2 * mt, dml + ko, idesc);
                         }
+                    }
+#pragma unroll
+                    for (int kk = 0; kk < NK_T; ++kk) {
+                        if (kk < nk) {
+                            const uint64_t ko = (uint64_t)(kk * 16);
+                            const uint32_t ka = tmem_a + kk * 8;
+                            umma_f16_ts_c<true>(d_c, ka + 0 * mt, dph + ko, idesc);
+                            umma_f16_ts_c<true>(d_s, ka + 2 * mt, dmh + ko, idesc);
+                        }
+                    }
                     umma_commit(&acc_full[gg]);
                 }
                 __syncwarp();
