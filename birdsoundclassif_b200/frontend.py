@@ -264,15 +264,32 @@ class File_Processor:
     def process_pcm(self, data: torch.Tensor, freq_accuracy=33.3, dt=0.003, overlap_spectro=0.2, w_pix=1024):
         """Same as process_file for PCM already in memory (host pinned or CUDA, int16/float32)."""
         n = data.shape[0]
-        if n > LONG_FILE_SAMPLES:
-            # prepare_dataset.py:187-225 splits such files and returns a list-of-lists that
-            # run_detection.py:47-53 cannot consume; pre-chunk recordings into <= 3401 s files.
-            raise ValueError(f"{self.filepath}: {n} samples > {LONG_FILE_SAMPLES}; split the recording first")
         plan = get_plan(freq_accuracy, dt, overlap_spectro, w_pix, self.FREQ, self.H_PIX, type(self).LOW_FREQ)
         for k, v in plan.const.items():
             setattr(self, k, v)
         dev = data if data.is_cuda else data.to(plan.device, non_blocking=True)
+        if n > LONG_FILE_SAMPLES:
+            return self._process_long(plan, dev, n)
         tiles, minmax = plan.run(dev)
         self.spectrogram_length, _, _ = plan.query(n)
         self.s_min_max = minmax
         return tiles[:, 0], None
+
+    def _process_long(self, plan, dev: torch.Tensor, n: int):
+        """prepare_dataset.py:187-225: a recording longer than max_l = 3401 s is cut into max_l-sample pieces and every
+        piece is processed as a file of its own (own STFT padding, own min/max, own tiling, own reflect-padded tail).
+        The reference round-trips the pieces through temp wav files; here they are the `files` of one batched
+        front-end call.  Returns the reference's ``(img_db, annotations)`` = ([tiles of piece 0, tiles of piece 1, ...],
+        []) -- a structure only prepare_dataset() consumes upstream (run_detection.py:47-53 crashes on it; this
+        package's run_detection handles it, see there).  An empty trailing piece (length an exact multiple of max_l)
+        is dropped; the reference writes an empty temp wav there and gets one meaningless image."""
+        L = LONG_FILE_SAMPLES
+        cuts = [min(n, k * L) for k in range(int(n / L) + 2)]
+        if cuts[-1] == cuts[-2]:
+            cuts.pop()
+        ch = 1 if dev.dim() == 1 else dev.shape[1]
+        tiles, tile_off, minmax = plan.run_batch(dev.reshape(-1), cuts, channels=ch)
+        self.piece_spectrogram_lengths = [plan.query(cuts[k + 1] - cuts[k])[0] for k in range(len(cuts) - 1)]
+        self.piece_samples = L
+        self.s_min_max = minmax
+        return [tiles[tile_off[k]:tile_off[k + 1], 0] for k in range(len(cuts) - 1)], []

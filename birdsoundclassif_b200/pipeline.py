@@ -37,7 +37,7 @@ import torch
 
 from . import postproc
 from .frontend import LONG_FILE_SAMPLES, STFT_CHUNK, derive_constants, get_plan
-from .run_detection import detect_tiles
+from .run_detection import detect_tiles, run_detection
 
 
 # ------------------------------------------------------------------ pure host arithmetic ------
@@ -96,6 +96,9 @@ def group_budget(index: int, max_group_tiles: int, first_group_tiles: int | None
     return min(max_group_tiles, first_group_tiles << min(index, 30))
 
 
+LONG_REASON = "long recording (> 3401 s): processed on its own after the batched groups"
+
+
 def plan_groups(infos, const, max_group_tiles: int, stft_chunk: int = STFT_CHUNK, first_group_tiles: int | None = None):
     """Contiguous groups of whole files in the given order, group i holding at most
     `group_budget(i, ...)` detector tiles (a single larger file forms its own group) and one channel count per group.
@@ -108,7 +111,7 @@ def plan_groups(infos, const, max_group_tiles: int, stft_chunk: int = STFT_CHUNK
         if info.sample_rate != 44100:
             rejected.append((info, f"sample rate {info.sample_rate} != 44100; resample first (no ffmpeg path)")); continue
         if info.n_samples > LONG_FILE_SAMPLES:
-            rejected.append((info, f"{info.n_samples} samples > {LONG_FILE_SAMPLES}; split the recording first")); continue
+            rejected.append((info, LONG_REASON)); continue
         fr, nt = count_frames_tiles(info.n_samples, const["HOP_LENGTH"], const["W_PIX"], const["HOP_SPECTRO"], stft_chunk)
         if cur is None or cur.channels != info.channels or \
                 (cur.files and cur.n_tiles + nt > group_budget(len(groups) - 1, max_group_tiles, first_group_tiles)):
@@ -130,8 +133,8 @@ def read_into(info: WavInfo, dst: np.ndarray) -> None:
 
 # ------------------------------------------------------------------------- the pipeline -------
 class DetectionPipeline:
-    """``run(paths)`` yields ``(path, output_dict)`` in input order, the dictionaries equal to
-    ``run_detection.run_detection(model, config, path, ...)``."""
+    """``run(paths)`` yields ``(path, output_dict)`` in input order (recordings longer than 3401 s last), the
+    dictionaries equal to ``run_detection.run_detection(model, config, path, ...)``."""
 
     def __init__(self, model, config, bird_dicts_path, min_score=0.5, bs=10, max_group_tiles=1024, readers=4, first_group_tiles=64,
                  freq_accuracy=33.3, dt=0.003, overlap_spectro=0.2, w_pix=1024):
@@ -140,6 +143,7 @@ class DetectionPipeline:
         self.model, self.config, self.min_score, self.bs = model, config, min_score, bs
         self.max_group_tiles, self.readers, self.first_group_tiles = int(max_group_tiles), int(readers), first_group_tiles
         self.fe_args = (freq_accuracy, dt, overlap_spectro, w_pix)
+        self.bird_dicts_path = bird_dicts_path
         self.const = derive_constants(*self.fe_args)
         with open(bird_dicts_path, "r") as f:
             birds = json.load(f)
@@ -176,13 +180,29 @@ class DetectionPipeline:
 
     def run(self, paths):
         plan = get_plan(*self.fe_args)
-        dev = plan.device
         infos = [probe_wav(p) for p in paths]
         groups, rejected = plan_groups(infos, self.const, self.max_group_tiles, first_group_tiles=self.first_group_tiles)
-        for info, why in rejected:
-            self.failed.append((info.path, why))
-        if not groups:
-            return
+        long_files = [info.path for info, why in rejected if why == LONG_REASON]
+        self.failed += [(info.path, why) for info, why in rejected if why != LONG_REASON]
+        if groups:
+            yield from self._run_groups(plan, groups)
+        # recordings longer than 3401 s: File_Processor cuts them into pieces that are one front-end batch already
+        # (frontend.File_Processor._process_long); they go through run_detection one at a time, after the groups
+        for path in long_files:
+            tm = {}
+            try:
+                output = run_detection(self.model, self.config, path, self.bird_dicts_path, min_score=self.min_score,
+                                       bs=self.bs, timings=tm)
+            except Exception as e:
+                self.failed.append((path, str(e))); continue
+            c = self.counts
+            c["files"] += 1; c["tiles"] += tm["tiles"]; c["frames"] += tm["frames"]; c["detections"] += tm["detections"]
+            c["t_front_us"] += int(tm["frontend_s"] * 1e6); c["t_model_us"] += int(tm["model_s"] * 1e6)
+            c["t_post_us"] += int(tm["post_s"] * 1e6)
+            yield path, output
+
+    def _run_groups(self, plan, groups):
+        dev = plan.device
         cap_tiles = max(g.n_tiles for g in groups)
         cap_vals = max(g.n_values for g in groups)
         n_buf = 2

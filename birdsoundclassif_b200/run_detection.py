@@ -19,6 +19,7 @@ from __future__ import annotations
 import json
 import sys
 import time
+import types
 
 import torch
 
@@ -84,14 +85,38 @@ def run_detection(model, config, wav_path, bird_dicts_path, min_score=0.5, bs=10
     img_db, _ = fp.process_file()
     if img_db is None:
         raise RuntimeError(f"{wav_path}: could not be loaded")      # the reference crashes at len(None), :47
-    t1 = time.perf_counter()
-    outputs = detect_tiles(model, img_db, min_score, bs)
-    t2 = time.perf_counter()
-
     with open(bird_dicts_path, "r") as f:
         birds_dict = json.load(f)
     birds_dict.update({"Non bird sound": 0})
     reverse_dict = {idx: name for name, idx in birds_dict.items()}
+    t1 = time.perf_counter()
+    if isinstance(img_db, list):
+        # Recording longer than 3401 s: the reference's File_Processor returns one image list per max_l-sample piece
+        # (prepare_dataset.py:187-225) and its run_detection cannot consume that.  Extension: every piece is detected
+        # and merged as a file of its own, its boxes are shifted to the recording's time axis (frames) and the
+        # per-species lists are concatenated in piece order.  Pieces do not overlap, so no NMS runs across them.
+        output, n_tiles, t_model = {}, 0, 0.0
+        for k, tiles in enumerate(img_db):
+            tm0 = time.perf_counter()
+            outs = detect_tiles(model, tiles, min_score, bs)
+            t_model += time.perf_counter() - tm0
+            piece = types.SimpleNamespace(W_PIX=fp.W_PIX, HOP_SPECTRO=fp.HOP_SPECTRO,
+                                          spectrogram_length=fp.piece_spectrogram_lengths[k])
+            shift = float(round(k * fp.piece_samples / fp.HOP_LENGTH))
+            for name, v in postproc.merge_to_output(piece, outs, config.num_classes, reverse_dict).items():
+                e = output.setdefault(name, {"bbox_coord": [], "scores": []})
+                e["bbox_coord"] += [[b[0] + shift, b[1], b[2] + shift, b[3]] for b in v["bbox_coord"]]
+                e["scores"] += v["scores"]
+            n_tiles += len(tiles)
+        output = {name: output[name] for name in sorted(output, key=lambda nm: birds_dict[nm])}     # classes ascending
+        if timings is not None:
+            t3 = time.perf_counter()
+            timings.update(frontend_s=t1 - t0, model_s=t_model, post_s=t3 - t1 - t_model, tiles=n_tiles,
+                           frames=int(sum(fp.piece_spectrogram_lengths)),
+                           detections=sum(len(v["scores"]) for v in output.values()))
+        return output
+    outputs = detect_tiles(model, img_db, min_score, bs)
+    t2 = time.perf_counter()
 
     # == merge_images + the dictionary comprehension of run_detection.py:69-77 (tested equal)
     output = postproc.merge_to_output(fp, outputs, config.num_classes, reverse_dict)

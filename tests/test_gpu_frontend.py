@@ -272,3 +272,33 @@ def test_fused_tiling_follows_transform_equals_plain(fe, monkeypatch):
         torch.cuda.synchronize()
         assert off == ref_off and torch.equal(mm, ref_mm) and torch.equal(tiles, ref_tiles)
     plain.close(); fused.close()
+
+
+def test_long_recording_is_cut_into_independent_pieces(fe, monkeypatch):
+    """prepare_dataset.py:187-225 at a small max_l: every max_l-sample piece is a file of its own (own padding, min/max,
+    tiling).  Checked against the oracle per piece and bit-for-bit against processing the pieces one by one."""
+    from oracle import frontend_oracle as fo
+    L = 2 * 44100
+    monkeypatch.setattr(fe, "LONG_FILE_SAMPLES", L)
+    pcm = synth.synth_pcm(5.3, 61)
+    fp = fe.File_Processor("long.wav")
+    img_db, ann = fp.process_pcm(torch.from_numpy(pcm).cuda())
+    assert isinstance(img_db, list) and len(img_db) == 3 and ann == []
+    assert (fp.W_PIX, fp.HOP_SPECTRO, fp.piece_samples) == (1024, 819, L)
+    for k, tiles in enumerate(img_db):
+        piece = pcm[k * L:(k + 1) * L]
+        r = fo.process(piece, fo.derive_params())
+        assert fp.piece_spectrogram_lengths[k] == r.spectrogram_length and len(tiles) == len(r.tiles)
+        assert_tiles_close(tiles.cpu().numpy(), np.stack(r.tiles), f"piece {k}")
+        _, alone = _gpu_tiles(fe, piece)
+        assert torch.equal(alone, tiles)
+    # a length that is an exact multiple of max_l: no empty trailing piece; exactly max_l is not a long file
+    img2, _ = fe.File_Processor("x.wav").process_pcm(torch.from_numpy(pcm[:2 * L]).cuda())
+    assert isinstance(img2, list) and len(img2) == 2
+    img3, none = fe.File_Processor("y.wav").process_pcm(torch.from_numpy(pcm[:L]).cuda())
+    assert not isinstance(img3, list) and none is None
+    # stereo
+    st = np.stack([pcm, synth.synth_pcm(5.3, 62)], axis=1)
+    img4, _ = fe.File_Processor("s.wav").process_pcm(torch.from_numpy(st).cuda())
+    _, alone = _gpu_tiles(fe, st[L:2 * L])
+    assert len(img4) == 3 and torch.equal(img4[1], alone)

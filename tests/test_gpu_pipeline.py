@@ -114,3 +114,46 @@ def test_pipelined_directory_equals_file_by_file(tmp_path, group_tiles):
     for k in ("files", "tiles", "detections", "frames"):
         assert c_pipe[k] == c_seq[k], k
     assert c_pipe["detections"] > 0
+
+
+def test_long_recording_detection(tmp_path, monkeypatch):
+    """A recording longer than max_l (made small here): run_detection detects each piece as a file of its own and
+    shifts its boxes to the recording's time axis; the pipelined driver defers such files to that path."""
+    from birdsoundclassif_b200 import frontend, nbm_detect, pipeline
+    from birdsoundclassif_b200 import run_detection as rd
+    L = 4 * 44100
+    monkeypatch.setattr(frontend, "LONG_FILE_SAMPLES", L)
+    monkeypatch.setattr(pipeline, "LONG_FILE_SAMPLES", L)
+    pcm = synth.synth_pcm(10.5, 810)
+    synth.write_wav(str(tmp_path / "a_long.wav"), pcm)
+    synth.write_wav(str(tmp_path / "b_short.wav"), synth.synth_pcm(3.0, 811))
+    pieces = tmp_path / "pieces"
+    pieces.mkdir()
+    for k in range(3):
+        synth.write_wav(str(pieces / f"p{k}.wav"), pcm[k * L:(k + 1) * L])
+    bird = str(tmp_path / "bird_dict.json")
+    with open(bird, "w") as f:
+        json.dump({f"Species {i}": i for i in range(1, 151)}, f)
+    args = synth.default_args("cuda")
+    model = StandInDetector(args, backend="nbm").cuda()
+    tm = {}
+    out = rd.run_detection(model, args, str(tmp_path / "a_long.wav"), bird, min_score=0.05, bs=4, timings=tm)
+    want = {}
+    for k in range(3):
+        shift = float(round(k * L / 132))
+        for name, v in rd.run_detection(model, args, str(pieces / f"p{k}.wav"), bird, min_score=0.05, bs=4).items():
+            e = want.setdefault(name, {"bbox_coord": [], "scores": []})
+            e["bbox_coord"] += [[b[0] + shift, b[1], b[2] + shift, b[3]] for b in v["bbox_coord"]]
+            e["scores"] += v["scores"]
+    assert out.keys() == want.keys() and all(out[k] == want[k] for k in out) and tm["detections"] > 0
+    ids = [int(n.split()[1]) for n in out]
+    assert ids == sorted(ids)
+    texts = {}
+    for pipelined in (False, True):
+        for f in glob.glob(str(tmp_path / "*.txt")):
+            os.remove(f)
+        c = nbm_detect.detect_directory(model, args, str(tmp_path), bird, 0.05, 4, verbose=False, pipelined=pipelined)
+        assert c["files"] == 2
+        texts[pipelined] = {os.path.basename(f): open(f).read() for f in sorted(glob.glob(str(tmp_path / "*.txt")))}
+    assert texts[True] == texts[False] and set(texts[True]) == {"a_long.txt", "b_short.txt"}
+    assert texts[True]["a_long.txt"] == str(out)

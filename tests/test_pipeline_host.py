@@ -77,7 +77,7 @@ def test_plan_groups_channels_and_rejects():
     assert [g.channels for g in groups] == [1, 2, 1]
     assert groups[1].n_values == 2 * 2 * 3 * 44100
     assert [r[0].path for r in rejected] == ["f005.wav", "f006.wav", "long.wav"]
-    assert "48000" in rejected[0][1] and "split the recording" in rejected[2][1]
+    assert "48000" in rejected[0][1] and rejected[2][1] == pl.LONG_REASON
 
 
 def test_probe_and_read_into(tmp_path):
