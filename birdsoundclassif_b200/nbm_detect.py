@@ -21,10 +21,12 @@ from . import sharding
 
 
 def detect_directory(model, model_args, audio_dir, bird_dict="bird_dict.json", min_score=0.2, bs=4,
-                     rank=0, world=1, skip_done=False, verbose=True, pipelined=True, group_tiles=1024) -> dict:
+                     rank=0, world=1, skip_done=False, verbose=True, pipelined=True, group_tiles=1024,
+                     json_sidecar=False) -> dict:
     """This rank's share of ``audio_dir/*.wav`` -> sibling ``.txt`` files (nbm_detect.py:23-29).  ``pipelined``: wav
     decoding, the batched front-end and the detector overlap across files (pipeline.DetectionPipeline); otherwise the
-    reference's one-file-at-a-time loop through ``run_detection``.  Same outputs either way."""
+    reference's one-file-at-a-time loop through ``run_detection``.  Same outputs either way.  ``json_sidecar``: also
+    write ``<wav>.json`` (the same dictionary as JSON; the ``.txt`` is ``str(dict)``, readable only by ``ast.literal_eval``)."""
     files = sharding.shard_files(glob.glob(os.path.join(audio_dir, "*.wav")), rank, world)
     if skip_done:
         files = [f for f in files if not os.path.exists(f.replace(".wav", ".txt"))]
@@ -34,6 +36,9 @@ def detect_directory(model, model_args, audio_dir, bird_dict="bird_dict.json", m
     def done(wav_path, output):
         with open(wav_path.replace(".wav", ".txt"), "w") as f:
             f.write(str(output))
+        if json_sidecar:
+            with open(wav_path.replace(".wav", ".json"), "w") as f:
+                json.dump(output, f)
         if verbose:
             print(f"~~~~~ File {os.path.basename(wav_path).replace('.wav', '')} done ~~~~~")
 
@@ -72,6 +77,7 @@ def main(argv=None):
     parser.add_argument("--batch", dest="bs", type=int, default=4)
     parser.add_argument("--bird_dict", type=str, default="bird_dict.json")
     parser.add_argument("--skip_done", action="store_true", help="skip wavs that already have a .txt")
+    parser.add_argument("--json", action="store_true", help="also write <wav>.json next to the reference's <wav>.txt")
     parser.add_argument("--no_pipeline", action="store_true", help="one file at a time, as the reference loops")
     parser.add_argument("--group_tiles", type=int, default=1024, help="detector tiles per front-end batch (pipelined)")
     args = parser.parse_args(argv)
@@ -91,7 +97,8 @@ def main(argv=None):
     rd.patch_reference()
     rd.accelerate_model(model)
     counts = detect_directory(model, model_args, args.audio_dirp, args.bird_dict, args.min_score, args.bs,
-                              rank, world, args.skip_done, pipelined=not args.no_pipeline, group_tiles=args.group_tiles)
+                              rank, world, args.skip_done, pipelined=not args.no_pipeline, group_tiles=args.group_tiles,
+                              json_sidecar=args.json)
     per_rank = sharding.gather_counts(counts, device=torch.device("cuda", local))
     if rank == 0:
         print(json.dumps({"per_rank": per_rank, "totals": sharding.totals(per_rank)}))

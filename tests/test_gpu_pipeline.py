@@ -152,8 +152,12 @@ def test_long_recording_detection(tmp_path, monkeypatch):
     for pipelined in (False, True):
         for f in glob.glob(str(tmp_path / "*.txt")):
             os.remove(f)
-        c = nbm_detect.detect_directory(model, args, str(tmp_path), bird, 0.05, 4, verbose=False, pipelined=pipelined)
+        c = nbm_detect.detect_directory(model, args, str(tmp_path), bird, 0.05, 4, verbose=False, pipelined=pipelined,
+                                        json_sidecar=True)
         assert c["files"] == 2
+        import ast
+        for f in glob.glob(str(tmp_path / "*.txt")):                 # the side-car holds the same dictionary
+            assert json.load(open(f.replace(".txt", ".json"))) == ast.literal_eval(open(f).read())
         texts[pipelined] = {os.path.basename(f): open(f).read() for f in sorted(glob.glob(str(tmp_path / "*.txt")))}
     assert texts[True] == texts[False] and set(texts[True]) == {"a_long.txt", "b_short.txt"}
     assert texts[True]["a_long.txt"] == str(out)
