@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--seconds", type=float, default=60.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-clips", type=int, default=0, help="clips in the CPU baseline sample (0 = 2 per core)")
+    ap.add_argument("--cpu-clips", type=int, default=0, help="clips in the CPU baseline sample (0 = 8 per core; 4 per core and step for --impl reference)")
     return ap.parse_args()
 
 
@@ -173,7 +173,7 @@ def run_reference(a):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    clips = a.cpu_clips or 2 * cores
+    clips = a.cpu_clips or 4 * cores
     per_step = []
     for i in range(a.warmup + a.steps):
         v, wall, _ = cpu_reference(a.seconds, clips, cores)
@@ -370,7 +370,7 @@ def run_b200(a):
                                "per-file (s_min, s_max) read back"}
     if not a.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        clips = a.cpu_clips or 2 * cores
+        clips = a.cpu_clips or 8 * cores
         v, wall, per = cpu_reference(a.seconds, clips, cores)
         line["cpu_baseline"] = {"value": v, "unit": "audio-hours/s", "cores": cores, "kind": "port",
                                 "sample": f"{clips} of the {a.seconds:g} s clips, one process per core, "
