@@ -368,7 +368,7 @@ def run_b200(a):
                        "note": "FrontendPlan.run_batch_from_host: pinned host PCM16 -> H2D in 64-file chunks on a side stream, "
                                "overlapped with the front-end; tiles stay on the device for the detector; "
                                "per-file (s_min, s_max) read back"}
-    if not a.no_cpu_baseline:
+    if not a.no_cpu_baseline and world == 1:          # rank 0 at N = 1 only: at N > 1 the ranks share the host cores
         cores = os.cpu_count() or 1
         clips = a.cpu_clips or 8 * cores
         v, wall, per = cpu_reference(a.seconds, clips, cores)
