@@ -24,7 +24,9 @@ data-dependent and cannot be captured unmodified; the north star keeps that netw
 from __future__ import annotations
 
 import json
+import os
 import queue
+import struct
 import threading
 import time
 import wave
@@ -61,13 +63,33 @@ class WavInfo:
     error: str | None = None
 
 
+def _data_chunk(path: str):
+    """(offset, bytes) of the RIFF 'data' chunk as the header states them."""
+    with open(path, "rb") as f:
+        head = f.read(12)
+        if len(head) < 12 or head[:4] != b"RIFF" or head[8:12] != b"WAVE":
+            raise ValueError("not a RIFF/WAVE file")
+        while True:
+            h = f.read(8)
+            if len(h) < 8:
+                raise ValueError("no data chunk")
+            size = struct.unpack("<I", h[4:])[0]
+            if h[:4] == b"data":
+                return f.tell(), size
+            f.seek(size + (size & 1), os.SEEK_CUR)
+
+
 def probe_wav(path: str) -> WavInfo:
-    """Header only (no sample data is read)."""
+    """Header only (no sample data is read).  n_samples counts the whole frames actually present: a truncated file is
+    processed up to where it ends, as the one-file path (synth.read_wav_pcm16) and libsndfile do."""
     try:
         with wave.open(path, "rb") as w:
             if w.getsampwidth() != 2 or w.getcomptype() != "NONE":
                 return WavInfo(path, error="only uncompressed PCM16 wav is supported")
-            return WavInfo(path, w.getnframes(), w.getnchannels(), w.getframerate())
+            ch, sr, n = w.getnchannels(), w.getframerate(), w.getnframes()
+        off, _ = _data_chunk(path)
+        held = max(0, os.path.getsize(path) - off) // (2 * ch)
+        return WavInfo(path, min(n, held), ch, sr)
     except Exception as e:          # the reference prints 'File loading failed' and returns None (prepare_dataset.py:163-165)
         return WavInfo(path, error=f"File loading failed ({e})")
 

@@ -111,7 +111,9 @@ def read_wav_pcm16(path: str) -> tuple[np.ndarray, int]:
         if w.getsampwidth() != 2 or w.getcomptype() != "NONE":
             raise ValueError(f"{path}: only uncompressed PCM16 wav is supported")
         sr, ch, n = w.getframerate(), w.getnchannels(), w.getnframes()
-        pcm = np.frombuffer(w.readframes(n), dtype="<i2")
+        raw = w.readframes(n)
+    raw = raw[:len(raw) - len(raw) % (2 * ch)]          # a truncated file yields the whole frames it holds (as libsndfile does)
+    pcm = np.frombuffer(raw, dtype="<i2")
     return (pcm if ch == 1 else pcm.reshape(-1, ch)), sr
 
 

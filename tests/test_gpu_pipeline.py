@@ -93,6 +93,8 @@ def test_pipelined_directory_equals_file_by_file(tmp_path, group_tiles):
     for i in (0, 1):
         st = np.stack([synth.synth_pcm(5.0 + i, 720 + i), synth.synth_pcm(5.0 + i, 730 + i)], axis=1)
         synth.write_wav(str(d / f"rec_1{i}_stereo.wav"), st)
+    raw = open(str(d / "rec_02.wav"), "rb").read()
+    (d / "rec_05_truncated.wav").write_bytes(raw[:len(raw) // 3 + 1])      # processed up to where it ends, by both drivers
     (d / "rec_20_broken.wav").write_bytes(b"RIFFjunk")
     synth.write_wav(str(d / "rec_21_48k.wav"), synth.synth_pcm(1.0, 740), sample_rate=48000)
     bird = str(d / "bird_dict.json")
@@ -110,7 +112,7 @@ def test_pipelined_directory_equals_file_by_file(tmp_path, group_tiles):
 
     c_seq, t_seq = run(False)
     c_pipe, t_pipe = run(True)
-    assert len(t_seq) == 9 and t_pipe == t_seq
+    assert len(t_seq) == 10 and t_pipe == t_seq
     for k in ("files", "tiles", "detections", "frames"):
         assert c_pipe[k] == c_seq[k], k
     assert c_pipe["detections"] > 0
