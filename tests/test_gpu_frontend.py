@@ -302,3 +302,54 @@ def test_long_recording_is_cut_into_independent_pieces(fe, monkeypatch):
     img4, _ = fe.File_Processor("s.wav").process_pcm(torch.from_numpy(st).cuda())
     _, alone = _gpu_tiles(fe, st[L:2 * L])
     assert len(img4) == 3 and torch.equal(img4[1], alone)
+
+
+def test_full_size_batch_properties(fe):
+    """BASELINE configs[1] at full size (1024 x 60 s clips in one call, 25 600 tiles = 39 GB) through size-independent
+    properties: per-file range exactly [0, 1]; overlap columns of consecutive tiles identical; reflect-padded tail
+    columns exact copies; identical clips give identical tiles wherever they sit in the batch; spot files equal their
+    single-file run bit for bit (which the oracle tests pin); two runs give the same checksum of checksums."""
+    torch.cuda.empty_cache()
+    free, _ = torch.cuda.mem_get_info()
+    if free < 90e9:
+        pytest.skip("needs ~80 GB of device memory (39 GB of tiles, 31 GB of workspace, comparison temporaries)")
+    from oracle import frontend_oracle as fo
+    plan = fe.get_plan()
+    n, clips, distinct = 2_646_000, 1024, 8
+    base = [torch.from_numpy(synth.synth_pcm(60.0, 500 + i)[:n]).cuda() for i in range(distinct)]
+    order = np.random.default_rng(3).integers(0, distinct, clips)
+    pcm = torch.cat([base[j] for j in order])
+    offs = (np.arange(clips + 1) * n).tolist()
+    tiles, tile_off, minmax = plan.run_batch(pcm, offs)
+    torch.cuda.synchronize()
+    assert tile_off[-1] == 25 * clips and tiles.shape == (25 * clips, 1, 375, 1024)
+    t = tiles.view(clips, 25, 375, 1024)
+    assert torch.all(t.amin(dim=(1, 2, 3)) == 0.0) and torch.all(t.amax(dim=(1, 2, 3)) == 1.0)
+    # overlap columns (tile k cols 819.. == tile k+1 cols ..204), all files at once, in slabs to bound temporaries
+    for f0 in range(0, clips, 128):
+        a = t[f0:f0 + 128, :-2, :, 819:]                # tiles 0..22 (tile 23 -> 24 is the partial one)
+        b = t[f0:f0 + 128, 1:-1, :, :205]
+        assert torch.equal(a, b)
+    last_w = 20046 - 24 * 819
+    src = torch.tensor([fo.reflect_index(j, last_w) for j in range(1024)], device="cuda")
+    for f0 in range(0, clips, 128):
+        last = t[f0:f0 + 128, -1]
+        assert torch.equal(last, last[..., src])
+    # identical clips -> identical tiles and min/max, whatever their position (and 16-byte phase) in the batch
+    first = {}
+    for f, j in enumerate(order.tolist()):
+        if j not in first:
+            first[j] = f
+        elif f % 37 == 0:
+            assert torch.equal(t[f], t[first[j]]) and torch.equal(minmax[f], minmax[first[j]])
+    for j in (0, 5):
+        single, mm = plan.run(base[j])
+        assert torch.equal(single.view(25, 375, 1024), t[first[j]]) and torch.equal(mm, minmax[first[j]])
+    def checksum(x):
+        return x.view(torch.int32).view(clips, -1).sum(dim=1, dtype=torch.int64).sum().item()
+    c1 = checksum(tiles)
+    tiles2, _, _ = plan.run_batch(pcm, offs, out=tiles)
+    torch.cuda.synchronize()
+    assert checksum(tiles2) == c1
+    del tiles, tiles2, t, pcm
+    torch.cuda.empty_cache()
