@@ -27,5 +27,30 @@ def pipe(**kw):
     return time.perf_counter() - t, {k: v / 1e6 for k, v in p.counts.items() if k.startswith("t_")}
 seq()
 print("seq", seq())
-for kw in (dict(), dict(readers=1), dict(max_group_tiles=245, first_group_tiles=None), dict(max_group_tiles=4096), dict(readers=1, max_group_tiles=100000, first_group_tiles=None)):
-    print("pipe", kw, pipe(**kw))
+print("pipe one group", pipe(readers=1, max_group_tiles=100000, first_group_tiles=None))
+from concurrent.futures import ThreadPoolExecutor
+pool = ThreadPoolExecutor(4); list(pool.map(lambda i: time.sleep(0.05), range(4)))
+print("seq with 4 idle pool threads", seq())
+pool.shutdown()
+pin = [torch.empty(320_000_000, dtype=torch.int16).pin_memory() for _ in range(3)]
+print("seq with 1.9 GB pinned held", seq())
+del pin
+big = torch.empty((2940 * 2, 1, 375, 1024), device="cuda")
+print("seq with 9 GB device buffer held", seq())
+del big
+# the pipeline's detection phase alone, on tiles produced up front (no reader, no second stream)
+from birdsoundclassif_b200.frontend import File_Processor
+from birdsoundclassif_b200 import postproc
+from types import SimpleNamespace
+fps = []
+for f in files:
+    fp = File_Processor(f); tiles, _ = fp.process_file(); fps.append((fp, tiles))
+torch.cuda.synchronize()
+rev = {i: f"S{i}" for i in range(151)}
+t = time.perf_counter(); tm = 0.0
+for fp, tiles in fps:
+    t0 = time.perf_counter()
+    outs = rd.detect_tiles(model, tiles, 0.2, 4)
+    tm += time.perf_counter() - t0
+    postproc.merge_to_output(fp, outs, 150, rev)
+print("detector + merge over resident tiles", time.perf_counter() - t, "model", tm)
