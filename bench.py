@@ -43,6 +43,10 @@ def parse():
     ap.add_argument("--seconds", type=float, default=60.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-detect", action="store_true", help="skip the nbm_detect leg (audio-h/s through the real detector)")
+    ap.add_argument("--detect-files", type=int, default=2, help="ten-minute wavs per GPU in the detect leg's night slice")
+    ap.add_argument("--detect-ref-files", type=int, default=16, help="cfg0 files the unpatched reference flow is timed on (N = 1)")
+    ap.add_argument("--no-detect-reference", action="store_true")
     ap.add_argument("--cpu-clips", type=int, default=0, help="clips in the CPU baseline sample (0 = 8 per core; 4 per core and step for --impl reference)")
     return ap.parse_args()
 
@@ -309,6 +313,22 @@ def run_b200(a):
         parity = {"clip": 0, "max_abs_err_norm": float(err.max()), "frac_gt_1e-4": float((err > 1e-4).mean()),
                   "rms": float(np.sqrt((err ** 2).mean()))}
 
+    # ---- audio-hours/s THROUGH nbm_detect (wav files -> reference CNN -> .txt), files sharded over the ranks ----
+    detect = None
+    if not a.no_detect:
+        n_tiles_total, n_out_bytes, n_in_bytes = int(tile_off[-1]), tiles.numel() * 4, pcm.numel() * 2
+        del tiles, pcm
+        plan._ws = None
+        torch.cuda.empty_cache()
+        import bench_detect
+        try:
+            detect = bench_detect.run(a, rank, world, local, dist)
+        except Exception as e:                              # the headline must still be printed
+            import traceback
+            detect = {"error": f"{type(e).__name__}: {e}", "trace": traceback.format_exc()[-1500:]}
+    else:
+        n_tiles_total, n_out_bytes, n_in_bytes = int(tile_off[-1]), tiles.numel() * 4, pcm.numel() * 2
+
     # ---- gather: max time over ranks, totals (NCCL all_gather of a small vector) ----------------
     stats = torch.tensor([ms, frames, audio_hours * 1e6, stft_ms, tile_ms, e2e[0] if e2e else 0.0,
                           kern_ms["anchor"], kern_ms["minmax"]], dtype=torch.float64, device=dev)
@@ -329,7 +349,7 @@ def run_b200(a):
     stft_per_launch_ms = float(allst[0, 3]) / max(runs, 1)
     achieved = frames * BYTES_PER_FRAME / (stft_per_launch_ms / 1e3) / 1e9
     tile_ms = float(allst[0, 4]) / max(runs, 1)
-    tile_bytes = frames * 375 * 4 + tiles.numel() * 4
+    tile_bytes = frames * 375 * 4 + n_out_bytes
     tile_gbs = tile_bytes / (tile_ms / 1e3) / 1e9 if tile_ms > 0 else 0.0
     line = {
         "metric": "audio-hours/sec", "value": value, "unit": "audio-hours/s", "n_gpus": world, "steps": a.steps,
@@ -338,9 +358,9 @@ def run_b200(a):
         "config": {"workload": f"front-end alone, {a.clips} x {a.seconds:g} s mono 44.1 kHz PCM16 clips per GPU "
                                "(BASELINE configs[1]): STFT 1324/132 Hann -> dB -> 375-bin crop -> file min/max -> "
                                "1024x375 tiles @ hop 819",
-                   "clips_per_gpu": a.clips, "frames_per_gpu": frames, "tiles_per_gpu": int(tile_off[-1]),
+                   "clips_per_gpu": a.clips, "frames_per_gpu": frames, "tiles_per_gpu": n_tiles_total,
                    "l2": "inputs (%.1f GB) and outputs (%.1f GB) per step exceed L2 (126 MB); no flush needed"
-                         % (pcm.numel() * 2 / 1e9, tiles.numel() * 4 / 1e9),
+                         % (n_in_bytes / 1e9, n_out_bytes / 1e9),
                    "sharding": "files sharded across ranks, no data-path collective"},
         "roofline": {"bound": "hbm", "kernel": "slide_ws_kernel" if plan.impl == "tcgen05" else "stft_db_kernel",
                      "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -368,6 +388,8 @@ def run_b200(a):
                        "note": "FrontendPlan.run_batch_from_host: pinned host PCM16 -> H2D in 64-file chunks on a side stream, "
                                "overlapped with the front-end; tiles stay on the device for the detector; "
                                "per-file (s_min, s_max) read back"}
+    if detect is not None:
+        line["detect"] = detect
     if not a.no_cpu_baseline and world == 1:          # rank 0 at N = 1 only: at N > 1 the ranks share the host cores
         cores = os.cpu_count() or 1
         clips = a.cpu_clips or 8 * cores

@@ -1,0 +1,164 @@
+"""`detect` leg of bench.py: audio-hours/s THROUGH ``nbm_detect`` (BASELINE.json metric, first half).
+
+wav files on disk -> ``birdsoundclassif_b200.nbm_detect.detect_directory`` (reader threads, batched front-end,
+the reference's own CNN with the library-backed post-processing, per-file merge) -> ``.txt`` files, wall clock
+from the first file read to the last ``.txt`` written, files sharded over the ranks, max over ranks.
+
+  * ``cfg0``  BASELINE configs[0]: 16 synthetic 30 s mono wavs, ONE directory sharded over all ranks (strong).
+  * ``night`` BASELINE configs[2]/[3] shape: ten-minute wavs (an 8-hour night is 48 of them; configs[3] shards
+              10 000 of them), ``--detect-files`` per GPU (weak: every rank brings its own files).
+  * ``reference`` (N = 1 only): the reference's UNPATCHED flow on the same GPU and the same cfg0 files -- its
+              ``run_detection`` (CPU front-end through the librosa restatement of oracle/ref_shims.py, its own
+              ProposalLayer / ROIPooling / FastRCNN tail / merge_images Python loops) -- as the baseline.
+
+The detector network is the reference's (``nbm_model.nets``), found at $NBM_REFERENCE_ROOT, /root/reference or
+the oracle/_ref copy (oracle/build_ref.py), with a seeded stand-in checkpoint (the shipped one is a Git-LFS
+stub): ``synth.write_standin_checkpoint(seed=0, sharpen=400)``.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+
+
+def find_reference_root():
+    for cand in (os.environ.get("NBM_REFERENCE_ROOT"), "/root/reference", os.path.join(ROOT, "oracle", "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "nbm_model", "nets", "nbm_model.py")):
+            return cand
+    return None
+
+
+def _write_files(dirpath, n_files, seconds, seed0, distinct=4):
+    """n_files wavs of `seconds` s; `distinct` different synthetic recordings, the rest circular shifts of them."""
+    from birdsoundclassif_b200 import synth
+    os.makedirs(dirpath, exist_ok=True)
+    base = [synth.synth_pcm(seconds, seed0 + i) for i in range(min(distinct, n_files))]
+    paths = []
+    for i in range(n_files):
+        pcm = base[i % len(base)]
+        if i >= len(base):
+            pcm = np.roll(pcm, (i // len(base)) * 44100 * 7)
+        paths.append(synth.write_wav(os.path.join(dirpath, f"rec_{i:04d}.wav"), pcm))
+    return paths
+
+
+def _rm_outputs(dirpath):
+    for f in os.listdir(dirpath):
+        if f.endswith(".txt"):
+            os.remove(os.path.join(dirpath, f))
+
+
+def run(a, rank, world, local, dist):
+    """Returns the `detect` dict on rank 0 (None elsewhere)."""
+    import torch
+    ref_root = find_reference_root()
+    if ref_root is None:
+        return {"unavailable": "no reference checkout (nbm_model.nets) on this machine"} if rank == 0 else None
+    for p in (ref_root,):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from birdsoundclassif_b200 import nbm_detect, run_detection as rd, sharding, synth
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    base = os.environ.get("NBM_BENCH_TMP") or ("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir())
+    work = os.path.join(base, f"nbm_bench_{os.environ.get('MASTER_PORT', '0')}_{os.getppid() if world > 1 else os.getpid()}")
+    bird_dict = os.path.join(ref_root, "bird_dict.json")
+    ckpt = os.path.join(work, "model_weights")
+    cfg0_dir = os.path.join(work, "cfg0")
+    night_dir = os.path.join(work, f"night_r{rank}")
+    out = {}
+    try:
+        if rank == 0:
+            os.makedirs(work, exist_ok=True)
+            synth.write_standin_checkpoint(ckpt, seed=0, sharpen=400.0)
+            _write_files(cfg0_dir, 16, 30.0, 1000 * 0)
+        barrier()
+        _write_files(night_dir, a.detect_files, 600.0, 1000 * 2 + 10 * rank, distinct=2)
+        model, margs = rd.load_model(ckpt)
+        rd.patch_reference()
+        rd.accelerate_model(model)
+        dev = torch.device("cuda", local)
+
+        def leg(dirpath, r, w, repeats):
+            best = None
+            for _ in range(repeats):
+                _rm_outputs(dirpath)
+                barrier()
+                c = nbm_detect.detect_directory(model, margs, dirpath, bird_dict, min_score=0.2, bs=4, rank=r, world=w,
+                                                verbose=False)
+                per_rank = sharding.gather_counts(c, device=dev)
+                wall = max(x["t_wall_us"] for x in per_rank) / 1e6
+                if best is None or wall < best[0]:
+                    best = (wall, per_rank)
+            return best
+
+        # warm-up: cuDNN heuristics, the allocator's pools, the front-end plan
+        leg(cfg0_dir, rank, world, 1)
+        wall, per_rank = leg(cfg0_dir, rank, world, 2)
+        tot = sharding.totals(per_rank)
+        hours = 16 * 30.0 / 3600.0
+        assert tot["files"] == 16
+        out["cfg0"] = {"workload": "BASELINE configs[0]: 16 x 30 s wavs -> .txt, one directory sharded over the ranks, "
+                                   "min_score 0.2, bs 4, reference CNN + stand-in checkpoint",
+                       "audio_hours_per_s": hours / wall, "wall_s": wall, "files": tot["files"], "tiles": tot["tiles"],
+                       "detections": tot["detections"], "scaling": "strong",
+                       "stage_s_sum_over_ranks": {k: sum(x[k] for x in per_rank) / 1e6 for k in ("t_front_us", "t_model_us", "t_post_us")}}
+        wall, per_rank = leg(night_dir, 0, 1, 1)
+        tot = sharding.totals(per_rank)
+        hours = tot["files"] * 600.0 / 3600.0
+        out["night"] = {"workload": f"BASELINE configs[2]/[3] shape: {a.detect_files} x 10-min wavs per GPU -> .txt, "
+                                    "min_score 0.2, bs 4, reference CNN + stand-in checkpoint",
+                        "audio_hours_per_s": hours / wall, "wall_s": wall, "files": tot["files"], "tiles": tot["tiles"],
+                        "detections": tot["detections"], "scaling": "weak",
+                        "stage_s_sum_over_ranks": {k: sum(x[k] for x in per_rank) / 1e6 for k in ("t_front_us", "t_model_us", "t_post_us")},
+                        "per_rank_wall_s": [x["t_wall_us"] / 1e6 for x in per_rank]}
+        rd.unpatch_reference()
+        if world == 1 and not a.no_detect_reference:
+            out["reference"] = _reference_flow(ckpt, cfg0_dir, bird_dict, a.detect_ref_files)
+        barrier()
+    finally:
+        if world > 1:
+            try:
+                dist.barrier()
+            except Exception:
+                pass
+        shutil.rmtree(night_dir, ignore_errors=True)
+        if rank == 0:
+            shutil.rmtree(work, ignore_errors=True)
+    return out if rank == 0 else None
+
+
+def _reference_flow(ckpt, cfg0_dir, bird_dict, n_files):
+    """The reference's unpatched nbm_detect loop (nbm_detect.py:23-29) on this GPU, first `n_files` of cfg0."""
+    import glob
+    import torch
+    from oracle import ref_shims            # the librosa / matplotlib stand-ins the reference's imports need here
+    ref_shims.install()
+    ref_rd = ref_shims.ref("nbm_model.run_detection")
+    model, margs = ref_rd.load_model(ckpt)
+    files = sorted(glob.glob(os.path.join(cfg0_dir, "*.wav")))[:n_files]
+    ref_rd.run_detection(model, margs, files[0], bird_dicts_path=bird_dict, min_score=0.2, bs=4)     # warm-up
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    n_det = 0
+    for w in files:
+        o = ref_rd.run_detection(model, margs, w, bird_dicts_path=bird_dict, min_score=0.2, bs=4)
+        with open(w.replace(".wav", ".ref.txt"), "w") as f:
+            f.write(str(o))
+        n_det += sum(len(v["scores"]) for v in o.values())
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t
+    return {"workload": f"the reference's own run_detection loop, unpatched, same GPU, {len(files)} of the cfg0 files "
+                        "(CPU front-end = librosa restatement, 1 host thread, as upstream)",
+            "audio_hours_per_s": len(files) * 30.0 / 3600.0 / wall, "wall_s": wall, "files": len(files), "detections": n_det}

@@ -89,11 +89,9 @@ def main(argv=None):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
     try:
-        from nbm_model.run_detection import load_model      # the reference's loader, unchanged
+        model, model_args = rd.load_model(args.model_dirp)      # the reference's network classes, unchanged
     except ImportError as e:
-        raise SystemExit("nbm_model (the reference checkout) must be importable: it provides the detector "
-                         f"network and load_model ({e})")
-    model, model_args = load_model(args.model_dirp)
+        raise SystemExit(str(e))
     rd.patch_reference()
     rd.accelerate_model(model)
     counts = detect_directory(model, model_args, args.audio_dirp, args.bird_dict, args.min_score, args.bs,

@@ -339,9 +339,10 @@ class ROIPooling(nn.Module):
     (roi_pool_out [B,R,C,ph,pw], roi_pe_out [B,R,C,ph,pw], level assignment numpy [B,R]), one kernel
     launch instead of a Python loop over batch x RoIs with .item() syncs.  Holds no parameters."""
 
-    def __init__(self, config):
+    def __init__(self, config, want_levels=True):
         super().__init__()
         self.config = config
+        self.want_levels = want_levels     # False: skip the device-to-host copy of the level table (a stream sync)
         self._pe = {}
 
     def _tables(self, device):
@@ -373,4 +374,4 @@ class ROIPooling(nn.Module):
         _lib.check(_lib.lib().nbm_roi_pool(r.data_ptr(), B, R, ptrs, hs, ws, n_layers, Cc, ph, pw, int(cfg.img_height),
                                            int(cfg.img_width), pe_f.data_ptr(), pe_t.data_ptr(), pool.data_ptr(),
                                            pe.data_ptr(), lvl.data_ptr(), _stream()), "nbm_roi_pool")
-        return pool, pe, lvl.cpu().numpy()
+        return pool, pe, (lvl.cpu().numpy() if self.want_levels else lvl)

@@ -17,6 +17,7 @@ image) of ``{'1'..str(num_classes): {'bbox_coord': [n,4], 'scores': [1,n]}}``.
 from __future__ import annotations
 
 import json
+import os
 import sys
 import time
 import types
@@ -27,12 +28,17 @@ from . import postproc
 from .frontend import File_Processor
 
 
+_PATCHED: dict = {}     # (module name, symbol) -> the reference's original object
+
+
 def patch_reference() -> list[str]:
     """Monkey-patch the reference modules (when importable as ``nbm_model.*``) so its unchanged
     model code calls libnbm_b200: ``nms`` and ``bbox_reg_to_coord`` are imported BY NAME into
     ``nbm_model.nets.layers`` (layers.py:4) and ``nbm_model.run_detection`` (run_detection.py:18).
-    Returns the list of patched symbols."""
+    Returns the list of patched symbols; ``unpatch_reference()`` restores the originals."""
     done = []
+    repl = {"nms": postproc.nms, "bbox_reg_to_coord": postproc.bbox_reg_to_coord,
+            "merge_images": postproc.merge_images, "File_Processor": File_Processor}
     for modname, names in (("nbm_model.nets.layers", ("nms", "bbox_reg_to_coord")),
                            ("nbm_model.nets.util.nets_utils", ("nms", "bbox_reg_to_coord")),
                            ("nbm_model.run_detection", ("nms", "merge_images", "File_Processor"))):
@@ -41,16 +47,41 @@ def patch_reference() -> list[str]:
             continue
         for n in names:
             if hasattr(mod, n):
-                setattr(mod, n, {"nms": postproc.nms, "bbox_reg_to_coord": postproc.bbox_reg_to_coord,
-                                 "merge_images": postproc.merge_images, "File_Processor": File_Processor}[n])
+                if getattr(mod, n) is not repl[n]:
+                    _PATCHED.setdefault((modname, n), getattr(mod, n))
+                    setattr(mod, n, repl[n])
                 done.append(f"{modname}.{n}")
     return done
 
 
-def accelerate_model(model):
+def unpatch_reference() -> None:
+    """Put the reference's own symbols back (tests compare the two in one process)."""
+    for (modname, n), orig in _PATCHED.items():
+        mod = sys.modules.get(modname)
+        if mod is not None:
+            setattr(mod, n, orig)
+    _PATCHED.clear()
+
+
+def _fast_rcnn_forward(self, conv_out, rois, nms_thresh=0.3, min_score=0.5, training=None):
+    """FastRCNN.forward (layers.py:668-778) with the inference branch (:688-778: argmax, class delta gather,
+    decode, clamp, sort, drop class 0, NMS, per-class NMS + ``> min_score``) done by one kernel launch
+    (``nbm_final_detections``) instead of a Python loop over images x 150 classes.  The network part
+    (roi_pooling -> rcnn, :674-676) and the training return (:678-681) are the reference's."""
+    roi_pool_out, roi_pe_out, _ = self.roi_pooling(rois, conv_out)
+    bbox_reg, bbox_classes = self.rcnn(roi_pool_out, roi_pe_out)
+    if training is None:
+        training = self.training
+    if training:
+        return bbox_reg, bbox_classes
+    return postproc.fastrcnn_inference_tail(bbox_reg, bbox_classes, rois, self.config, nms_thresh, min_score)
+
+
+def accelerate_model(model, tail: bool = True):
     """Swap the parameter-free ProposalLayer (head.prop_layer, head.py:18) and ROIPooling
-    (head.fast_rcnn.roi_pooling, layers.py:661) of a reference NbmModel for the library-backed ones;
-    state_dict keys are unaffected."""
+    (head.fast_rcnn.roi_pooling, layers.py:661) of a reference NbmModel for the library-backed ones and, with
+    ``tail``, bind ``_fast_rcnn_forward`` over ``head.fast_rcnn.forward`` (the fused inference tail).  None of
+    them holds weights, so state_dict keys are unaffected."""
     head = getattr(model, "head", None)
     if head is not None and hasattr(head, "prop_layer"):
         old = head.prop_layer
@@ -58,8 +89,58 @@ def accelerate_model(model):
     # second stage: the parameter-free ROIPooling of FastRCNN (layers.py:661) -> one-launch kernel
     frcnn = getattr(head, "fast_rcnn", None) if head is not None else None
     if frcnn is not None and hasattr(frcnn, "roi_pooling"):
-        frcnn.roi_pooling = postproc.ROIPooling(frcnn.roi_pooling.config)
+        frcnn.roi_pooling = postproc.ROIPooling(frcnn.roi_pooling.config, want_levels=not tail)
+        if tail:
+            frcnn.forward = types.MethodType(_fast_rcnn_forward, frcnn)
     return model
+
+
+def build_model(args, device=None):
+    """The model-building half of the reference's ``load_model`` (run_detection.py:100-118), restated on the
+    reference's own builders: only ``nbm_model.nets`` has to be importable (``nbm_model/run_detection.py``
+    itself imports matplotlib and librosa at module level, :7-12, which an inference box need not have)."""
+    try:
+        from nbm_model.nets.backbone import build_backbone
+        from nbm_model.nets.fpn import build_fpn
+        from nbm_model.nets.head import build_head
+        from nbm_model.nets.nbm_model import NbmModel
+        from nbm_model.nets.self_attention import build_sa_layers
+    except ImportError as e:
+        raise ImportError("nbm_model.nets (the reference checkout: it provides the detector network) must be "
+                          f"importable, e.g. PYTHONPATH=<reference checkout> ({e})") from e
+    if device is None:
+        device = "cuda" if torch.cuda.is_available() else "cpu"          # run_detection.py:22-25
+    backbone = build_backbone(args)
+    if args.fpn_first:
+        attn_channels = [args.out_fpn_chan] * len(backbone.num_channels)
+    elif args.sandwich_attn:
+        attn_channels = (backbone.num_channels, [args.out_fpn_chan] * len(backbone.num_channels))
+    else:
+        attn_channels = backbone.num_channels
+    attn = build_sa_layers(args, attn_channels)
+    fpn = build_fpn(args, backbone.num_channels)
+    head = build_head(args)
+    return NbmModel(args, backbone, attn, fpn, head).to(device)
+
+
+def load_model(mod_p, device=None):
+    """Same contract as the reference's ``load_model`` (run_detection.py:87-122): reads ``<mod_p>/args`` (the JSON
+    dump of the training namespace) and ``<mod_p>/model_chkpt.pt`` (``{'checkpoints': state_dict, ...}``,
+    train.py:171-187) and returns ``(model.eval(), args)``.  The network classes are the reference's."""
+    from nbm_model.nets.nbm_model import initialize_model
+    from nbm_model.nets.util.nets_utils import setattr_others
+
+    class Args:
+        def __init__(self, **kwargs):
+            for k, v in kwargs.items():
+                setattr(self, k, v)
+
+    with open(os.path.join(mod_p, "args"), "rb") as f:
+        args = Args(**json.load(f))
+    setattr_others(args)
+    model = build_model(args, device)
+    model = initialize_model(model, path=os.path.join(mod_p, "model_chkpt.pt"), train=False)
+    return model, args
 
 
 def detect_tiles(model, tiles: torch.Tensor, min_score: float, bs: int) -> list:

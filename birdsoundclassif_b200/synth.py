@@ -66,11 +66,49 @@ def default_args(device: str = "cuda") -> Args:
     return a
 
 
-def write_args(dirpath: str) -> str:
+def write_args(dirpath: str, **overrides) -> str:
+    """``<dirpath>/args``: the JSON the training script writes (train.py:286-288) with the parser's defaults;
+    ``overrides`` e.g. ``device='cpu'`` (layers.py:271,290,419 read ``config.device``)."""
     os.makedirs(dirpath, exist_ok=True)
     p = os.path.join(dirpath, "args")
     with open(p, "w") as f:
-        json.dump(DEFAULT_ARGS, f)
+        json.dump({**DEFAULT_ARGS, **overrides}, f)
+    return p
+
+
+def write_standin_checkpoint(dirpath: str, seed: int = 0, sharpen: float = 0.0, **arg_overrides) -> str:
+    """Stand-in for the reference's ``model_weights/`` directory (its ``args`` and ``model_chkpt.pt`` are Git-LFS
+    stubs): ``args`` from the training parser's defaults and ``model_chkpt.pt`` in the format ``train.save``
+    writes (train.py:171-187: ``{'checkpoints': state_dict, 'steps', 'epoch', 'best_val_cls_loss'}``) and
+    ``initialize_model`` reads (nbm_model.py:325-334), holding a seeded random initialisation of the reference's
+    own network (``nbm_model.nets`` must be importable).
+
+    A random 151-way softmax peaks near 1/151, so nothing clears a useful ``min_score``.  ``sharpen``
+    > 0 scales the weights of the second-stage classifier (``head.fast_rcnn.rcnn.bbox_classif_layer``) by that
+    factor and lowers the background logit, so that a few classes collect the probability mass and the tail, the
+    per-file merge and the ``.txt`` output see real detections; the network is otherwise untouched."""
+    import torch
+    from .run_detection import build_model
+
+    write_args(dirpath, **arg_overrides)
+    with open(os.path.join(dirpath, "args")) as f:
+        a = Args(**json.load(f))
+    from nbm_model.nets.util.nets_utils import setattr_others
+    setattr_others(a)
+    rng_state = torch.get_rng_state()
+    try:
+        torch.manual_seed(seed)
+        model = build_model(a, device="cpu")
+        sd = model.state_dict()
+        if sharpen:
+            w, b = "head.fast_rcnn.rcnn.bbox_classif_layer.weight", "head.fast_rcnn.rcnn.bbox_classif_layer.bias"
+            sd[w] = sd[w] * float(sharpen)
+            sd[b] = sd[b].clone()
+            sd[b][0] -= 2.0
+    finally:
+        torch.set_rng_state(rng_state)
+    p = os.path.join(dirpath, "model_chkpt.pt")
+    torch.save({"checkpoints": sd, "steps": 0, "epoch": 0, "best_val_cls_loss": float("inf")}, p)
     return p
 
 

@@ -1,9 +1,10 @@
-"""Run the UNMODIFIED reference (``/root/reference``) in the build container.
+"""Run the UNMODIFIED reference: ``/root/reference`` in the build container, or the byte-identical
+copy of its ``nbm_model`` package that ``oracle/build_ref.py`` leaves in git-ignored ``oracle/_ref/``
+(which travels to the GPU box with the snapshot).
 
-TEST INFRASTRUCTURE: used by ``oracle/make_golden.py`` and by the container-only
-tests that pin the oracle restatements.  ``/root/reference`` does not exist on the
-GPU box, so nothing here may be needed at run time there (callers skip when
-``have_reference()`` is False).
+TEST INFRASTRUCTURE: used by ``oracle/make_golden.py``, by the tests that pin the oracle
+restatements and the system-level parity tests, and by ``bench.py``'s reference legs.  Callers
+skip when ``have_reference()`` is False.
 
 The reference imports third-party modules that are not in this image.  We install
 ``sys.modules`` stand-ins for them:
@@ -27,7 +28,17 @@ import wave
 
 import numpy as np
 
-REFERENCE_ROOT = "/root/reference"
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root() -> str:
+    for cand in ("/root/reference", os.path.join(_HERE, "_ref")):
+        if os.path.isfile(os.path.join(cand, "nbm_model", "run_detection.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def have_reference() -> bool:

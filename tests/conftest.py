@@ -12,12 +12,13 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
-    config.addinivalue_line("markers", "reference: needs /root/reference (build container only)")
+    config.addinivalue_line("markers", "reference: needs the reference (/root/reference or oracle/_ref)")
 
 
 def pytest_collection_modifyitems(config, items):
-    have_ref = os.path.isfile("/root/reference/nbm_model/run_detection.py")
-    skip_ref = pytest.mark.skip(reason="/root/reference not present on this machine")
+    have_ref = any(os.path.isfile(os.path.join(r, "nbm_model", "run_detection.py"))
+                   for r in ("/root/reference", os.path.join(ROOT, "oracle", "_ref")))
+    skip_ref = pytest.mark.skip(reason="neither /root/reference nor oracle/_ref on this machine")
     for item in items:
         if "reference" in item.keywords and not have_ref:
             item.add_marker(skip_ref)

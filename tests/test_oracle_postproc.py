@@ -3,6 +3,8 @@ nms / bbox_reg_to_coord / ProposalLayer / FastRCNN tail / merge_images, and (con
 only) against those functions live on fresh random inputs."""
 import types
 
+import os
+
 import numpy as np
 import pytest
 
@@ -113,7 +115,8 @@ def test_default_args_match_reference_parser():
     """synth.DEFAULT_ARGS is the reference training parser's defaults (the schema of `args`)."""
     import ast
     from birdsoundclassif_b200 import synth
-    src = open("/root/reference/nbm_model/train.py").read()
+    from oracle import ref_shims
+    src = open(os.path.join(ref_shims.REFERENCE_ROOT, "nbm_model", "train.py")).read()
     tree = ast.parse(src)
     found = {}
     for node in ast.walk(tree):

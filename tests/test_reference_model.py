@@ -1,0 +1,223 @@
+"""System-level parity: the reference's REAL detector (``nbm_model.nets`` NbmModel, unmodified, from
+/root/reference or the oracle/_ref copy) loaded from a stand-in ``model_weights/`` directory, run
+
+  (a) as the reference runs it -- its own ``nms`` / ``bbox_reg_to_coord`` / ``ProposalLayer`` / ``ROIPooling`` /
+      ``FastRCNN.forward`` tail / ``merge_images`` (torch ops + Python loops), and
+  (b) through the product hooks -- ``patch_reference()`` + ``accelerate_model()`` (libnbm_b200 kernels),
+
+on the SAME device tiles, for several batch sizes and score cut-offs (layers.py:226-303, :668-778,
+run_detection.py:28-84, :163-249).  The reference is test infrastructure here (the checker); the product package
+only needs ``nbm_model.nets`` on the PYTHONPATH.
+"""
+import ast
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from birdsoundclassif_b200 import run_detection as rd
+from birdsoundclassif_b200 import synth
+from oracle import ref_shims
+
+pytestmark = pytest.mark.reference
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHARPEN = 400.0       # second-stage classifier scale of the stand-in: ~25 detections per tile at min_score 0.2
+
+
+@pytest.fixture(scope="module")
+def standin_dir(tmp_path_factory):
+    ref_shims.install()
+    d = str(tmp_path_factory.mktemp("model_weights"))
+    synth.write_standin_checkpoint(d, seed=0, sharpen=SHARPEN, device="cuda" if torch.cuda.is_available() else "cpu")
+    return d
+
+
+def test_standin_checkpoint_format_and_loaders_agree(standin_dir):
+    """The stand-in follows train.save's format (train.py:171-187) and the package's load_model builds the same
+    network with the same weights as the reference's load_model (run_detection.py:87-122)."""
+    ck = torch.load(os.path.join(standin_dir, "model_chkpt.pt"))
+    assert {"checkpoints", "steps", "epoch", "best_val_cls_loss"} <= set(ck)
+    import json
+    with open(os.path.join(standin_dir, "args")) as f:
+        a = json.load(f)
+    assert {k: v for k, v in a.items() if k != "device"} == {k: v for k, v in synth.DEFAULT_ARGS.items() if k != "device"}
+    m_ref, a_ref = ref_shims.ref("nbm_model.run_detection").load_model(standin_dir)
+    m, a2 = rd.load_model(standin_dir)
+    sd1, sd2 = m_ref.state_dict(), m.state_dict()
+    assert list(sd1) == list(sd2) == [k for k in ck["checkpoints"]]
+    for k in sd1:
+        assert torch.equal(sd1[k].cpu(), sd2[k].cpu()) and torch.equal(sd1[k].cpu(), ck["checkpoints"][k]), k
+    assert not m.training and vars(a_ref).keys() == vars(a2).keys()
+    assert a2.n_layers == 5 and a2.ratios == [0.5, 1, 2] and tuple(a2.top_size) == (24, 64)
+
+
+def test_accelerate_model_keeps_state_dict_and_unpatch_restores(standin_dir):
+    layers = ref_shims.ref("nbm_model.nets.layers")
+    nu = ref_shims.ref("nbm_model.nets.util.nets_utils")
+    orig = (layers.nms, layers.bbox_reg_to_coord, nu.nms)
+    m, _ = rd.load_model(standin_dir, device="cpu")
+    keys = list(m.state_dict())
+    try:
+        done = rd.patch_reference()
+        assert "nbm_model.nets.layers.nms" in done and layers.nms is not orig[0]
+        rd.accelerate_model(m)
+        assert list(m.state_dict()) == keys
+        assert type(m.head.prop_layer).__module__ == "birdsoundclassif_b200.postproc"
+        assert m.head.fast_rcnn.forward.__func__ is rd._fast_rcnn_forward
+    finally:
+        rd.unpatch_reference()
+    assert (layers.nms, layers.bbox_reg_to_coord, nu.nms) == orig
+
+
+# ------------------------------------------------------------------------------------------ GPU ----
+def _canon(tile_dict, num_classes=150):
+    """per-tile dict -> {class: (boxes [n,4] float32, scores [n] float32)} for the non-empty classes"""
+    out = {}
+    for c in range(1, num_classes + 1):
+        e = tile_dict[str(c)]
+        n = len(e["bbox_coord"])
+        if n:
+            out[c] = (e["bbox_coord"].detach().cpu().numpy().reshape(-1, 4).astype(np.float32),
+                      e["scores"].detach().cpu().numpy().reshape(-1).astype(np.float32))
+    return out
+
+
+def _assert_same_tiles(ref_out, got_out, score_tol):
+    assert len(ref_out) == len(got_out)
+    n_box = 0
+    for bi, (rb, gb) in enumerate(zip(ref_out, got_out)):
+        assert len(rb) == len(gb)
+        for ti, (r, g) in enumerate(zip(rb, gb)):
+            assert list(r.keys()) == list(g.keys()) == [str(c) for c in range(1, 151)]
+            for c in range(1, 151):     # container conventions of layers.py:750-775
+                assert r[str(c)]["scores"].dim() == g[str(c)]["scores"].dim(), (bi, ti, c)
+            r, g = _canon(r), _canon(g)
+            assert r.keys() == g.keys(), (bi, ti, sorted(r), sorted(g))
+            for c in r:
+                np.testing.assert_array_equal(r[c][0], g[c][0], err_msg=f"batch {bi} tile {ti} class {c}")
+                if score_tol == 0:
+                    np.testing.assert_array_equal(r[c][1], g[c][1])
+                else:
+                    np.testing.assert_allclose(r[c][1], g[c][1], rtol=0, atol=score_tol)
+                n_box += len(r[c][1])
+    return n_box
+
+
+@pytest.fixture(scope="module")
+def gpu_case(standin_dir):
+    """Tiles of two clips on the device + the unpatched reference model's outputs for every (bs, min_score)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from birdsoundclassif_b200 import frontend
+    ref_shims.install()
+    torch.backends.cudnn.benchmark = False
+    clips = {}
+    for name, secs, seed in (("a", 22.0, 41), ("b", 9.0, 42)):      # 9 and 4 tiles
+        pcm = synth.synth_pcm(secs, seed, calls_per_s=6.0)
+        fp = frontend.File_Processor(name + ".wav")
+        tiles, _ = fp.process_pcm(torch.from_numpy(pcm).cuda())
+        clips[name] = (fp, tiles)
+    m_ref, args = ref_shims.ref("nbm_model.run_detection").load_model(standin_dir)
+    ref = {}
+    for name, (fp, tiles) in clips.items():
+        for bs in (4, 3):
+            for ms in (0.0, 0.02, 0.2):
+                ref[name, bs, ms] = rd.detect_tiles(m_ref, tiles, ms, bs)
+    ref_rd = sys.modules["nbm_model.run_detection"]
+    merged = {k: ref_rd.merge_images(clips[k[0]][0], v, args.num_classes) for k, v in ref.items()}
+    return clips, args, ref, merged, standin_dir
+
+
+@pytest.mark.gpu
+def test_patched_reference_model_identical_to_unpatched(gpu_case):
+    """patch_reference() + accelerate_model() on the reference NbmModel: per-tile dictionaries and the merged
+    per-file dictionaries equal the unpatched model's -- boxes bit-exact, scores bit-exact (the second stage sees
+    bit-identical RoIs and pooled features, so the classifier's inputs are identical)."""
+    clips, args, ref, ref_merged, standin_dir = gpu_case
+    model, a2 = rd.load_model(standin_dir)
+    try:
+        rd.patch_reference()
+        rd.accelerate_model(model)
+        total = 0
+        for (name, bs, ms), r in ref.items():
+            fp, tiles = clips[name]
+            got = rd.detect_tiles(model, tiles, ms, bs)
+            total += _assert_same_tiles(r, got, score_tol=0)
+            # merged per-file result: the library merge on the accelerated outputs vs the reference's merge_images
+            from birdsoundclassif_b200 import postproc
+            mg = postproc.merge_images(fp, got, a2.num_classes)
+            mr = ref_merged[name, bs, ms]
+            for c in range(1, 151):
+                rb, gb = mr[str(c)]["bbox_coord"], mg[str(c)]["bbox_coord"]
+                assert len(rb) == len(gb), (name, bs, ms, c)
+                if len(rb):
+                    assert torch.equal(rb.cpu(), gb.cpu()) and torch.equal(mr[str(c)]["scores"].cpu(), mg[str(c)]["scores"].cpu())
+        assert total > 500, "the stand-in should produce detections to compare"
+    finally:
+        rd.unpatch_reference()
+
+
+@pytest.mark.gpu
+def test_patched_symbols_only_without_module_swaps(gpu_case):
+    """patch_reference() alone (the reference's own ProposalLayer / ROIPooling / FastRCNN.forward Python code calling
+    the library-backed nms and bbox_reg_to_coord, layers.py:272,301,719,742,761) gives the same dictionaries."""
+    clips, args, ref, _, standin_dir = gpu_case
+    model, _ = rd.load_model(standin_dir)
+    try:
+        rd.patch_reference()
+        for (name, bs, ms), r in ref.items():
+            if bs != 4 or ms == 0.02:
+                continue
+            got = rd.detect_tiles(model, clips[name][1], ms, bs)
+            _assert_same_tiles(r, got, score_tol=0)
+    finally:
+        rd.unpatch_reference()
+
+
+@pytest.mark.gpu
+def test_nbm_detect_cli_subprocess(gpu_case, tmp_path):
+    """``python -m birdsoundclassif_b200.nbm_detect --ckpt <stand-in> --audio_dir <3 wavs>`` in a fresh process with
+    only the reference checkout on PYTHONPATH (no shims: the product needs nbm_model.nets, not matplotlib/librosa).
+    Its .txt files equal (i) the in-process accelerated run bit for bit, and (ii) the REFERENCE's own run_detection
+    (CPU librosa-restated front-end, unpatched model) up to the front-end tolerance: same species, same box counts,
+    boxes within 1 px, scores within 2e-3."""
+    clips, args, ref, _, standin_dir = gpu_case
+    wavs = []
+    for i, (secs, seed) in enumerate(((7.0, 51), (12.5, 52), (3.0, 53))):
+        wavs.append(synth.write_wav(str(tmp_path / f"rec{i}.wav"), synth.synth_pcm(secs, seed, calls_per_s=6.0)))
+    bird_dict = os.path.join(ref_shims.REFERENCE_ROOT, "bird_dict.json")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([ROOT, ref_shims.REFERENCE_ROOT]))
+    r = subprocess.run([sys.executable, "-m", "birdsoundclassif_b200.nbm_detect", "--ckpt", standin_dir, "--audio_dir",
+                        str(tmp_path), "--min_score", "0.2", "--batch", "4", "--bird_dict", bird_dict],
+                       env=env, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    cli = {w: ast.literal_eval(open(w.replace(".wav", ".txt")).read()) for w in wavs}
+    assert sum(len(v["scores"]) for d in cli.values() for v in d.values()) > 20
+
+    # (ii) the reference's flow first (unpatched)
+    ref_rd = ref_shims.ref("nbm_model.run_detection")
+    m_ref, a_ref = ref_rd.load_model(standin_dir)
+    theirs = {w: ref_rd.run_detection(m_ref, a_ref, w, bird_dicts_path=bird_dict, min_score=0.2, bs=4) for w in wavs}
+    # (i) in-process accelerated
+    model, a2 = rd.load_model(standin_dir)
+    try:
+        rd.patch_reference()
+        rd.accelerate_model(model)
+        ours = {w: rd.run_detection(model, a2, w, bird_dicts_path=bird_dict, min_score=0.2, bs=4) for w in wavs}
+    finally:
+        rd.unpatch_reference()
+    assert cli == ours
+    n_exact = n_all = 0
+    for w in wavs:
+        assert list(theirs[w].keys()) == list(cli[w].keys()), w
+        for sp in theirs[w]:
+            tb, cb = np.array(theirs[w][sp]["bbox_coord"]), np.array(cli[w][sp]["bbox_coord"])
+            assert tb.shape == cb.shape, (w, sp)
+            assert np.abs(tb - cb).max() <= 1.0
+            np.testing.assert_allclose(theirs[w][sp]["scores"], cli[w][sp]["scores"], rtol=0, atol=2e-3)
+            n_exact += int((tb == cb).all(axis=1).sum())
+            n_all += len(tb)
+    print(f"nbm_detect vs reference flow: {n_exact}/{n_all} boxes identical")
