@@ -90,30 +90,36 @@ def run(a, rank, world, local, dist):
         rd.accelerate_model(model)
         dev = torch.device("cuda", local)
 
-        def leg(dirpath, r, w, repeats):
+        from birdsoundclassif_b200.graphed import GraphedDetector
+        graphed = GraphedDetector(model)
+
+        def leg(dirpath, r, w, repeats, det=None):
             best = None
             for _ in range(repeats):
                 _rm_outputs(dirpath)
                 barrier()
-                c = nbm_detect.detect_directory(model, margs, dirpath, bird_dict, min_score=0.2, bs=4, rank=r, world=w,
-                                                verbose=False)
+                c = nbm_detect.detect_directory(det or graphed, margs, dirpath, bird_dict, min_score=0.2, bs=4, rank=r,
+                                                world=w, verbose=False)
                 per_rank = sharding.gather_counts(c, device=dev)
                 wall = max(x["t_wall_us"] for x in per_rank) / 1e6
                 if best is None or wall < best[0]:
                     best = (wall, per_rank)
             return best
 
-        # warm-up: cuDNN heuristics, the allocator's pools, the front-end plan
+        # warm-up: cuDNN heuristics, the allocator's pools, the front-end plan, graph capture
         leg(cfg0_dir, rank, world, 1)
-        wall, per_rank = leg(cfg0_dir, rank, world, 2)
-        tot = sharding.totals(per_rank)
+        leg(cfg0_dir, rank, world, 1, det=model)
         hours = 16 * 30.0 / 3600.0
-        assert tot["files"] == 16
-        out["cfg0"] = {"workload": "BASELINE configs[0]: 16 x 30 s wavs -> .txt, one directory sharded over the ranks, "
-                                   "min_score 0.2, bs 4, reference CNN + stand-in checkpoint",
-                       "audio_hours_per_s": hours / wall, "wall_s": wall, "files": tot["files"], "tiles": tot["tiles"],
-                       "detections": tot["detections"], "scaling": "strong",
-                       "stage_s_sum_over_ranks": {k: sum(x[k] for x in per_rank) / 1e6 for k in ("t_front_us", "t_model_us", "t_post_us")}}
+        for name, det in (("cfg0", None), ("cfg0_eager", model)):
+            wall, per_rank = leg(cfg0_dir, rank, world, 2, det=det)
+            tot = sharding.totals(per_rank)
+            assert tot["files"] == 16
+            out[name] = {"workload": "BASELINE configs[0]: 16 x 30 s wavs -> .txt, one directory sharded over the ranks, "
+                                     "min_score 0.2, bs 4, reference CNN + stand-in checkpoint, detector forward "
+                                     + ("launched eagerly" if det is not None else "replayed from CUDA graphs"),
+                         "audio_hours_per_s": hours / wall, "wall_s": wall, "files": tot["files"], "tiles": tot["tiles"],
+                         "detections": tot["detections"], "scaling": "strong",
+                         "stage_s_sum_over_ranks": {k: sum(x[k] for x in per_rank) / 1e6 for k in ("t_front_us", "t_model_us", "t_post_us")}}
         wall, per_rank = leg(night_dir, 0, 1, 1)
         tot = sharding.totals(per_rank)
         hours = tot["files"] * 600.0 / 3600.0

@@ -49,6 +49,7 @@ SIGNATURES = {
     "nbm_nms_greedy": (C.c_int, [_p, _p, _i32, _i32, _f32, _p, _p, _p, _sz, _p]),
     "nbm_proposals_workspace_bytes": (_sz, [C.POINTER(ProposalParams), _i32]),
     "nbm_proposals": (C.c_int, [C.POINTER(ProposalParams), _p, _p, _p, _i32, _p, _p, C.POINTER(_i32), _p, _sz, _p]),
+    "nbm_proposals_async": (C.c_int, [C.POINTER(ProposalParams), _p, _p, _p, _i32, _p, _p, _p, _p, _sz, _p]),
     "nbm_final_detections": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _f32, _f32, _f32, _f32, _p, _p, _p, _p, _p]),
     "nbm_roi_pool": (C.c_int, [_p, _i32, _i32, C.POINTER(_p), C.POINTER(_i32), C.POINTER(_i32), _i32, _i32, _i32, _i32,
                                _i32, _i32, _p, _p, _p, _p, _p, _p]),

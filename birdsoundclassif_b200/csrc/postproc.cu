@@ -454,10 +454,29 @@ extern "C" size_t nbm_proposals_workspace_bytes(const nbm_proposal_params *p, in
     return proposal_ws(*p, B).total;
 }
 
+namespace {
+int proposals_impl(const nbm_proposal_params *p, const float *d_cls, const float *d_reg, const float *d_anchors, int32_t B,
+                   float *d_rois, float *d_scores, int32_t *h_M, int32_t *d_M, void *ws_, size_t ws_bytes, void *stream_);
+}
+
 extern "C" int nbm_proposals(const nbm_proposal_params *p, const float *d_cls, const float *d_reg,
                              const float *d_anchors, int32_t B, float *d_rois, float *d_scores, int32_t *h_M,
                              void *ws_, size_t ws_bytes, void *stream_) {
-    NBM_REQUIRE(p && d_cls && d_reg && d_anchors && d_rois && d_scores && h_M && ws_ && B >= 1, "bad argument");
+    NBM_REQUIRE(h_M, "bad argument");
+    return proposals_impl(p, d_cls, d_reg, d_anchors, B, d_rois, d_scores, h_M, nullptr, ws_, ws_bytes, stream_);
+}
+
+extern "C" int nbm_proposals_async(const nbm_proposal_params *p, const float *d_cls, const float *d_reg,
+                                   const float *d_anchors, int32_t B, float *d_rois, float *d_scores, int32_t *d_M,
+                                   void *ws_, size_t ws_bytes, void *stream_) {
+    NBM_REQUIRE(d_M, "bad argument");
+    return proposals_impl(p, d_cls, d_reg, d_anchors, B, d_rois, d_scores, nullptr, d_M, ws_, ws_bytes, stream_);
+}
+
+namespace {
+int proposals_impl(const nbm_proposal_params *p, const float *d_cls, const float *d_reg, const float *d_anchors, int32_t B,
+                   float *d_rois, float *d_scores, int32_t *h_M, int32_t *d_M, void *ws_, size_t ws_bytes, void *stream_) {
+    NBM_REQUIRE(p && d_cls && d_reg && d_anchors && d_rois && d_scores && ws_ && B >= 1, "bad argument");
     NBM_REQUIRE(p->pre_nms_topN >= 1 && p->post_nms_topN >= 1, "topN must be positive");
     cudaStream_t s = (cudaStream_t)stream_;
     const ProposalWs w = proposal_ws(*p, B);
@@ -473,7 +492,7 @@ extern "C" int nbm_proposals(const nbm_proposal_params *p, const float *d_cls, c
     auto *n_valid = reinterpret_cast<int *>(ws + w.n_valid);
     auto *pre = reinterpret_cast<int *>(ws + w.pre);
     auto *status = reinterpret_cast<int *>(ws + w.status);
-    auto *M = reinterpret_cast<int *>(ws + w.M);
+    auto *M = d_M ? d_M : reinterpret_cast<int *>(ws + w.M);
     auto *top_boxes = reinterpret_cast<float4 *>(ws + w.top_boxes);
     auto *top_scores = reinterpret_cast<float *>(ws + w.top_scores);
     auto *keep_idx = reinterpret_cast<int *>(ws + w.keep_idx);
@@ -496,11 +515,14 @@ extern "C" int nbm_proposals(const nbm_proposal_params *p, const float *d_cls, c
     if (rc != NBM_OK) return rc;
     proposal_out_kernel<<<B, 128, 0, s>>>(top_boxes, top_scores, keep_idx, keep_cnt, B, cap, p->post_nms_topN, status,
                                           reinterpret_cast<float4 *>(d_rois), d_scores, M);
-    NBM_CUDA(cudaMemcpyAsync(h_M, M, sizeof(int), cudaMemcpyDeviceToHost, s));
-    NBM_CUDA(cudaStreamSynchronize(s));
+    if (h_M) {
+        NBM_CUDA(cudaMemcpyAsync(h_M, M, sizeof(int), cudaMemcpyDeviceToHost, s));
+        NBM_CUDA(cudaStreamSynchronize(s));
+    }
     NBM_CUDA(cudaGetLastError());
     return NBM_OK;
 }
+}  // namespace
 
 extern "C" int nbm_final_detections(const float *d_bbox_reg, const float *d_probs, const float *d_rois, int32_t B,
                                     int32_t R, int32_t num_classes, float img_width, float img_height,

@@ -1,0 +1,176 @@
+"""CUDA-graph replay of the detector forward ("CUDA-graph the fixed-shape bs=4 forward").
+
+The reference network (``nbm_model.nets`` NbmModel, unchanged, weights from ``model_chkpt.pt``) is a few hundred
+small eager launches per batch of four tiles -- ResNet-50 whose FrozenBatchNorm recomputes scale and bias from
+five elementwise kernels per layer (backbone.py:55-62), two self-attention blocks, an FPN, an RPN with per-level
+heads -- and on a B200 the Python interpreter, not the GPU, sets its pace (~20 ms per batch, GPU mostly idle).  The
+launch sequence is fixed for a fixed input shape once the post-processing no longer reads sizes back to the host, so
+it is recorded once per batch size and replayed:
+
+  graph 1   samples [B,1,H,W] -> backbone -> attention -> FPN -> RPN (nbm_model.py:39-53, head.py:32-38) ->
+            ``nbm_proposals_async`` (ProposalLayer, layers.py:226-303): full ``rois [B,50,4]`` + RoI count M on the device
+  host      reads M (4 bytes; the reference's batch-coupled truncation makes the RoI count data-dependent)
+  graph 2   one per distinct M: ROIPooling kernel -> RCNN (layers.py:560-586) -> ``nbm_final_detections`` (FastRCNN
+            tail, layers.py:688-778) -> class sort of the records
+  host      one device-to-host copy of the sorted class keys -> the reference's per-image dictionaries
+
+Same kernels, same order, same inputs as the eager accelerated model, hence bit-identical outputs (tested).  The
+position embedding the reference's ``Joiner`` computes for every level (backbone.py:139-147, a host-side
+``torch.ones(...).to(device)`` per call) is skipped when ``args.add_posenc`` is False, because ``NbmModel`` then
+discards it (nbm_model.py:44-46); with ``add_posenc`` it is computed once per shape outside the graph (it depends
+on the shape only).
+
+Anything the capture cannot digest (a configuration whose forward still syncs, e.g. ``pyramid_top_n_attn`` = all
+levels with its per-call ``.to(device)``, self_attention.py:27-31) raises at capture time; ``GraphedDetector`` then
+falls back to calling the eager accelerated model and says so once (still the GPU path, no CPU fallback).
+"""
+from __future__ import annotations
+
+import warnings
+
+import torch
+
+from . import postproc
+
+
+class _Stage1:
+    __slots__ = ("graph", "x", "rois", "M_dev", "M_host", "fpn_out", "stage2")
+
+
+class _Stage2:
+    __slots__ = ("graph", "rec", "skey", "sb", "ss", "skey_host")
+
+
+class GraphedDetector:
+    """``GraphedDetector(model)(batch[:, None], min_score=...)`` == ``model(batch[:, None], min_score=...)`` for a
+    reference NbmModel that went through ``accelerate_model`` (inference only)."""
+
+    def __init__(self, model, warmup: int = 2):
+        head = getattr(model, "head", None)
+        if head is None or not isinstance(head.prop_layer, postproc.ProposalLayer) or \
+                not isinstance(head.fast_rcnn.roi_pooling, postproc.ROIPooling):
+            raise ValueError("GraphedDetector needs a model prepared by run_detection.accelerate_model()")
+        self.model = model
+        self.args = model.args
+        self.warmup = warmup
+        self._s1: dict = {}          # (B, H, W, nms_thresh, min_score) -> _Stage1
+        self._pos: dict = {}
+        self._eager_only = False
+        self._pool = None
+        self.training = False
+
+    def eval(self):
+        return self
+
+    # ------------------------------------------------------------------ the network, as nbm_model.py runs it
+    def _first_stage(self, samples, M_dev):
+        m, a = self.model, self.args
+        xs = m.backbone[0](samples)                                     # backbone.py:139-142 (Joiner -> Backbone)
+        features = [x for _, x in xs.items()]
+        if a.add_posenc:                                                # nbm_model.py:45-46
+            features = [f + self._pos_for(f) for f in features]
+        if a.fpn_first:                                                 # nbm_model.py:47-52
+            fpn_out = m.attn(m.fpn(features))
+        elif a.sandwich_attn:
+            fpn_out = m.attn[1](m.fpn(m.attn[0](features)))
+        else:
+            fpn_out = m.fpn(m.attn(features))
+        cls_scores, bbox_reg = m.head.rpn(fpn_out)                      # head.py:34
+        rois, _ = m.head.prop_layer.forward_async(cls_scores, bbox_reg, M_dev)
+        return rois, fpn_out
+
+    def _pos_for(self, f):
+        key = tuple(f.shape)
+        if key not in self._pos:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("position embedding must be cached before capture")
+            self._pos[key] = self.model.backbone[1](f).to(f.dtype)
+        return self._pos[key]
+
+    def _second_stage(self, fpn_out, rois, nms_thresh, min_score):
+        frc, a = self.model.head.fast_rcnn, self.args
+        roi_pool_out, roi_pe_out, _ = frc.roi_pooling(rois, fpn_out)    # layers.py:674
+        bbox_reg, bbox_classes = frc.rcnn(roi_pool_out, roi_pe_out)     # layers.py:676
+        rec = postproc.final_detections_flat(bbox_reg, bbox_classes, rois, a.num_classes, a.img_width, a.img_height,
+                                             nms_thresh, min_score)
+        return rec, postproc.records_sort_device(*rec, a.num_classes)
+
+    # ------------------------------------------------------------------ capture
+    def _capture1(self, samples):
+        dev = samples.device
+        s1 = _Stage1()
+        s1.x = torch.empty_like(samples)
+        s1.x.copy_(samples)
+        s1.M_dev = torch.zeros((1,), dtype=torch.int32, device=dev)
+        s1.M_host = torch.zeros((1,), dtype=torch.int32).pin_memory()
+        s1.stage2 = {}
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(self.warmup):            # cuDNN plans, workspaces, anchors, position tables: all outside the graph
+                self._first_stage(s1.x, s1.M_dev)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        s1.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(s1.graph, pool=self._pool):
+            s1.rois, s1.fpn_out = self._first_stage(s1.x, s1.M_dev)
+            s1.M_host.copy_(s1.M_dev, non_blocking=True)
+        if self._pool is None:
+            self._pool = s1.graph.pool()
+        return s1
+
+    def _capture2(self, s1, M, nms_thresh, min_score):
+        dev = s1.x.device
+        s2 = _Stage2()
+        rois = s1.rois[:, :M]
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(self.warmup):
+                self._second_stage(s1.fpn_out, rois, nms_thresh, min_score)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        s2.skey_host = torch.empty((rois.shape[0], M), dtype=torch.int32).pin_memory()    # not inside the capture
+        s2.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(s2.graph, pool=self._pool):
+            s2.rec, (s2.skey, s2.sb, s2.ss) = self._second_stage(s1.fpn_out, rois, nms_thresh, min_score)
+            s2.skey_host.copy_(s2.skey, non_blocking=True)
+        return s2
+
+    # ------------------------------------------------------------------ call
+    @torch.no_grad()
+    def __call__(self, samples, nms_thresh=0.3, min_score=0.5):
+        if self._eager_only:
+            return self.model(samples, nms_thresh=nms_thresh, min_score=min_score)
+        if not samples.is_cuda:
+            raise postproc._lib.NbmError("GraphedDetector needs CUDA tensors (no CPU fallback)")
+        key = (tuple(samples.shape), float(nms_thresh), float(min_score))
+        s1 = self._s1.get(key)
+        dev = samples.device
+        if s1 is None:
+            try:
+                s1 = self._capture1(samples.contiguous())
+            except Exception as e:          # a configuration whose forward still talks to the host: stay eager, say so
+                torch.cuda.synchronize(dev)
+                warnings.warn(f"GraphedDetector: capture failed ({type(e).__name__}: {e}); running the eager accelerated model")
+                self._eager_only = True
+                return self.model(samples, nms_thresh=nms_thresh, min_score=min_score)
+            self._s1[key] = s1
+        s1.x.copy_(samples)
+        s1.graph.replay()
+        torch.cuda.current_stream(dev).synchronize()
+        M = int(s1.M_host[0])
+        if M < 0:                            # layers.py:288-290; the reference then fails inside ROIPooling on the empty RoIs
+            print("Not enough possible RoIs, RPN failed")
+            raise RuntimeError("RPN produced fewer than rcnn_batch_size candidate boxes (the reference crashes here too)")
+        s2 = s1.stage2.get(M)
+        if s2 is None:
+            s2 = s1.stage2[M] = self._capture2(s1, M, nms_thresh, min_score)
+        s2.graph.replay()
+        torch.cuda.current_stream(dev).synchronize()
+        a = self.args
+        # the records live in the graph's static buffers and are overwritten by the next replay: the dictionaries
+        # (which callers keep until the per-file merge) get their own copies, one clone per tensor per batch
+        boxes, scores, classes, _ = (t.clone() for t in s2.rec)
+        return postproc.records_build_dicts(s2.skey_host.numpy().copy(), s2.sb.clone(), s2.ss.clone(), boxes, scores,
+                                            classes, a.num_classes, a.proposal_number)

@@ -79,6 +79,7 @@ def main(argv=None):
     parser.add_argument("--skip_done", action="store_true", help="skip wavs that already have a .txt")
     parser.add_argument("--json", action="store_true", help="also write <wav>.json next to the reference's <wav>.txt")
     parser.add_argument("--no_pipeline", action="store_true", help="one file at a time, as the reference loops")
+    parser.add_argument("--no_graphs", action="store_true", help="run the detector eagerly instead of replaying CUDA graphs")
     parser.add_argument("--group_tiles", type=int, default=1024, help="detector tiles per front-end batch (pipelined)")
     args = parser.parse_args(argv)
     assert os.path.isfile(args.bird_dict), "Missing dictionary of bird species names --> bird_dict.json."
@@ -94,6 +95,9 @@ def main(argv=None):
         raise SystemExit(str(e))
     rd.patch_reference()
     rd.accelerate_model(model)
+    if not args.no_graphs:
+        from .graphed import GraphedDetector
+        model = GraphedDetector(model)
     counts = detect_directory(model, model_args, args.audio_dirp, args.bird_dict, args.min_score, args.bs,
                               rank, world, args.skip_done, pipelined=not args.no_pipeline, group_tiles=args.group_tiles,
                               json_sidecar=args.json)

@@ -125,7 +125,7 @@ class ProposalLayer(nn.Module):
         self.config = config
         self._ws = None
 
-    def forward(self, labels_pred: torch.Tensor, bbox_reg: torch.Tensor):
+    def _launch(self, labels_pred, bbox_reg, M_dev=None):
         cfg = self.config
         if self.training:
             raise NotImplementedError("training-time proposals are out of scope (inference hot path only)")
@@ -145,16 +145,34 @@ class ProposalLayer(nn.Module):
             self._ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         rois = torch.empty((B, p.post_nms_topN, 4), dtype=torch.float32, device=dev)
         scores = torch.empty((B, p.post_nms_topN), dtype=torch.float32, device=dev)
-        M = C.c_int32(0)
         cls, reg = _f32c(labels_pred), _f32c(bbox_reg)
         with torch.cuda.device(dev):
-            _lib.check(_lib.lib().nbm_proposals(C.byref(p), cls.data_ptr(), reg.data_ptr(), anchors.data_ptr(), B,
-                                                rois.data_ptr(), scores.data_ptr(), C.byref(M), self._ws.data_ptr(),
-                                                self._ws.numel(), _stream()), "nbm_proposals")
-        if M.value < 0:
+            if M_dev is None:
+                M = C.c_int32(0)
+                _lib.check(_lib.lib().nbm_proposals(C.byref(p), cls.data_ptr(), reg.data_ptr(), anchors.data_ptr(), B,
+                                                    rois.data_ptr(), scores.data_ptr(), C.byref(M), self._ws.data_ptr(),
+                                                    self._ws.numel(), _stream()), "nbm_proposals")
+                return rois, scores, M.value
+            _lib.check(_lib.lib().nbm_proposals_async(C.byref(p), cls.data_ptr(), reg.data_ptr(), anchors.data_ptr(), B,
+                                                      rois.data_ptr(), scores.data_ptr(), M_dev.data_ptr(),
+                                                      self._ws.data_ptr(), self._ws.numel(), _stream()),
+                       "nbm_proposals_async")
+        return rois, scores, M_dev
+
+    def forward(self, labels_pred: torch.Tensor, bbox_reg: torch.Tensor):
+        rois, scores, M = self._launch(labels_pred, bbox_reg)
+        if M < 0:
             print("Not enough possible RoIs, RPN failed")                  # layers.py:288-290
+            dev = labels_pred.device
             return torch.tensor([]).to(dev), torch.tensor([]).to(dev)
-        return rois[:, :M.value], scores[:, :M.value]
+        return rois[:, :M], scores[:, :M]
+
+    def forward_async(self, labels_pred: torch.Tensor, bbox_reg: torch.Tensor, M_dev: torch.Tensor):
+        """No host read, no synchronisation (CUDA-graph capturable): returns the FULL ``rois [B, post_nms_topN, 4]``
+        and ``scores [B, post_nms_topN]``; the number of valid rows (or -1 for the reference's "RPN failed" branch)
+        is written to ``M_dev`` (int32 [1] on the device)."""
+        rois, scores, _ = self._launch(labels_pred, bbox_reg, M_dev)
+        return rois, scores
 
 
 # ----------------------------------------------------------------------------- final tail -----
@@ -188,21 +206,23 @@ class TileDetections(dict):
     __slots__ = ("flat",)
 
 
-def records_to_dicts(boxes, scores, classes, counts, num_classes, proposal_number=None):
-    """Flat records -> the reference's list(B) of {str(c): {'bbox_coord': [n,4], 'scores': [1,n]}}
-    (layers.py:750-775); empty classes are CPU ``torch.Tensor()`` like the reference.  One stable sort by class
-    for the whole batch and one device-to-host copy; the per-class entries are views of the sorted rows (the
-    reference spends 150 iterations with a nonzero + sync each per image, layers.py:757-775)."""
+def records_sort_device(boxes, scores, classes, counts, num_classes):
+    """Device half of ``records_to_dicts`` (no host read: CUDA-graph capturable): one stable sort by class for the
+    whole batch -> (skey int32 [B,R] sorted class keys with num_classes+1 for dead rows, sb [B,R,4], ss [B,R])."""
     B, R = classes.shape
-    dev = boxes.device
     invalid = int(num_classes) + 1
-    key = torch.where(torch.arange(R, device=dev)[None] < counts[:, None], classes, invalid)
+    key = torch.where(torch.arange(R, device=boxes.device)[None] < counts[:, None], classes, invalid)
     skey, order = torch.sort(key, dim=1, stable=True)               # per-class order = surviving order
     sb = torch.gather(boxes, 1, order[..., None].expand(-1, -1, 4))
     ss = torch.gather(scores, 1, order)
-    skey_h = skey.cpu().numpy()
+    return skey, sb, ss
+
+
+def records_build_dicts(skey_h, sb, ss, boxes, scores, classes, num_classes, proposal_number=None):
+    """Host half of ``records_to_dicts``: ``skey_h`` is the sorted key table on the host (numpy [B,R])."""
+    invalid = int(num_classes) + 1
     out = []
-    for b in range(B):
+    for b in range(skey_h.shape[0]):
         row = skey_h[b]
         n = int((row < invalid).sum())
         d = TileDetections((str(c), dict(bbox_coord=torch.Tensor(), scores=torch.Tensor())) for c in range(1, num_classes + 1))
@@ -217,6 +237,15 @@ def records_to_dicts(boxes, scores, classes, counts, num_classes, proposal_numbe
         d.flat = None if truncated else (boxes[b, :n], scores[b, :n], classes[b, :n])
         out.append(d)
     return out
+
+
+def records_to_dicts(boxes, scores, classes, counts, num_classes, proposal_number=None):
+    """Flat records -> the reference's list(B) of {str(c): {'bbox_coord': [n,4], 'scores': [1,n]}}
+    (layers.py:750-775); empty classes are CPU ``torch.Tensor()`` like the reference.  One stable sort by class
+    for the whole batch and one device-to-host copy; the per-class entries are views of the sorted rows (the
+    reference spends 150 iterations with a nonzero + sync each per image, layers.py:757-775)."""
+    skey, sb, ss = records_sort_device(boxes, scores, classes, counts, num_classes)
+    return records_build_dicts(skey.cpu().numpy(), sb, ss, boxes, scores, classes, num_classes, proposal_number)
 
 
 def fastrcnn_inference_tail(bbox_reg, bbox_classes, rois, config, nms_thresh=0.3, min_score=0.5):

@@ -164,6 +164,12 @@ size_t nbm_proposals_workspace_bytes(const nbm_proposal_params *p, int32_t B);
 int nbm_proposals(const nbm_proposal_params *p, const float *d_cls, const float *d_reg,
                   const float *d_anchors, int32_t B, float *d_rois, float *d_scores,
                   int32_t *h_M, void *d_workspace, size_t workspace_bytes, void *stream);
+/* The same without the host read: M goes to d_M (device int32) and the call neither copies to the
+ * host nor synchronises, so it can be recorded into a CUDA graph together with the network that
+ * produces d_cls / d_reg (the caller reads d_M when it needs the RoI count). */
+int nbm_proposals_async(const nbm_proposal_params *p, const float *d_cls, const float *d_reg,
+                        const float *d_anchors, int32_t B, float *d_rois, float *d_scores,
+                        int32_t *d_M, void *d_workspace, size_t workspace_bytes, void *stream);
 
 /* FastRCNN.forward inference branch (layers.py:688-778), fused per image: argmax class,
  * class-specific delta gather, decode against rois, clamp, stable descending sort, drop
