@@ -42,7 +42,6 @@ struct FileDesc {
     int last_width;        // valid columns of the last tile (rest is reflect padding)
     int group0, n_groups;  // the file's 64-frame groups (contiguous)
     int seg0, n_segs;      // the file's STFT chunks (contiguous)
-    unsigned int done_target;   // units the slide kernel publishes for this file (fused tiling), 0 otherwise
 };
 
 struct KParams {
@@ -74,7 +73,9 @@ __device__ __forceinline__ void fold_idx(int L, int j, int &hi, int &lo) {
 
 __global__ void __launch_bounds__(512, 1)
 stft_db_kernel(KParams P, const SegDesc *__restrict__ segs, int n_segs, const void *__restrict__ pcm,
-               int dtype, int channels, float *__restrict__ spec, float2 *__restrict__ tile_mm, int group_begin) {
+               int dtype, int channels, float *__restrict__ spec, float2 *__restrict__ tile_mm, int group_begin,
+               float rel_db, unsigned long long *__restrict__ cand,
+               unsigned int *__restrict__ cand_count, unsigned int cand_cap) {
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
 
@@ -96,6 +97,7 @@ stft_db_kernel(KParams P, const SegDesc *__restrict__ segs, int n_segs, const vo
     float2 *F = reinterpret_cast<float2 *>(buf + buf_pad);
     float2 *E = F + ((P.npN + 1) & ~1);
     float *stage = reinterpret_cast<float *>(E + P.npH * PASS);
+    __shared__ float bin_rmax[16 * 32];     // largest |R| each thread's bin carried in the pass (thread = bin), see refine_groups_kernel
 
     // ---- samples of the group (zero outside the segment: centre padding, pad_mode='constant') --
     const long long s0 = (long long)t0 * hop - N / 2;
@@ -145,6 +147,18 @@ stft_db_kernel(KParams P, const SegDesc *__restrict__ segs, int n_segs, const vo
     const float2 gf = __ldg(P.tw + (int)(((long long)kk * (hop + 1)) % N2));   // e^{+i theta (hop+1)/2}
     const float2 gb = __ldg(P.tw + (int)(((long long)kk * (hop - 1)) % N2));   // e^{-i theta (hop-1)/2} = (c,-s)
     const float Ra_r = Rr, Ra_i = Ri;
+    // The float32 twiddle cf is off by rho = cf_true / cf in every step of the recurrence (a systematic error that grows
+    // linearly along the pass); every 4 steps the recurrence multiplies by rho^4 = 1 + fx (see frontend_tc.cu).
+    float2 fx;
+    {
+        double sn, cs;
+        sincospi((double)(((long long)kk * 2 * hop) % N2) / (double)N, &sn, &cs);
+        const double cr = (double)cf.x, ci = (double)cf.y, d2 = cr * cr + ci * ci;
+        const double pr = (cs * cr + sn * ci) / d2, pi = (sn * cr - cs * ci) / d2;
+        double qr = pr * pr - pi * pi, qi = 2.0 * pr * pi;               // rho^2
+        const double q4r = qr * qr - qi * qi, q4i = 2.0 * qr * qi;       // rho^4
+        fx = make_float2((float)(q4r - 1.0), (float)q4i);
+    }
 
     const int out_bin = warp * BINS_PER_WARP + lane - 1;
     const bool emit = lane >= 1 && lane <= BINS_PER_WARP && out_bin < P.n_bins;
@@ -159,11 +173,7 @@ stft_db_kernel(KParams P, const SegDesc *__restrict__ segs, int n_segs, const vo
         const float xi = 0.5f * im - 0.25f * (li + ri);
         const float p = fmaxf(fmaf(xr, xr, xi * xi), P.min_level_sq);
         const float db = 3.0102999566398120f * __log2f(p);     // 10 log10(p)
-        if (emit) {
-            stage[out_bin * STAGE_LD + col] = db;
-            vmin = fminf(vmin, db);
-            vmax = fmaxf(vmax, db);
-        }
+        if (emit) stage[out_bin * STAGE_LD + col] = db;
     };
 
     for (int pass = 0; pass < 2; ++pass) {
@@ -208,15 +218,22 @@ stft_db_kernel(KParams P, const SegDesc *__restrict__ segs, int n_segs, const vo
         }
         // ---- slide, Hann (shuffles), dB, stage -------------------------------------------------
         Rr = Ra_r; Ri = Ra_i;
+        float mR = fmaxf(fabsf(Rr), fabsf(Ri));
         if (fwd) {
             emit_frame(Rr, Ri, 0);
 #pragma unroll
             for (int i = 0; i < PASS; ++i) {
                 if (i < cnt) {       // block-uniform
                     const float Gr = gr[i], Gi = -gi[i];
-                    const float nr = cf.x * Rr - cf.y * Ri + gf.x * Gr - gf.y * Gi;
-                    const float ni = cf.x * Ri + cf.y * Rr + gf.x * Gi + gf.y * Gr;
+                    float nr = cf.x * Rr - cf.y * Ri + gf.x * Gr - gf.y * Gi;
+                    float ni = cf.x * Ri + cf.y * Rr + gf.x * Gi + gf.y * Gr;
+                    if ((i & 3) == 3) {
+                        const float tr = fmaf(fx.x, nr, fmaf(-fx.y, ni, nr));
+                        ni = fmaf(fx.x, ni, fmaf(fx.y, nr, ni));
+                        nr = tr;
+                    }
                     Rr = nr; Ri = ni;
+                    mR = fmaxf(mR, fmaxf(fabsf(nr), fabsf(ni)));
                     emit_frame(Rr, Ri, i + 1);
                 }
             }
@@ -226,20 +243,47 @@ stft_db_kernel(KParams P, const SegDesc *__restrict__ segs, int n_segs, const vo
                 if (i < cnt) {
                     const float Gr = gr[i], Gi = -gi[i];
                     // R_t = conj(cf) R_{t+1} - (gb.x - i gb.y) G_t
-                    const float nr = cf.x * Rr + cf.y * Ri - (gb.x * Gr + gb.y * Gi);
-                    const float ni = cf.x * Ri - cf.y * Rr - (gb.x * Gi - gb.y * Gr);
+                    float nr = cf.x * Rr + cf.y * Ri - (gb.x * Gr + gb.y * Gi);
+                    float ni = cf.x * Ri - cf.y * Rr - (gb.x * Gi - gb.y * Gr);
+                    if ((i & 3) == 3) {
+                        const float tr = fmaf(fx.x, nr, fmaf(fx.y, ni, nr));
+                        ni = fmaf(fx.x, ni, fmaf(-fx.y, nr, ni));
+                        nr = tr;
+                    }
                     Rr = nr; Ri = ni;
+                    mR = fmaxf(mR, fmaxf(fabsf(nr), fabsf(ni)));
                     emit_frame(Rr, Ri, a - 1 - i);
                 }
             }
         }
+        bin_rmax[tid] = mR;
         __syncthreads();
         // ---- coalesced rows out -----------------------------------------------------------------
         const int ncols = fwd ? (cnt + 1) : cnt;
         const int col0 = t0 + (fwd ? a : 0);
-        for (int b = warp; b < P.n_bins; b += n_warps) {
-            if (lane < ncols) spec_seg[(long long)b * sd.row_stride + col0 + lane] = stage[b * STAGE_LD + lane];
-            if (lane + 32 < ncols) spec_seg[(long long)b * sd.row_stride + col0 + lane + 32] = stage[b * STAGE_LD + lane + 32];
+        // min / max of the unflagged pixels; pixels below their frame's flag level go to the float64 pass
+        // (refine_groups_kernel), exactly as in the tensor-core kernel
+        for (int h = 0; h < 2; ++h) {
+            const int c = lane + 32 * h;
+            if (c >= ncols) continue;
+            for (int b = warp; b < P.n_bins; b += n_warps) {
+                // bin b is thread (b / 30) * 32 + b % 30 + 1; its Hann neighbours are the threads next to it
+                const int tb = (b / BINS_PER_WARP) * 32 + b % BINS_PER_WARP + 1;
+                const float m3 = fmaxf(bin_rmax[tb], fmaxf(bin_rmax[tb - 1], bin_rmax[tb + 1]));
+                const float th = m3 > 0.f ? fmaf(__log2f(m3), 6.0205999132796239f, rel_db) : -INFINITY;
+                const float v = stage[b * STAGE_LD + c];
+                spec_seg[(long long)b * sd.row_stride + col0 + c] = v;
+                vmax = fmaxf(vmax, v);
+                bool listed = false;
+                if (v < th) {
+                    const unsigned int at = atomicAdd(cand_count, 1u);
+                    if (at < cand_cap) {
+                        cand[at] = pack_group(lo_s, b, 1, 1, col0 + c);
+                        listed = true;
+                    }
+                }
+                if (!listed) vmin = fminf(vmin, v);
+            }
         }
         __syncthreads();
     }
@@ -266,20 +310,124 @@ stft_db_kernel(KParams P, const SegDesc *__restrict__ segs, int n_segs, const vo
 }
 
 // ---------------------------------------------------------------------------------------------
-// Whole-file min / max (prepare_dataset.py:248-250) from the per-(group, slot) partials, with the
-// minimum made exact.  s_min is by construction the deepest spectral null of the file, where any
-// float32 transform has its largest relative error, and it shifts EVERY normalised pixel.  So the
-// few pixels within `margin_db` of the float32 minimum are recomputed as the reference computes
-// them (float64 windowed DFT -> complex64 -> float32 |.| -> float64 log10), patched in the dB band,
-// and the minimum is taken over the patched values.  One block per file.
+// Float64 refinement of the pixels float32 cannot deliver within tolerance, and the whole-file min / max
+// (prepare_dataset.py:248-250).
+//
+// The transform's absolute error in a pixel is float32 rounding (~2^-24 rms, < ~2e-6 worst) of the largest rectangular-
+// window magnitude |R_t[k]| its bin carried along the sliding recurrence since the anchor (measured,
+// scripts/fe_outliers.py) -- inherent to any float32 sliding DFT.  In dB that is invisible except where the pixel lies
+// ~60 dB below that magnitude: deep spectral nulls, and quiet frames a few hops after a loud call swept through the bin.
+// The deepest null of a file is s_min, which offsets every normalised pixel.  So:
+//   transform kernels        track max |R| per bin along the chain, list the pixels (tensor-core kernel: the thread's block of
+//                            pixels) that fall `rel_db` below it and keep them out of the min/max partials;
+//   refine_groups_kernel     recomputes each listed pixel the way the reference does -- float64 windowed DFT ->
+//                            complex64 -> float32 |.| -> float64 log10 (prepare_dataset.py:237-240) -- patches the dB
+//                            band and folds the exact value into the file's minimum (ordered-integer atomicMin);
+//   minmax_kernel            file min = min(partials of the unlisted pixels, exact minimum of the listed blocks), with the
+//                            unlisted pixels within 0.25 dB of it recomputed too, so that s_min is the reference's value.
 struct RefineParams {
     int N, hop, low_idx, n_bins;
     int mm_frames;          // frames per min/max partial group (a divisor of GF)
-    int n_ranges, slots_per_range, bins_per_range, bins_per_slot;
+    int mm_per_group;       // partials per mm_frames group (ranges x slots)
+    int slots_per_range, bins_per_range, bins_per_slot;
     double min_level;
-    float margin_db;
+    float margin_db;        // unlisted pixels this close to the file minimum are recomputed as well
+    int n_ranges;           // tensor-core path: 128-row ranges (flag levels are per (chain, range, emit warp)), else 0
+    const double2 *tw64;    // [N] (cos, sin)(2 pi q / N)
+    const double *hann64;   // [N] periodic Hann window / 32768
 };
-constexpr int REFINE_CAP = 64;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// One warp per listed block (pack_group): lane = pixel (row = lane / 2, frame = lane % 2).  Pixels below the flag level
+// are recomputed one after the other by the whole warp.  Sample i = 32 j + l of the window belongs to lane l, and
+// e^{-i theta (32 j + l)} = e^{-i theta 32 j} e^{-i theta l}: inside the loop the twiddle is the same for every lane (one
+// broadcast load from the float64 table per step), the lane's own factor is applied once at the end.  Per sample and lane
+// that leaves four float64 operations: the int16 sample becomes a double by the 2^52 trick (no conversion unit), times the
+// window (exactly the reference's float32 x float64 product, rounded once), and two fused multiply-adds.
+__global__ void __launch_bounds__(256)
+refine_groups_kernel(RefineParams R, const SegDesc *__restrict__ segs, const unsigned long long *__restrict__ cand,
+                     const unsigned int *__restrict__ cand_count, unsigned int cand_cap, const float *__restrict__ flag_db,
+                     float *__restrict__ spec, const void *__restrict__ pcm, int dtype, int channels,
+                     unsigned int *__restrict__ file_min) {
+    const int lane = threadIdx.x & 31;
+    const unsigned int n = min(*cand_count, cand_cap);
+    const unsigned int warps = gridDim.x * (blockDim.x >> 5);
+    const bool fast = dtype == NBM_PCM_INT16 && channels == 1;
+    constexpr double MAGIC = 4503601774854144.0;            // 2^52 + 2^31
+    for (unsigned int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < n; c += warps) {
+        const unsigned long long key = cand[c];
+        const int seg = (int)(key >> 42), bin0 = (int)((key >> 32) & 1023), rows = (int)((key >> 28) & 15) + 1;
+        const int nfr = (int)((key >> 27) & 1) + 1, frame0 = (int)(key & GROUP_MAX_FRAME);
+        const SegDesc sd = segs[seg];
+        // tensor-core blocks: the level their emit warp used; single pixels (CUDA-core kernel) were tested against their own
+        // bin's level already and are recomputed unconditionally
+        float th = INFINITY;
+        if (R.n_ranges > 0) {
+            const int bpr = R.bins_per_range;
+            th = flag_db[((2 * (size_t)sd.group0 + frame0 / (GF / 2)) * R.n_ranges + bin0 / bpr) * 4 + (bin0 % bpr) / R.bins_per_slot];
+        }
+        const int row = lane >> 1, e = lane & 1;
+        const bool mine = row < rows && e < nfr;
+        float *px = spec + sd.spec_off + (long long)(bin0 + row) * sd.row_stride + frame0 + e;
+        float v = mine ? *px : INFINITY;
+        unsigned int todo = __ballot_sync(0xffffffffu, mine && v < th);
+        const short *p16 = reinterpret_cast<const short *>(pcm) + sd.pcm_start;
+        while (todo) {
+            const int l = __ffs((int)todo) - 1;
+            todo &= todo - 1;
+            const long long k = R.low_idx + bin0 + (l >> 1);
+            const long long s0 = (long long)(frame0 + (l & 1)) * R.hop - R.N / 2;
+            const int qstep = (int)((k * 32) % R.N);
+            int q = 0;                                       // (32 j k) mod N
+            double ar = 0.0, ai = 0.0;
+            constexpr int UB = 6;                           // samples in flight per lane
+            for (int i0 = lane; i0 < R.N; i0 += 32 * UB) {
+                double x[UB];
+#pragma unroll
+                for (int u = 0; u < UB; ++u) {
+                    const int i = i0 + 32 * u;
+                    const long long sx = s0 + i;
+                    x[u] = 0.0;
+                    if (i < R.N && sx >= 0 && sx < sd.n_samples) {    // centre padding, pad_mode='constant'
+                        // the reference multiplies the float32 sample (int16 / 32768, exact) by the float64 window: one rounding
+                        const double xs = fast ? __hiloint2double(0x43300000, (int)__ldg(p16 + sx) ^ 0x80000000) - MAGIC
+                                               : 32768.0 * (double)load_sample(pcm, dtype, channels, sd.pcm_start + sx);
+                        x[u] = xs * R.hann64[i];            // hann64 = window / 32768 (a power of two: still one rounding)
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UB; ++u) {
+                    const double2 w = R.tw64[q];            // same address in every lane
+                    ar = fma(x[u], w.x, ar);
+                    ai = fma(-x[u], w.y, ai);
+                    q += qstep;
+                    if (q >= R.N) q -= R.N;
+                }
+            }
+            {
+                const double2 w = R.tw64[(int)((k * lane) % R.N)];                  // the lane's own factor e^{-i theta l}
+                const double tr = ar * w.x + ai * w.y;
+                ai = ai * w.x - ar * w.y;
+                ar = tr;
+            }
+            ar = warp_sum(ar);
+            ai = warp_sum(ai);
+            const float re = (float)ar, im = (float)ai;                             // stored complex64
+            const float mag = (float)hypot((double)re, (double)im);                // np.abs -> float32
+            const float db = (float)(20.0 * log10(fmax(R.min_level, (double)mag)));
+            if (lane == l) { v = db; *px = db; }
+        }
+        // the block's exact minimum (it was left out of the min/max partial)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if (lane == 0) atomicMin(file_min + sd.file, float_to_ordered(v));
+    }
+}
 
 __device__ __forceinline__ double block_sum_256(double v, double *red) {
 #pragma unroll
@@ -293,20 +441,25 @@ __device__ __forceinline__ double block_sum_256(double v, double *red) {
     return t;
 }
 
-__device__ __forceinline__ void
-refine_file(const RefineParams &R, const SegDesc *__restrict__ segs, const FileDesc *__restrict__ files,
-            const float2 *__restrict__ tile_mm, float *__restrict__ spec, const void *__restrict__ pcm,
-            int dtype, int channels, float *__restrict__ out, int file) {
+// Whole-file min / max, one block per file.  s_min offsets EVERY normalised pixel, so it has to be the reference's own
+// value, not a float32 approximation of it: the minimum is min(exact minimum of the listed blocks, partials of the rest),
+// and the few unlisted pixels within `margin_db` of it (their float32 values are good to ~0.01 dB, the deep nulls having
+// been listed) are recomputed like the listed ones, patched, and the minimum is taken over the exact values.
+constexpr int MINMAX_CAP = 64;
+__global__ void __launch_bounds__(256)
+minmax_kernel(RefineParams R, const SegDesc *__restrict__ segs, const FileDesc *__restrict__ files,
+              const float2 *__restrict__ tile_mm, const unsigned int *__restrict__ file_min, float *__restrict__ spec,
+              const void *__restrict__ pcm, int dtype, int channels, float *__restrict__ out, int file_begin) {
     __shared__ float s_red[16];
     __shared__ double d_red[16];
-    __shared__ int c_seg[REFINE_CAP], c_bin[REFINE_CAP], c_frame[REFINE_CAP];
-    __shared__ int n_cand, n_hot, hot[REFINE_CAP];
+    __shared__ int c_seg[MINMAX_CAP], c_bin[MINMAX_CAP], c_frame[MINMAX_CAP];
+    __shared__ int n_cand, n_hot, hot[MINMAX_CAP];
+    const int file = blockIdx.x + file_begin;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const FileDesc fd = files[file];
-    const int per_gf = GF / R.mm_frames, n_slots = R.n_ranges * R.slots_per_range;
-    const int n_ent = fd.n_groups * per_gf * n_slots;
-    const float2 *mm = tile_mm + (size_t)fd.group0 * per_gf * n_slots;
-
+    const int per_gf = GF / R.mm_frames;
+    const int n_ent = fd.n_groups * per_gf * R.mm_per_group;
+    const float2 *mm = tile_mm + (size_t)fd.group0 * per_gf * R.mm_per_group;
     float vmin = INFINITY, vmax = -INFINITY;
     for (int i = tid; i < n_ent; i += 256) {
         const float2 v = mm[i];
@@ -324,16 +477,20 @@ refine_file(const RefineParams &R, const SegDesc *__restrict__ segs, const FileD
     vmin = s_red[0]; vmax = s_red[8];
 #pragma unroll
     for (int w = 1; w < 8; ++w) { vmin = fminf(vmin, s_red[w]); vmax = fmaxf(vmax, s_red[8 + w]); }
-    const float thr = vmin + R.margin_db;
+    const unsigned int fm = file_min[file];
+    const float listed_min = fm != 0xffffffffu ? ordered_to_float(fm) : INFINITY;     // exact
+    vmax = fmaxf(vmax, listed_min == INFINITY ? -INFINITY : listed_min);             // a file whose every pixel was listed
+    const float thr = fminf(vmin, listed_min) + R.margin_db;
 
     // partial groups whose minimum is within the margin (a handful), then their pixels
     for (int i = tid; i < n_ent; i += 256)
         if (mm[i].x <= thr) {
             const int at = atomicAdd(&n_hot, 1);
-            if (at < REFINE_CAP) hot[at] = i;
+            if (at < MINMAX_CAP) hot[at] = i;
         }
     __syncthreads();
-    const int nh = min(n_hot, REFINE_CAP);
+    const int nh = min(n_hot, MINMAX_CAP);
+    const int n_slots = R.mm_per_group, slots_per_range = R.slots_per_range;
     for (int h = 0; h < nh; ++h) {
         const int i = hot[h];
         const int mg = fd.group0 * per_gf + i / n_slots, slot = i % n_slots;     // partial group (mm_frames frames)
@@ -341,19 +498,19 @@ refine_file(const RefineParams &R, const SegDesc *__restrict__ segs, const FileD
         while (si > fd.seg0 && segs[si].group0 * per_gf > mg) --si;
         const SegDesc sd = segs[si];
         const int t0 = (mg - sd.group0 * per_gf) * R.mm_frames, nf = min(R.mm_frames, sd.n_frames - t0);
-        const int rng = slot / R.slots_per_range, sl = slot % R.slots_per_range;
+        const int rng = slot / slots_per_range, sl = slot % slots_per_range;
         const int b0 = rng * R.bins_per_range + sl * R.bins_per_slot;
         const int nb = min(min(R.bins_per_slot, R.bins_per_range - sl * R.bins_per_slot), R.n_bins - b0);
         for (int p = tid; p < nb * nf; p += 256) {
             const int b = b0 + p / nf, t = t0 + p % nf;
             if (spec[sd.spec_off + (long long)b * sd.row_stride + t] <= thr) {
                 const int at = atomicAdd(&n_cand, 1);
-                if (at < REFINE_CAP) { c_seg[at] = si; c_bin[at] = b; c_frame[at] = t; }
+                if (at < MINMAX_CAP) { c_seg[at] = si; c_bin[at] = b; c_frame[at] = t; }
             }
         }
     }
     __syncthreads();
-    const int nc = min(n_cand, REFINE_CAP);
+    const int nc = min(n_cand, MINMAX_CAP);
     double best = INFINITY;
     for (int c = 0; c < nc; ++c) {
         const SegDesc sd = segs[c_seg[c]];
@@ -364,11 +521,10 @@ refine_file(const RefineParams &R, const SegDesc *__restrict__ segs, const FileD
             const long long s = s0 + n;
             if (s < 0 || s >= sd.n_samples) continue;           // centre padding, pad_mode='constant'
             const double x = (double)load_sample(pcm, dtype, channels, sd.pcm_start + s);
-            const double w = 0.5 - 0.5 * cospi(2.0 * (double)n / (double)R.N);     // periodic Hann
-            double sn, cs;
-            sincospi(2.0 * (double)((k * n) % R.N) / (double)R.N, &sn, &cs);
-            ar += x * w * cs;
-            ai -= x * w * sn;
+            const double xw = x * (0.5 - 0.5 * R.tw64[n].x);                        // periodic Hann
+            const double2 w = R.tw64[(int)((k * n) % R.N)];
+            ar = fma(xw, w.x, ar);
+            ai = fma(-xw, w.y, ai);
         }
         ar = block_sum_256(ar, d_red);
         ai = block_sum_256(ai, d_red);
@@ -379,19 +535,13 @@ refine_file(const RefineParams &R, const SegDesc *__restrict__ segs, const FileD
         if (tid == 0) spec[sd.spec_off + (long long)c_bin[c] * sd.row_stride + c_frame[c]] = (float)db;
     }
     if (tid == 0) {
-        // every pixel within the margin was recomputed unless the list overflowed (e.g. digital silence)
-        float smin = vmin;
-        if (nc > 0) smin = (n_cand > REFINE_CAP || n_hot > REFINE_CAP) ? fminf(vmin, (float)best) : (float)best;
+        // every unlisted pixel within the margin was recomputed unless the list overflowed (e.g. digital silence)
+        float smin = fminf(vmin, listed_min);
+        if (nc > 0 && n_cand <= MINMAX_CAP && n_hot <= MINMAX_CAP) smin = fminf((float)best, listed_min);
+        else if (nc > 0) smin = fminf(smin, (float)best);
         out[2 * file] = smin;
         out[2 * file + 1] = vmax;
     }
-}
-
-__global__ void __launch_bounds__(256)
-refine_minmax_kernel(RefineParams R, const SegDesc *__restrict__ segs, const FileDesc *__restrict__ files,
-                     const float2 *__restrict__ tile_mm, float *__restrict__ spec, const void *__restrict__ pcm,
-                     int dtype, int channels, float *__restrict__ out, int file_begin) {
-    refine_file(R, segs, files, tile_mm, spec, pcm, dtype, channels, out, blockIdx.x + file_begin);
 }
 
 // Descriptor upload without the copy engine: a DMA copy on the caller's stream would queue behind whatever large
@@ -513,99 +663,6 @@ tile_kernel(KParams P, const FileDesc *__restrict__ files, int n_files, const fl
     tile_block<VEC4, false>(P, files[f], tile, blockIdx.y, minmax[2 * f], minmax[2 * f + 1], spec, tiles);
 }
 
-// Tiling that FOLLOWS the transform inside one launch window (tensor-core path): blocks run in file order, two per SM
-// beside the 96-register slide kernel.  The first block of a file waits until the slide kernel has published all of the
-// file's units (file_done), computes the file's exact min / max (refine_file) and raises mm_ready; the file's other
-// blocks wait for that flag.  The dB band is then read while it is still in L2, one file behind the transform, so the
-// pass costs HBM only its tile writes.  Waits are bounded: a lost flag traps instead of hanging the device.
-__device__ __forceinline__ void wait_flag_ge(const unsigned int *flag, unsigned int target) {
-    if (threadIdx.x == 0) {
-        unsigned int v;
-        long long spins = 0;
-        while (true) {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-            if (v >= target) break;
-            __nanosleep(1000);
-            if (++spins > 20000000ll) __trap();
-        }
-    }
-    __syncthreads();
-}
-
-#ifdef NBM_WS_TIMING
-__device__ unsigned long long follow_dbg[8];   // [0] first block start, [1] file 0 ready, [2] middle file ready, [3] last block end
-__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-__device__ unsigned long long follow_files[2][2048];   // per file: min/max block scheduled | file complete (seen by it)
-extern "C" int nbm_debug_follow_timing(unsigned long long *out) {
-    return cudaMemcpyFromSymbol(out, follow_dbg, sizeof(follow_dbg)) == cudaSuccess ? 0 : -1;
-}
-extern "C" int nbm_debug_follow_files(unsigned long long *out) {
-    return cudaMemcpyFromSymbol(out, follow_files, sizeof(follow_files)) == cudaSuccess ? 0 : -1;
-}
-#endif
-
-template <bool VEC4>
-__global__ void __launch_bounds__(256, 8)
-tile_follow_kernel(KParams P, RefineParams R, const SegDesc *__restrict__ segs, const FileDesc *__restrict__ files, int n_files,
-                   const float2 *__restrict__ tile_mm, float *__restrict__ spec, const void *__restrict__ pcm,
-                   float *__restrict__ minmax, float *__restrict__ tiles, const unsigned int *__restrict__ file_done,
-                   unsigned int *__restrict__ mm_ready, int row_blocks, int ahead) {
-    // Block order (file-major): `lead` min/max blocks for files 0 .. lead-1, then per file f the min/max block of file
-    // f + lead followed by f's tiling blocks.  A file's min/max (tens of microseconds of float64 refinement) is thus
-    // under way `lead` files before its tiling blocks reach the SMs instead of in front of them -- only about one
-    // file's blocks are resident at a time, so a min/max placed directly before its tiles serialises per file.
-    const int lead = min(ahead, n_files);
-    const int b = blockIdx.x;
-    int refine_f = -1, f = 0, rb = 0;
-    long long tile = 0;
-    if (b < lead) {
-        refine_f = b;
-    } else {
-        auto group_start = [&](int g) { return (long long)lead + (long long)row_blocks * files[g].tile0 + min(g, n_files - lead); };
-        int lo_f = 0, hi_f = n_files - 1;
-        while (lo_f < hi_f) {
-            const int mid = (lo_f + hi_f + 1) >> 1;
-            if (group_start(mid) <= b) lo_f = mid; else hi_f = mid - 1;
-        }
-        f = lo_f;
-        int r = (int)(b - group_start(f));
-        const int has_ref = (f + lead < n_files) ? 1 : 0;
-        if (has_ref && r == 0) {
-            refine_f = f + lead;
-        } else {
-            r -= has_ref;
-            tile = files[f].tile0 + r / row_blocks;
-            rb = r % row_blocks;
-        }
-    }
-#ifdef NBM_WS_TIMING
-    if (b == 0 && threadIdx.x == 0) follow_dbg[0] = gtime();
-#endif
-    if (refine_f >= 0) {
-#ifdef NBM_WS_TIMING
-        if (threadIdx.x == 0 && refine_f < 2048) follow_files[0][refine_f] = gtime();
-#endif
-        wait_flag_ge(file_done + refine_f, files[refine_f].done_target);
-#ifdef NBM_WS_TIMING
-        if (threadIdx.x == 0 && refine_f < 2048) follow_files[1][refine_f] = gtime();
-        if (threadIdx.x == 0 && (refine_f == 0 || refine_f == n_files / 2)) follow_dbg[refine_f == 0 ? 1 : 2] = gtime();
-#endif
-        refine_file(R, segs, files, tile_mm, spec, pcm, NBM_PCM_INT16, 1, minmax, refine_f);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence();
-            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(mm_ready + refine_f), "r"(1u) : "memory");
-        }
-        return;
-    }
-    wait_flag_ge(mm_ready + f, 1u);
-    const float smin = __ldcg(minmax + 2 * f), smax = __ldcg(minmax + 2 * f + 1);
-    tile_block<VEC4, true>(P, files[f], tile, rb, smin, smax, spec, tiles);
-#ifdef NBM_WS_TIMING
-    if (b == gridDim.x - 1 && threadIdx.x == 0) follow_dbg[3] = gtime();
-#endif
-}
-
 // Dataset images (prepare_dataset.py:85: np.round(img * 255).astype(np.uint8)): round-half-even of the normalised
 // tile value times 255.  Pure streaming pass, 4 B read + 1 B written per pixel.
 __global__ void __launch_bounds__(256)
@@ -639,21 +696,21 @@ struct nbm_frontend_plan {
     cudaEvent_t staged = nullptr;
     // optional per-kernel timing (nbm_frontend_set_profiling)
     bool profiling = false;
-    static constexpr int MAX_SUB = 8;          // sub-batches of a run: tiling of sub-batch g overlaps the transform of g+1
-    cudaEvent_t ev[MAX_SUB][5] = {};           // per sub-batch: anchors | slides (or the CUDA-core STFT) | min/max | tiles
-    int ev_subs = 0;
+    cudaEvent_t ev[5] = {};                    // anchors | slides (or the CUDA-core STFT) | refinement + min/max | tiles
+
     double acc_ms[4] = {0.0, 0.0, 0.0, 0.0};
     long long acc_runs = 0;
     bool ev_pending = false;
-    // the transform runs on a high-priority side stream so that its persistent CTAs are placed ahead of the
-    // bandwidth-bound tiling kernel of the previous sub-batch, which stays on the caller's stream
+    // the transform runs on a high-priority side stream
     cudaStream_t s_hi = nullptr;
-    cudaEvent_t ev_in = nullptr, ev_sub[MAX_SUB] = {};
-    bool overlap = false;
-    int fused_ahead = 4;        // files by which a file's min/max block runs ahead of its tiling blocks (fused tiling)
-    bool fused = false;         // NBM_FRONTEND_FUSED=1: tiling follows the transform file by file inside one launch window
-    CUresult (*wait_value32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
-    int sub_groups = 8192;      // least 64-frame groups per sub-batch
+    cudaEvent_t ev_in = nullptr, ev_done = nullptr;
+    double2 *d_tw64 = nullptr;  // [n_fft] float64 twiddles of the refinement pass
+    double *d_hann64 = nullptr; // [n_fft] float64 periodic Hann window / 32768
+    float flag_rel_db = -62.0f; // a pixel this far below the largest |R| its bin carried is recomputed in float64 (NBM_REFINE_REL_DB)
+    double cand_frac = 0.004;   // candidate list capacity as a fraction of the batch's pixels
+    const unsigned int *last_count = nullptr;   // device counter of the last run's list (nbm_frontend_last_listed)
+    unsigned int last_cap = 0;
+    cudaStream_t last_stream = nullptr;
 };
 
 namespace {
@@ -661,7 +718,7 @@ namespace {
 // Everything the host derives from the per-file sample counts: STFT chunks (prepare_dataset.py:236),
 // detector windows (:266) with the last window's valid width (:268-278 incl. the seam quirk), the
 // 64-frame groups, and the workspace carve-up
-//   [segs | files | min/max partials | anchors | dB bands].
+//   [segs | files | per-file exact minima + candidate counter | min/max partials | flag levels | candidates | anchors | dB bands].
 struct BatchLayout {
     std::vector<SegDesc> segs;
     std::vector<FileDesc> files;
@@ -669,7 +726,8 @@ struct BatchLayout {
     size_t spec_floats = 0;
     long long tiles = 0, n_anchors = 0;
     int groups = 0;
-    size_t o_segs = 0, o_files = 0, o_flags = 0, o_mm = 0, o_anchors = 0, o_spec = 0, total = 0;
+    size_t o_segs = 0, o_files = 0, o_cnt = 0, o_mm = 0, o_flag = 0, o_cand = 0, o_anchors = 0, o_spec = 0, total = 0;
+    unsigned int cand_cap = 0;
     size_t upload_bytes = 0;       // segs and files are uploaded from the host
 };
 
@@ -695,6 +753,7 @@ int build_layout(const nbm_frontend_plan *pl, const int64_t *sizes, const int64_
             sd.n_samples = len;
             sd.spec_off = 0;                                         // patched below (needs row_stride)
             sd.n_frames = (int)(1 + len / p.hop);
+            NBM_REQUIRE(sd.n_frames <= GROUP_MAX_FRAME, "STFT chunk of file %d has too many frames", f);
             sd.row_stride = 0;
             sd.file = f;
             sd.group0 = B.groups;
@@ -727,7 +786,6 @@ int build_layout(const nbm_frontend_plan *pl, const int64_t *sizes, const int64_
             last_width = (int)(edge + B.segs[i].n_frames - start);
         }
         fd.n_groups = B.groups - fd.group0;
-        fd.done_target = pl->tc ? (unsigned int)(fd.n_groups * 2 * tc_units_per_chain(pl->tc)) : 0u;
         fd.n_segs = (int)B.segs.size() - fd.seg0;
         fd.row_stride = (int)stride;
         fd.n_tiles = (int)nt;
@@ -742,11 +800,14 @@ int build_layout(const nbm_frontend_plan *pl, const int64_t *sizes, const int64_
     B.o_segs = take(B.segs.size() * sizeof(SegDesc));
     B.o_files = take(B.files.size() * sizeof(FileDesc));
     B.upload_bytes = o;
-    B.o_flags = take(((size_t)n_files * 2 + 1) * sizeof(unsigned int));  // file_done | mm_ready | slide CTAs started (fused tiling)
+    B.o_cnt = take(((size_t)n_files + 1) * sizeof(unsigned int));    // per-file exact minimum (ordered uint) | candidates listed
     B.o_mm = take((size_t)B.groups * (pl->tc ? (GF / tc_chain_frames()) * tc_n_ranges(pl->tc) * tc_slots_per_range() : 1) *
                   sizeof(float2));                                  // min/max partials
+    B.o_flag = take(pl->tc ? (size_t)B.groups * 2 * tc_n_ranges(pl->tc) * tc_slots_per_range() * sizeof(float) : 0);   // flag level per (chain, range, emit warp)
+    B.cand_cap = (unsigned int)std::min<double>(64.0 * 1024 * 1024, std::max<double>(65536.0, pl->cand_frac * (double)B.spec_floats));
+    B.o_cand = take((size_t)B.cand_cap * sizeof(unsigned long long));
     B.o_anchors = take(pl->tc ? tc_anchor_bytes(pl->tc, B.n_anchors) : 0);
-    B.o_spec = take(B.spec_floats * sizeof(float) + 16);         // + one vector: the fused tiling pass reads aligned 16-byte pairs
+    B.o_spec = take(B.spec_floats * sizeof(float) + 16);
     B.total = o;
     return NBM_OK;
 }
@@ -780,6 +841,10 @@ extern "C" int nbm_frontend_plan_create(const nbm_frontend_params *p, nbm_fronte
     if (e != cudaSuccess) { delete pl; return cuda_fail(e, "cudaGetDevice"); }
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, pl->device);
+    {
+        cudaFuncAttributes fa{};
+        if (cudaFuncGetAttributes(&fa, stft_db_kernel) == cudaSuccess) max_smem -= (int)fa.sharedSizeBytes;   // static part
+    }
     if ((size_t)max_smem < pl->smem_bytes) {
         set_error("front-end needs %zu B of shared memory per block, device offers %d", pl->smem_bytes, max_smem);
         delete pl;
@@ -807,38 +872,30 @@ extern "C" int nbm_frontend_plan_create(const nbm_frontend_params *p, nbm_fronte
         cudaDeviceGetStreamPriorityRange(&lo, &hi);             // hi = numerically lowest = greatest priority
         e = cudaStreamCreateWithPriority(&pl->s_hi, cudaStreamNonBlocking, hi);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_in, cudaEventDisableTiming);
-        for (auto &ev : pl->ev_sub)
-            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_done, cudaEventDisableTiming);
         if (e != cudaSuccess) { int rc = cuda_fail(e, "plan_create(streams)"); nbm_frontend_plan_destroy(pl); return rc; }
-        // Off by default: measured on B200 the two kernels contend for the L1 / LSU data path and the
-        // power cap, and the tiling kernel, squeezed to two CTAs per SM, loses its memory-level parallelism.
-        const char *ov = getenv("NBM_FRONTEND_OVERLAP");
-        pl->overlap = ov && strcmp(ov, "1") == 0;
-        const char *sg = getenv("NBM_FRONTEND_SUB_GROUPS");
-        pl->sub_groups = sg ? std::max(1, atoi(sg)) : 8192;
-        const char *fu = getenv("NBM_FRONTEND_FUSED");
-        pl->fused = fu && strcmp(fu, "1") == 0;
-        const char *fa = getenv("NBM_FRONTEND_FUSED_AHEAD");
-        if (fa) pl->fused_ahead = std::max(1, atoi(fa));
-        if (pl->fused) {
-            void *fn = nullptr;
-            cudaDriverEntryPointQueryResult qr;
-            if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn ||
-                qr != cudaDriverEntryPointSuccess) {
-                cudaGetLastError();
-                pl->fused = false;          // no stream memory operations on this driver: keep the plain launch sequence
-            }
-            pl->wait_value32 = reinterpret_cast<CUresult (*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int)>(fn);
+        const char *rd = getenv("NBM_REFINE_REL_DB");          // diagnostic: how far below the frame's level a pixel is flagged
+        if (rd) pl->flag_rel_db = (float)atof(rd);
+        const char *cf = getenv("NBM_REFINE_CAND_FRAC");
+        if (cf) pl->cand_frac = std::min(0.5, std::max(1e-6, atof(cf)));
+    }
+    {
+        // float64 twiddles of the refinement pass
+        std::vector<double2> t64(p->n_fft);
+        for (int q = 0; q < p->n_fft; ++q) {
+            const double ang = 2.0 * M_PI * (double)q / (double)p->n_fft;
+            t64[q] = make_double2(cos(ang), sin(ang));
         }
-        if (pl->fused) {
-            cudaFuncSetAttribute(tile_follow_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            cudaFuncSetAttribute(tile_follow_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        }
-        if (pl->overlap) {
-            // to share an SM with the persistent slide kernel (maximum shared-memory carve-out) the tiling kernel
-            // has to ask for the same L1 / shared memory split
-            cudaFuncSetAttribute(tile_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            cudaFuncSetAttribute(tile_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        // scipy.signal.get_window('hann', N, fftbins=True) = 0.5 - 0.5 cos(2 pi n / N), here pre-divided by 32768
+        std::vector<double> h64(p->n_fft);
+        for (int q = 0; q < p->n_fft; ++q) h64[q] = (0.5 - 0.5 * cos(2.0 * M_PI * (double)q / (double)p->n_fft)) / 32768.0;
+        if ((e = cudaMalloc(&pl->d_tw64, t64.size() * sizeof(double2))) != cudaSuccess ||
+            (e = cudaMemcpy(pl->d_tw64, t64.data(), t64.size() * sizeof(double2), cudaMemcpyHostToDevice)) != cudaSuccess ||
+            (e = cudaMalloc(&pl->d_hann64, h64.size() * sizeof(double))) != cudaSuccess ||
+            (e = cudaMemcpy(pl->d_hann64, h64.data(), h64.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) {
+            int rc = cuda_fail(e, "plan_create(tw64)");
+            nbm_frontend_plan_destroy(pl);
+            return rc;
         }
     }
     // tensor-core path unless the parameters do not fit it or NBM_FRONTEND_IMPL=cuda-core asks for the other one
@@ -856,9 +913,11 @@ extern "C" int nbm_frontend_plan_destroy(nbm_frontend_plan *pl) {
     if (pl->d_tw) cudaFree(pl->d_tw);
     if (pl->h_stage) cudaFreeHost(pl->h_stage);
     if (pl->staged) cudaEventDestroy(pl->staged);
-    for (auto &row : pl->ev) for (auto &e : row) if (e) cudaEventDestroy(e);
-    for (auto &e : pl->ev_sub) if (e) cudaEventDestroy(e);
+    for (auto &e : pl->ev) if (e) cudaEventDestroy(e);
     if (pl->ev_in) cudaEventDestroy(pl->ev_in);
+    if (pl->ev_done) cudaEventDestroy(pl->ev_done);
+    if (pl->d_tw64) cudaFree(pl->d_tw64);
+    if (pl->d_hann64) cudaFree(pl->d_hann64);
     if (pl->s_hi) cudaStreamDestroy(pl->s_hi);
     tc_plan_destroy(pl->tc);
     delete pl;
@@ -904,13 +963,11 @@ extern "C" int nbm_frontend_spectrogram_view(const nbm_frontend_plan *pl, const 
 // fold the previous profiled run's event pairs into the accumulators (waits for that run)
 static int collect_profile(nbm_frontend_plan *pl) {
     if (!pl->ev_pending) return NBM_OK;
-    for (int g = 0; g < pl->ev_subs; ++g) {
-        NBM_CUDA(cudaEventSynchronize(pl->ev[g][4]));
-        for (int i = 0; i < 4; ++i) {
-            float ms = 0.f;
-            NBM_CUDA(cudaEventElapsedTime(&ms, pl->ev[g][i], pl->ev[g][i + 1]));
-            pl->acc_ms[i] += ms;
-        }
+    NBM_CUDA(cudaEventSynchronize(pl->ev[4]));
+    for (int i = 0; i < 4; ++i) {
+        float ms = 0.f;
+        NBM_CUDA(cudaEventElapsedTime(&ms, pl->ev[i], pl->ev[i + 1]));
+        pl->acc_ms[i] += ms;
     }
     pl->acc_runs += 1;
     pl->ev_pending = false;
@@ -920,8 +977,8 @@ static int collect_profile(nbm_frontend_plan *pl) {
 extern "C" int nbm_frontend_set_profiling(nbm_frontend_plan *pl, int32_t enable) {
     NBM_REQUIRE(pl, "null plan");
     std::lock_guard<std::mutex> lock(pl->mu);
-    if (enable && !pl->ev[0][0])
-        for (auto &row : pl->ev) for (auto &e : row) NBM_CUDA(cudaEventCreate(&e));
+    if (enable && !pl->ev[0])
+        for (auto &e : pl->ev) NBM_CUDA(cudaEventCreate(&e));
     pl->profiling = enable != 0;
     for (auto &a : pl->acc_ms) a = 0.0;
     pl->acc_runs = 0; pl->ev_pending = false;
@@ -1001,105 +1058,71 @@ extern "C" int nbm_frontend_run_batch(const nbm_frontend_plan *cpl, const void *
     RefineParams rp;
     rp.N = p.n_fft; rp.hop = p.hop; rp.low_idx = p.low_idx; rp.n_bins = p.n_bins;
     rp.mm_frames = use_tc ? tc_chain_frames() : GF;
-    rp.n_ranges = use_tc ? tc_n_ranges(pl->tc) : 1;
+    rp.mm_per_group = use_tc ? tc_n_ranges(pl->tc) * tc_slots_per_range() : 1;
     rp.slots_per_range = use_tc ? tc_slots_per_range() : 1;
     rp.bins_per_range = use_tc ? tc_bins_per_range() : p.n_bins;
     rp.bins_per_slot = use_tc ? tc_bins_per_slot() : p.n_bins;
-    rp.min_level = p.min_level;
     rp.margin_db = 0.25f;
+    rp.min_level = p.min_level;
+    rp.n_ranges = use_tc ? tc_n_ranges(pl->tc) : 0;
+    rp.tw64 = pl->d_tw64;
+    rp.hann64 = pl->d_hann64;
+    float *d_flag = reinterpret_cast<float *>(ws + B.o_flag);
+    auto *d_cand = reinterpret_cast<unsigned long long *>(ws + B.o_cand);
+    unsigned int *d_file_min = reinterpret_cast<unsigned int *>(ws + B.o_cnt), *d_cand_count = d_file_min + n_files;
 
-    // Optional (NBM_FRONTEND_OVERLAP=1): sub-batches of whole files, balanced by 64-frame groups.  Per sub-batch
-    // the transform (anchors, slides, min/max) runs on the plan's high-priority stream and the HBM-bound tiling on
-    // the caller's stream behind an event, so tiling of sub-batch g overlaps the transform of g+1 (the slide kernel
-    // leaves room for two tiling CTAs per SM).  With one sub-batch this degenerates to the plain launch sequence.
-    int n_sub = 1;
-    if (pl->overlap) n_sub = std::max(1, std::min({(int)nbm_frontend_plan::MAX_SUB, n_files, B.groups / pl->sub_groups}));
-    std::vector<int> cut(n_sub + 1, n_files);
-    cut[0] = 0;
-    for (int g = 1, f = 0; g < n_sub; ++g) {
-        const long long want = (long long)B.groups * g / n_sub;
-        while (f < n_files && B.files[f].group0 < want) ++f;
-        cut[g] = std::max(f, cut[g - 1]);
-    }
+    // caller's stream: descriptors ............................................................. | tiles
+    // side stream:                 | anchors -> slides -> float64 refinement -> min/max |
     NBM_CUDA(cudaEventRecord(pl->ev_in, stream));              // inputs and descriptors are ready on the caller's stream
-    NBM_CUDA(cudaStreamWaitEvent(pl->s_hi, pl->ev_in, 0));
     cudaStream_t sc = pl->s_hi;
-    if (use_tc && pl->fused) {
-        // anchors -> slide kernel (96 registers, publishes per-file completion) on the priority stream; the tiling
-        // kernel starts on the caller's stream as soon as the anchors are done and follows the transform file by file
-        unsigned int *d_flags = reinterpret_cast<unsigned int *>(ws + B.o_flags);
-        NBM_CUDA(cudaMemsetAsync(d_flags, 0, ((size_t)n_files * 2 + 1) * sizeof(unsigned int), sc));
-        if (prof) NBM_CUDA(cudaEventRecord(pl->ev[0][0], sc));
+    NBM_CUDA(cudaStreamWaitEvent(sc, pl->ev_in, 0));
+    NBM_CUDA(cudaMemsetAsync(d_file_min, 0xff, (size_t)n_files * sizeof(unsigned int), sc));
+    NBM_CUDA(cudaMemsetAsync(d_cand_count, 0, sizeof(unsigned int), sc));
+    if (prof) NBM_CUDA(cudaEventRecord(pl->ev[0], sc));
+    if (use_tc) {
+        // globally numbered anchors: segment s owns group0[s] + s .. group0[s] + s + tiles[s]
         rc = tc_launch_anchors(pl->tc, d_segs, 0, (int)B.segs.size(), 0, B.n_anchors, d_pcm, ws + B.o_anchors, sc);
         if (rc != NBM_OK) return rc;
-        if (prof) NBM_CUDA(cudaEventRecord(pl->ev[0][1], sc));
-        NBM_CUDA(cudaEventRecord(pl->ev_sub[1], sc));
-        NBM_CUDA(cudaStreamWaitEvent(stream, pl->ev_sub[1], 0));
-        int slide_grid = 0;
-        rc = tc_launch_slides(pl->tc, d_segs, (int)B.segs.size(), 0, 0, B.groups, d_pcm, d_spec, d_tile_mm, ws + B.o_anchors,
-                              d_flags, d_flags + 2 * n_files, &slide_grid, sc);
+        if (prof) NBM_CUDA(cudaEventRecord(pl->ev[1], sc));
+        rc = tc_launch_slides(pl->tc, d_segs, (int)B.segs.size(), 0, 0, B.groups, d_pcm, d_spec, d_tile_mm,
+                              ws + B.o_anchors, d_flag, pl->flag_rel_db, d_cand, d_cand_count, B.cand_cap, sc);
         if (rc != NBM_OK) return rc;
-        // the caller's stream waits (in hardware) until every slide CTA is resident; only then may tiling blocks be
-        // placed -- they fill what is left of each SM (two per SM) instead of taking the SMs first
-        {
-            const CUresult cr = pl->wait_value32((CUstream)stream, (CUdeviceptr)(uintptr_t)(d_flags + 2 * n_files),
-                                                 (cuuint32_t)slide_grid, CU_STREAM_WAIT_VALUE_GEQ);
-            if (cr != CUDA_SUCCESS) { set_error("cuStreamWaitValue32 failed (%d)", (int)cr); return NBM_ERR_CUDA; }
-        }
-        // profile: anchors | slide kernel | 0 | what is left of the tiling pass after the slide kernel has ended
-        if (prof) { NBM_CUDA(cudaEventRecord(pl->ev[0][2], sc)); NBM_CUDA(cudaEventRecord(pl->ev[0][3], sc)); }
-        const int row_blocks = (p.n_bins + TILE_ROWS - 1) / TILE_ROWS;
-        const unsigned int blocks = (unsigned int)(B.tiles * row_blocks + n_files);
-        const int ahead = pl->fused_ahead;
-        if (p.w_pix % 4 == 0)
-            tile_follow_kernel<true><<<blocks, 256, 0, stream>>>(pl->kp, rp, d_segs, d_files, n_files, d_tile_mm, d_spec, d_pcm,
-                                                                 d_minmax, d_tiles, d_flags, d_flags + n_files, row_blocks, ahead);
-        else
-            tile_follow_kernel<false><<<blocks, 256, 0, stream>>>(pl->kp, rp, d_segs, d_files, n_files, d_tile_mm, d_spec, d_pcm,
-                                                                  d_minmax, d_tiles, d_flags, d_flags + n_files, row_blocks, ahead);
-        if (prof) { NBM_CUDA(cudaEventRecord(pl->ev[0][4], stream)); pl->ev_subs = 1; pl->ev_pending = true; }
-        NBM_CUDA(cudaEventRecord(pl->ev_sub[0], sc));
-        NBM_CUDA(cudaStreamWaitEvent(stream, pl->ev_sub[0], 0));
-        NBM_CUDA(cudaGetLastError());
-        return NBM_OK;
+    } else {
+        if (prof) NBM_CUDA(cudaEventRecord(pl->ev[1], sc));
+        stft_db_kernel<<<B.groups, pl->n_threads, pl->smem_bytes, sc>>>(pl->kp, d_segs, (int)B.segs.size(), d_pcm, pcm_dtype,
+                                                                        channels, d_spec, d_tile_mm, 0, pl->flag_rel_db, d_cand,
+                                                                        d_cand_count, B.cand_cap);
     }
-    int sub = 0;
-    for (int g = 0; g < n_sub; ++g) {
-        const int f0 = cut[g], f1 = cut[g + 1];
-        if (f1 <= f0) continue;
-        const FileDesc &fa = B.files[f0], &fz = B.files[f1 - 1];
-        const int seg0 = fa.seg0, seg1 = fz.seg0 + fz.n_segs;
-        const int grp0 = fa.group0, grp1 = fz.group0 + fz.n_groups;
-        const long long tile0 = fa.tile0, tile1 = fz.tile0 + fz.n_tiles;
-        if (prof) NBM_CUDA(cudaEventRecord(pl->ev[sub][0], sc));
-        if (use_tc) {
-            // globally numbered anchors of these segments: group0[s] + s .. group0[s] + s + tiles[s]
-            rc = tc_launch_anchors(pl->tc, d_segs, seg0, seg1, (long long)grp0 + seg0, (long long)grp1 + seg1, d_pcm,
-                                   ws + B.o_anchors, sc);
-            if (rc != NBM_OK) return rc;
-            if (prof) NBM_CUDA(cudaEventRecord(pl->ev[sub][1], sc));
-            rc = tc_launch_slides(pl->tc, d_segs, (int)B.segs.size(), seg0, grp0, grp1, d_pcm, d_spec, d_tile_mm,
-                                  ws + B.o_anchors, nullptr, nullptr, nullptr, sc);
-            if (rc != NBM_OK) return rc;
-        } else {
-            if (prof) NBM_CUDA(cudaEventRecord(pl->ev[sub][1], sc));
-            stft_db_kernel<<<grp1 - grp0, pl->n_threads, pl->smem_bytes, sc>>>(pl->kp, d_segs, (int)B.segs.size(), d_pcm,
-                                                                               pcm_dtype, channels, d_spec, d_tile_mm, grp0);
-        }
-        if (prof) NBM_CUDA(cudaEventRecord(pl->ev[sub][2], sc));
-        refine_minmax_kernel<<<f1 - f0, 256, 0, sc>>>(rp, d_segs, d_files, d_tile_mm, d_spec, d_pcm, pcm_dtype, channels,
-                                                     d_minmax, f0);
-        NBM_CUDA(cudaEventRecord(pl->ev_sub[sub], sc));
-        NBM_CUDA(cudaStreamWaitEvent(stream, pl->ev_sub[sub], 0));
-        if (prof) NBM_CUDA(cudaEventRecord(pl->ev[sub][3], stream));
-        dim3 grid((unsigned)(tile1 - tile0), (unsigned)((p.n_bins + TILE_ROWS - 1) / TILE_ROWS));
-        if (p.w_pix % 4 == 0) tile_kernel<true><<<grid, 256, 0, stream>>>(pl->kp, d_files, n_files, d_spec, d_minmax, d_tiles, tile0);
-        else tile_kernel<false><<<grid, 256, 0, stream>>>(pl->kp, d_files, n_files, d_spec, d_minmax, d_tiles, tile0);
-        if (prof) NBM_CUDA(cudaEventRecord(pl->ev[sub][4], stream));
-        ++sub;
+    if (prof) NBM_CUDA(cudaEventRecord(pl->ev[2], sc));
+    {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
+        refine_groups_kernel<<<sms * 4, 256, 0, sc>>>(rp, d_segs, d_cand, d_cand_count, B.cand_cap, d_flag, d_spec, d_pcm,
+                                                     pcm_dtype, channels, d_file_min);
+        minmax_kernel<<<n_files, 256, 0, sc>>>(rp, d_segs, d_files, d_tile_mm, d_file_min, d_spec, d_pcm, pcm_dtype, channels,
+                                               d_minmax, 0);
     }
-    if (prof) { pl->ev_subs = sub; pl->ev_pending = true; }
+    pl->last_count = d_cand_count; pl->last_cap = B.cand_cap; pl->last_stream = stream;
+    NBM_CUDA(cudaEventRecord(pl->ev_done, sc));
+    NBM_CUDA(cudaStreamWaitEvent(stream, pl->ev_done, 0));
+    if (prof) NBM_CUDA(cudaEventRecord(pl->ev[3], stream));
+    dim3 grid((unsigned)B.tiles, (unsigned)((p.n_bins + TILE_ROWS - 1) / TILE_ROWS));
+    if (p.w_pix % 4 == 0) tile_kernel<true><<<grid, 256, 0, stream>>>(pl->kp, d_files, n_files, d_spec, d_minmax, d_tiles, 0);
+    else tile_kernel<false><<<grid, 256, 0, stream>>>(pl->kp, d_files, n_files, d_spec, d_minmax, d_tiles, 0);
+    if (prof) { NBM_CUDA(cudaEventRecord(pl->ev[4], stream)); pl->ev_pending = true; }
     NBM_CUDA(cudaGetLastError());
+    return NBM_OK;
+}
+
+extern "C" int nbm_frontend_last_listed(nbm_frontend_plan *pl, int64_t *listed, int64_t *capacity) {
+    NBM_REQUIRE(pl && listed && capacity, "null argument");
+    std::lock_guard<std::mutex> lock(pl->mu);
+    NBM_REQUIRE(pl->last_count, "no run yet");
+    unsigned int n = 0;
+    NBM_CUDA(cudaStreamSynchronize(pl->last_stream));
+    NBM_CUDA(cudaMemcpy(&n, pl->last_count, sizeof(n), cudaMemcpyDeviceToHost));
+    *listed = n;
+    *capacity = pl->last_cap;
     return NBM_OK;
 }
 

@@ -39,7 +39,7 @@ struct TcParams {
     float min_level_sq;
     const __half *a_slide;      // [n_ranges][128 rows][cos_h, cos_l, sin_h, sin_l][KP], row-contiguous (copied into TMEM lanes)
     const __half *a_anchor;     // [n_ranges][n_stages][cos_h, cos_l, sin_h, sin_l][128 x AKB] UMMA layout
-    const float2 *cf, *gf, *gb, *rot;   // [n_ranges*128] per-bin constants
+    const float2 *cf, *gf, *gb, *rot, *cfix;   // [n_ranges*128] per-bin constants (cfix: see the recurrence)
 };
 
 struct TcPlan {
@@ -454,6 +454,7 @@ constexpr int TM_ACC_PER_GROUP = 2 * CF;    // (cos, sin) accumulators of a grou
 constexpr int NK_T = 5;                     // k-steps whose twiddles fit in TMEM next to the accumulators (any further one is
                                             // read from shared memory, at 4 KB per MMA)
 constexpr int TM_COLS = 512;
+constexpr int FIX_EVERY = 4;                // recurrence steps between two corrections of the twiddle's rounding error
 
 // group-local barrier of 128 threads.  The id must be a literal: with a register id the compiler reserves all 16
 // hardware barriers for the CTA, and a kernel that needs a barrier of its own can then no longer share the SM.
@@ -503,17 +504,35 @@ constexpr int WS_G = 3;
 constexpr int WS_THREADS = 32 * (4 * WS_G + 1 + WS_G);
 constexpr int PV = 11;                      // 16-byte PCM vectors per fill lane per round (two rounds per chain)
 
-// file_done (optional): per-file count of finished (chain, range, emit warp) units, published with release semantics
-// when a warp moves on to another file -- the tiling kernel that follows the transform file by file waits on it.
-template <int PS>                           // shifted-path vectors per fill lane per round (register budget)
+constexpr int PS = 4;                       // shifted-path vectors per fill lane per round (register budget)
+
+// Pixels that a float32 transform cannot deliver within tolerance are FLAGGED here and recomputed in float64 by
+// refine_groups_kernel (frontend.cu).  Measured (scripts/fe_outliers.py): the absolute error of a pixel is float32
+// rounding, ~2^-24 rms and < ~2e-6 worst, of the LARGEST rectangular-window magnitude |R_t[k]| its bin carried along the
+// chain -- the recurrence is an integrator, so what a loud call leaves behind when it sweeps through a bin stays in that
+// bin until the next anchor.  In dB this is invisible unless the pixel itself lies ~60 dB below that magnitude (a deep
+// null, or a quiet frame right after a loud one).  The recurrence therefore tracks max |R| per bin (one FMNMX3 per step);
+// each emit warp takes the largest over its 32 rows and their halo as its reference, writes the resulting level
+// flag_db[(chain, range, warp)] for the refinement pass, and a thread whose minimum falls below it puts its block of pixels
+// on the `cand` list (pack_group) and leaves it out of the warp's min/max partial.  When the list is full the block keeps
+// its float32 values (and stays in the partial).
+struct FlagArgs {
+    float *flag_db;                         // [chains][n_ranges][4] flag level of every (chain, range, emit warp), written here
+    float rel_db;                           // how far below the reference magnitude a pixel is flagged (negative)
+    unsigned long long *cand;
+    unsigned int *cand_count;
+    unsigned int cand_cap;
+};
+
 __device__ __forceinline__ void
 slide_ws_body(const TcParams &P, const SegDesc *__restrict__ segs, int n_segs, int seg_begin, int chain_begin, int total_chains,
               const short *__restrict__ pcm, const float2 *__restrict__ anchors,
-              float *__restrict__ spec, float2 *__restrict__ chain_mm, unsigned int *__restrict__ file_done) {
+              float *__restrict__ spec, float2 *__restrict__ chain_mm, const FlagArgs FA) {
     constexpr int G = WS_G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t acc_full[G], b_ready[G], s_full[G], s_free[G];
     __shared__ uint32_t tmem_base_s;
+    __shared__ float rmax_s[G][4];          // largest |R| of the chain per worker warp (32 bin rows), recur -> emit
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool is_worker = warp < 4 * G, is_mma_warp = warp == 4 * G;
     const int g = is_worker ? warp >> 2 : (is_mma_warp ? 0 : warp - 4 * G - 1);    // group served
@@ -761,7 +780,7 @@ slide_ws_body(const TcParams &P, const SegDesc *__restrict__ segs, int n_segs, i
     const int base = PADF + P.off + n * hop;
     const uint32_t acc_col = tmem_base + (uint32_t)g * TM_ACC_PER_GROUP;
     const uint32_t lane_sel = (uint32_t)(wq * 32) << 16;
-    const float2 cf = P.cf[range * 128 + gt];
+    const float2 cf = P.cf[range * 128 + gt], cfx = P.cfix[range * 128 + gt];
     const float2 gF = P.gf[range * 128 + gt], gB = P.gb[range * 128 + gt];
     const int r_lo = 1 + ROWS_PER_EWARP * wq;
     // rows inside the band (only the last range is cut short)
@@ -784,14 +803,22 @@ slide_ws_body(const TcParams &P, const SegDesc *__restrict__ segs, int n_segs, i
         ph = h2_as_u32(__hadd2(dhh, dlh)); pl = h2_as_u32(__hadd2(dhl, dll));
         mh = h2_as_u32(__hsub2(dhh, dlh)); ml = h2_as_u32(__hsub2(dhl, dll));
     };
+    const bool new_al8 = (N & 3) == 0;      // N % 4 == 2 (e.g. n_fft 4410): the NEW samples sit 4-byte, not 8-byte, aligned
     auto build_unit = [&](int jg) {         // thread = (frame n, pairs 8 jg .. 8 jg + 7), all live
         // 8 consecutive samples = two 8-byte loads (frames are 8-byte, not 16-byte, aligned)
         const uint2 *nh = reinterpret_cast<const uint2 *>(buf16 + base + N + half_hop + 8 * jg);
         const uint2 *oh = reinterpret_cast<const uint2 *>(buf16 + base + half_hop + 8 * jg);
         const uint2 *nl = reinterpret_cast<const uint2 *>(buf16 + base + N + half_hop - 8 - 8 * jg);
         const uint2 *ol = reinterpret_cast<const uint2 *>(buf16 + base + half_hop - 8 - 8 * jg);
-        const uint2 a0 = nh[0], a1 = nh[1], b0 = oh[0], b1 = oh[1];
-        const uint2 c0 = nl[0], c1 = nl[1], e0 = ol[0], e1 = ol[1];
+        uint2 a0, a1, c0, c1;
+        if (new_al8) {
+            a0 = nh[0]; a1 = nh[1]; c0 = nl[0]; c1 = nl[1];
+        } else {
+            const uint32_t *nh4 = reinterpret_cast<const uint32_t *>(nh), *nl4 = reinterpret_cast<const uint32_t *>(nl);
+            a0 = make_uint2(nh4[0], nh4[1]); a1 = make_uint2(nh4[2], nh4[3]);
+            c0 = make_uint2(nl4[0], nl4[1]); c1 = make_uint2(nl4[2], nl4[3]);
+        }
+        const uint2 b0 = oh[0], b1 = oh[1], e0 = ol[0], e1 = ol[1];
         const uint32_t wa[4] = {a0.x, a0.y, a1.x, a1.y}, wb[4] = {b0.x, b0.y, b1.x, b1.y};
         // the lo sample of pair jj sits at position 7 - jj of the ascending vector: words in reverse
         const uint32_t wc[4] = {c1.y, c1.x, c0.y, c0.x}, we[4] = {e1.y, e1.x, e0.y, e0.x};
@@ -841,20 +868,10 @@ slide_ws_body(const TcParams &P, const SegDesc *__restrict__ segs, int n_segs, i
         anc_next = anchor_of(first);
         build(0);
     }
-    int pub_file = -1;                      // units finished for this file and not yet published
-    unsigned int pub_cnt = 0;
-    auto publish = [&]() {
-        if (file_done != nullptr && pub_file >= 0 && pub_cnt > 0) {
-            __syncwarp();
-            if (lane == 0) { __threadfence(); atomicAdd(file_done + pub_file, pub_cnt); }
-        }
-        pub_cnt = 0;
-    };
     WS_T0();
     for (int it = 0; it < n_iters; ++it) {
         const int chain = first + it * cstride;
         cw.seek(chain);
-        if (cw.sd.file != pub_file) { publish(); pub_file = cw.sd.file; }
         const int lc = chain - 2 * cw.sd.group0;
         const int t0 = lc * CF;
         const bool fwd = (lc & 1) == 0;
@@ -869,6 +886,7 @@ slide_ws_body(const TcParams &P, const SegDesc *__restrict__ segs, int n_segs, i
             float4 *st4 = reinterpret_cast<float4 *>(stage + (size_t)gt * ST_LD);
             float Rr = anc.x, Ri = anc.y;
             float pr = Rr, pi = Ri;
+            float mR = fmaxf(fabsf(Rr), fabsf(Ri));                          // largest |R| (inf-norm) this bin carries along the chain
 #pragma unroll 1
             for (int hh = 0; hh < 2; ++hh) {          // not unrolled: the straight-line recurrence is instruction-fetch bound
                 const int c0 = fwd ? 16 * hh : 16 - 16 * hh;             // forward chains walk the columns up, backward ones down
@@ -884,9 +902,15 @@ slide_ws_body(const TcParams &P, const SegDesc *__restrict__ segs, int n_segs, i
                         if (c == CF - 1) break;
                         const float gr = gF.x * gc[i] + gF.y * gs[i];
                         const float gi = gF.y * gc[i] - gF.x * gs[i];
-                        const float nr = fmaf(cf.x, Rr, fmaf(-cf.y, Ri, gr));
-                        const float ni = fmaf(cf.x, Ri, fmaf(cf.y, Rr, gi));
+                        float nr = fmaf(cf.x, Rr, fmaf(-cf.y, Ri, gr));
+                        float ni = fmaf(cf.x, Ri, fmaf(cf.y, Rr, gi));
+                        if ((i & (FIX_EVERY - 1)) == FIX_EVERY - 1) {          // R *= rho^FIX_EVERY = 1 + cfx
+                            const float tr = fmaf(cfx.x, nr, fmaf(-cfx.y, ni, nr));
+                            ni = fmaf(cfx.x, ni, fmaf(cfx.y, nr, ni));
+                            nr = tr;
+                        }
                         Rr = nr; Ri = ni;
+                        mR = fmaxf(mR, fmaxf(fabsf(nr), fabsf(ni)));
                         if (c & 1) { pr = Rr; pi = Ri; }                       // column c+1 even: first of a pair
                         else st4[c >> 1] = make_float4(pr, pi, Rr, Ri);       // columns (c, c+1)
                     }
@@ -897,14 +921,23 @@ slide_ws_body(const TcParams &P, const SegDesc *__restrict__ segs, int n_segs, i
                         const int c = c0 + i;
                         const float gr = gB.y * gs[i] - gB.x * gc[i];
                         const float gi = gB.x * gs[i] + gB.y * gc[i];
-                        const float nr = fmaf(cf.x, Rr, fmaf(cf.y, Ri, gr));
-                        const float ni = fmaf(cf.x, Ri, fmaf(-cf.y, Rr, gi));
+                        float nr = fmaf(cf.x, Rr, fmaf(cf.y, Ri, gr));
+                        float ni = fmaf(cf.x, Ri, fmaf(-cf.y, Rr, gi));
+                        if ((i & (FIX_EVERY - 1)) == 0) {                      // R *= conj(rho)^FIX_EVERY
+                            const float tr = fmaf(cfx.x, nr, fmaf(cfx.y, ni, nr));
+                            ni = fmaf(cfx.x, ni, fmaf(-cfx.y, nr, ni));
+                            nr = tr;
+                        }
                         Rr = nr; Ri = ni;
+                        mR = fmaxf(mR, fmaxf(fabsf(nr), fabsf(ni)));
                         if (c & 1) { pr = Rr; pi = Ri; }                       // odd column: second of a pair
                         else st4[c >> 1] = make_float4(Rr, Ri, pr, pi);       // columns (c, c+1)
                     }
                 }
             }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mR = fmaxf(mR, __shfl_xor_sync(0xffffffffu, mR, o));
+            if (lane == 0) rmax_s[g][wq] = mR;
             tc_fence_before();
         }
         WS_MARK(2);
@@ -927,6 +960,10 @@ slide_ws_body(const TcParams &P, const SegDesc *__restrict__ segs, int n_segs, i
                 const int stride = cw.sd.row_stride;
                 char *out = reinterpret_cast<char *>(spec + cw.sd.spec_off + (long long)(range * BINS_PER_RANGE + ra - 1) * stride + t0 + fc);
                 const long long stride_b = (long long)stride * 4;
+                // flag level of this warp's rows (r_lo .. r_lo + 31 and their halo live in recur warps wq and wq + 1):
+                // 20 log10(|R|max) + rel_db; -inf for a silent chain
+                const float th = fmaf(fast_log2(fmaxf(rmax_s[g][wq], rmax_s[g][min(wq + 1, 3)])), 6.0205999132796239f, FA.rel_db);
+                if (lane == 0) FA.flag_db[((size_t)chain * P.n_ranges + range) * 4 + wq] = th;
                 const bool pair_ok = (cw.sd.spec_off & 1) == 0;          // a later STFT chunk of a long file may start on an odd column
                 // 4 X = 2 R[k] - (R[k-1] + R[k+1]);  10 log10(|X|^2) = 10 log10(|4X|^2) - 10 log10(16)
                 auto row_db = [&](const float4 &nx, float &db0, float &db1) {
@@ -972,6 +1009,18 @@ slide_ws_body(const TcParams &P, const SegDesc *__restrict__ segs, int n_segs, i
                         pv = cu; cu = nx;
                     }
                 }
+                if (vmin < th) {
+                    // rare: some pixel of this thread lies below the chain's flag level.  The thread's block of pixels
+                    // (rb - ra rows x min(nfr, 2) frames) goes on the list as ONE entry -- refine_groups_kernel finds the
+                    // flagged pixels in it, recomputes them in float64 and folds the block's exact minimum into the file's --
+                    // and the block stays out of this warp's min/max partial.  No loop here: the other three warps of the
+                    // group wait for this one at the barrier below.
+                    const unsigned int at = atomicAdd(FA.cand_count, 1u);
+                    if (at < FA.cand_cap) {
+                        FA.cand[at] = pack_group(cw.seg_idx, range * BINS_PER_RANGE + ra - 1, rb - ra, nfr > 1 ? 2 : 1, t0 + fc);
+                        vmin = INFINITY;
+                    }
+                }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -979,13 +1028,11 @@ slide_ws_body(const TcParams &P, const SegDesc *__restrict__ segs, int n_segs, i
                 vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
             }
             if (lane == 0) chain_mm[((size_t)chain * P.n_ranges + range) * 4 + wq] = make_float2(vmin, vmax);
-            ++pub_cnt;
         }
         WS_MARK(5);
         named_bar_sync(bar_id, 128);        // stage free for the next recurrence
         WS_MARK(6);
     }
-    publish();
     WS_FLUSH(0);
     }
     tc_fence_before();
@@ -996,28 +1043,8 @@ slide_ws_body(const TcParams &P, const SegDesc *__restrict__ segs, int n_segs, i
 __global__ void __launch_bounds__(WS_THREADS, 1)
 slide_ws_kernel(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int seg_begin, int chain_begin, int total_chains,
                 const short *__restrict__ pcm, const float2 *__restrict__ anchors,
-                float *__restrict__ spec, float2 *__restrict__ chain_mm) {
-    slide_ws_body<4>(P, segs, n_segs, seg_begin, chain_begin, total_chains, pcm, anchors, spec, chain_mm, nullptr);
-}
-
-#ifdef NBM_WS_TIMING
-#define WS_STAMP(i) if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); ws_dbg[i] = t; }
-#else
-#define WS_STAMP(i)
-#endif
-
-// The same kernel held to 96 registers, so that two CTAs of the tiling kernel fit on the SM beside it.
-__global__ void __maxnreg__(96)
-slide_ws_kernel_shared_sm(TcParams P, const SegDesc *__restrict__ segs, int n_segs, int seg_begin, int chain_begin, int total_chains,
-                          const short *__restrict__ pcm, const float2 *__restrict__ anchors,
-                          float *__restrict__ spec, float2 *__restrict__ chain_mm, unsigned int *__restrict__ file_done,
-                          unsigned int *__restrict__ started) {
-    // the tiling kernel is released (stream wait on this counter) only once every CTA of this grid is resident:
-    // if its blocks took the SMs first, they would wait forever for files these CTAs could then never produce
-    if (threadIdx.x == 0) atomicAdd(started, 1u);
-    WS_STAMP(24);
-    slide_ws_body<1>(P, segs, n_segs, seg_begin, chain_begin, total_chains, pcm, anchors, spec, chain_mm, file_done);
-    WS_STAMP(25);
+                float *__restrict__ spec, float2 *__restrict__ chain_mm, FlagArgs FA) {
+    slide_ws_body(P, segs, n_segs, seg_begin, chain_begin, total_chains, pcm, anchors, spec, chain_mm, FA);
 }
 
 }  // namespace nbm
@@ -1039,7 +1066,7 @@ int nbm::tc_plan_create(const nbm_frontend_params &p, TcPlan **out) {
     *out = nullptr;
     const int N = p.n_fft, hop = p.hop;
     const int npH = hop / 2, KP = ((npH + 15) / 16) * 16;
-    const bool ok = (N % 4 == 0) && (hop % 4 == 0) && KP / 16 <= NK_T && hop >= 8 && p.n_bins <= 3 * BINS_PER_RANGE &&
+    const bool ok = (N % 2 == 0) && (hop % 4 == 0) && KP / 16 <= NK_T && hop >= 8 && p.n_bins <= 3 * BINS_PER_RANGE &&
                     p.low_idx >= 1 && N >= 2 * hop;
     if (!ok) return NBM_ERR_UNSUPPORTED;
     auto *pl = new TcPlan();
@@ -1056,7 +1083,7 @@ int nbm::tc_plan_create(const nbm_frontend_params &p, TcPlan **out) {
     const size_t slide_elems = (size_t)R * 4 * 128 * KP;
     const size_t anchor_elems = (size_t)R * k.n_stages * 4 * 128 * AKB;
     std::vector<__half> a_slide(slide_elems, __float2half_rn(0.f)), a_anchor(anchor_elems, __float2half_rn(0.f));
-    std::vector<float2> cf(R * 128), gf(R * 128), gb(R * 128), rot(R * 128);
+    std::vector<float2> cf(R * 128), gf(R * 128), gb(R * 128), rot(R * 128), cfix(R * 128);
     auto ang = [&](long long q) { return M_PI * (double)(q % N2) / (double)N; };
     const double s18 = 1.0 / 262144.0;        // byte planes (value / 256) x twiddles x 2^11, samples / 32768
     for (int r = 0; r < R; ++r)
@@ -1082,6 +1109,15 @@ int nbm::tc_plan_create(const nbm_frontend_params &p, TcPlan **out) {
             const int i = r * 128 + row;
             double a = ang(kbin * 2 * hop);
             cf[i] = make_float2((float)cos(a), (float)sin(a));
+            {
+                // the float32 twiddle is off by rho = cf_true / cf_f32 in EVERY step of the recurrence, a systematic error
+                // that grows linearly along the chain; every FIX_EVERY steps the recurrence multiplies by rho^FIX_EVERY
+                const double cr = (double)cf[i].x, ci = (double)cf[i].y, d2 = cr * cr + ci * ci;
+                double pr = (cos(a) * cr + sin(a) * ci) / d2, pi = (sin(a) * cr - cos(a) * ci) / d2;      // rho
+                double qr = 1.0, qi = 0.0;
+                for (int e = 0; e < FIX_EVERY; ++e) { const double t = qr * pr - qi * pi; qi = qr * pi + qi * pr; qr = t; }
+                cfix[i] = make_float2((float)(qr - 1.0), (float)qi);
+            }
             a = ang(kbin * (hop + 1));
             gf[i] = make_float2((float)(cos(a) * s18), (float)(sin(a) * s18));
             a = ang(kbin * (hop - 1));
@@ -1091,14 +1127,14 @@ int nbm::tc_plan_create(const nbm_frontend_params &p, TcPlan **out) {
         }
     const size_t b_slide = align_up(slide_elems * 2, 256), b_anchor = align_up(anchor_elems * 2, 256);
     const size_t b_c = align_up((size_t)R * 128 * sizeof(float2), 256);
-    const size_t total = b_slide + b_anchor + 4 * b_c;
+    const size_t total = b_slide + b_anchor + 5 * b_c;
     cudaError_t e = cudaMalloc(&pl->d_blob, total);
     if (e != cudaSuccess) { delete pl; return cuda_fail(e, "cudaMalloc(tc tables)"); }
     unsigned char *d = reinterpret_cast<unsigned char *>(pl->d_blob);
     e = cudaMemcpy(d, a_slide.data(), slide_elems * 2, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(d + b_slide, a_anchor.data(), anchor_elems * 2, cudaMemcpyHostToDevice);
-    const float2 *src[4] = {cf.data(), gf.data(), gb.data(), rot.data()};
-    for (int i = 0; i < 4 && e == cudaSuccess; ++i)
+    const float2 *src[5] = {cf.data(), gf.data(), gb.data(), rot.data(), cfix.data()};
+    for (int i = 0; i < 5 && e == cudaSuccess; ++i)
         e = cudaMemcpy(d + b_slide + b_anchor + i * b_c, src[i], (size_t)R * 128 * sizeof(float2), cudaMemcpyHostToDevice);
     k.a_slide = reinterpret_cast<const __half *>(d);
     k.a_anchor = reinterpret_cast<const __half *>(d + b_slide);
@@ -1106,6 +1142,7 @@ int nbm::tc_plan_create(const nbm_frontend_params &p, TcPlan **out) {
     k.gf = reinterpret_cast<const float2 *>(d + b_slide + b_anchor + b_c);
     k.gb = reinterpret_cast<const float2 *>(d + b_slide + b_anchor + 2 * b_c);
     k.rot = reinterpret_cast<const float2 *>(d + b_slide + b_anchor + 3 * b_c);
+    k.cfix = reinterpret_cast<const float2 *>(d + b_slide + b_anchor + 4 * b_c);
     pl->smem_slide = WS_G * ((size_t)4 * CF * KP * 2 + (size_t)128 * ST_LD * 8 + (size_t)k.buf_len * 2) +
                      (size_t)4 * 128 * 16 * 2 * std::max(0, k.nk - NK_T);
     pl->smem_anchor = (size_t)A_STAGES * A_STAGE_BYTES + 128;
@@ -1125,13 +1162,6 @@ int nbm::tc_plan_create(const nbm_frontend_params &p, TcPlan **out) {
     // per-function attribute (not per plan): allow the device maximum minus the kernel's static shared memory
     if (e == cudaSuccess) e = cudaFuncSetAttribute(slide_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    max_smem - (int)fa_s.sharedSizeBytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(slide_ws_kernel_shared_sm, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   max_smem - (int)fa_s.sharedSizeBytes);
-    // Without this the driver runs the CTA under the smallest shared-memory split that holds it (196 KB), the CTA fills
-    // that split, and no block of another kernel can join it on the SM however small it is (measured with a probe and
-    // in the pipeline: the tiling kernel ran on the one SM this grid leaves free).  Under the 228 KB split ~30 KB stay free.
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(slide_ws_kernel_shared_sm, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                                   cudaSharedmemCarveoutMaxShared);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(anchor_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    max_smem - (int)fa_a.sharedSizeBytes);
     if (e != cudaSuccess) { tc_plan_destroy(pl); return cuda_fail(e, "tc_plan_create"); }
@@ -1161,7 +1191,6 @@ extern "C" int nbm_debug_ws_timing(unsigned long long *out, int reset) {
 int nbm::tc_n_ranges(const TcPlan *pl) { return pl->p.n_ranges; }
 int nbm::tc_bins_per_range() { return BINS_PER_RANGE; }
 int nbm::tc_chain_frames() { return CF; }
-int nbm::tc_units_per_chain(const TcPlan *pl) { return pl->p.n_ranges * 4; }
 int nbm::tc_slots_per_range() { return 4; }
 int nbm::tc_bins_per_slot() { return ROWS_PER_EWARP; }
 
@@ -1179,19 +1208,15 @@ int nbm::tc_launch_anchors(const TcPlan *pl, const SegDesc *d_segs, int seg_lo, 
 
 int nbm::tc_launch_slides(const TcPlan *pl, const SegDesc *d_segs, int n_segs, int seg_begin, int group_begin, int group_end,
                           const void *d_pcm, float *d_spec, float2 *d_tile_mm, const void *d_anchors,
-                          unsigned int *d_file_done, unsigned int *d_started, int *grid_out, cudaStream_t stream) {
+                          float *d_flag_db, float rel_db, unsigned long long *d_cand, unsigned int *d_cand_count,
+                          unsigned int cand_cap, cudaStream_t stream) {
     const TcParams &k = pl->p;
     const int chain_begin = 2 * group_begin, chain_end = 2 * group_end;
     const int grid = std::min(pl->grid_slide, std::max(1, chain_end - chain_begin) * k.n_ranges);
-    if (grid_out) *grid_out = (grid / k.n_ranges) * k.n_ranges;
-    if (d_file_done)
-        slide_ws_kernel_shared_sm<<<(grid / k.n_ranges) * k.n_ranges, WS_THREADS, pl->smem_slide, stream>>>(
-            k, d_segs, n_segs, seg_begin, chain_begin, chain_end, reinterpret_cast<const short *>(d_pcm),
-            reinterpret_cast<const float2 *>(d_anchors), d_spec, d_tile_mm, d_file_done, d_started);
-    else
-        slide_ws_kernel<<<(grid / k.n_ranges) * k.n_ranges, WS_THREADS, pl->smem_slide, stream>>>(
-            k, d_segs, n_segs, seg_begin, chain_begin, chain_end, reinterpret_cast<const short *>(d_pcm),
-            reinterpret_cast<const float2 *>(d_anchors), d_spec, d_tile_mm);
+    FlagArgs fa{d_flag_db, rel_db, d_cand, d_cand_count, cand_cap};
+    slide_ws_kernel<<<(grid / k.n_ranges) * k.n_ranges, WS_THREADS, pl->smem_slide, stream>>>(
+        k, d_segs, n_segs, seg_begin, chain_begin, chain_end, reinterpret_cast<const short *>(d_pcm),
+        reinterpret_cast<const float2 *>(d_anchors), d_spec, d_tile_mm, fa);
     NBM_CUDA(cudaGetLastError());
     return NBM_OK;
 }

@@ -16,6 +16,14 @@ struct SegDesc {
     int group0;            // index of the segment's first 64-frame group (tile)
 };
 
+// One entry of the refinement list: a block of `rows` bins x `nfr` frames of segment `seg`, first pixel (bin0, frame).
+// seg 22 bits | bin0 10 | rows-1 4 | nfr-1 1 | frame 27
+__host__ __device__ inline unsigned long long pack_group(int seg, int bin0, int rows, int nfr, int frame) {
+    return ((unsigned long long)seg << 42) | ((unsigned long long)bin0 << 32) | ((unsigned long long)(rows - 1) << 28) |
+           ((unsigned long long)(nfr - 1) << 27) | (unsigned long long)(unsigned int)frame;
+}
+constexpr int GROUP_MAX_FRAME = (1 << 27) - 1;
+
 struct TcPlan;
 
 // NBM_OK, or NBM_ERR_UNSUPPORTED when (n_fft, hop, n_bins) do not fit the tensor-core formulation
@@ -34,14 +42,13 @@ int tc_bins_per_slot();
 int tc_launch_anchors(const TcPlan *pl, const SegDesc *d_segs, int seg_lo, int seg_hi, long long anchor_begin,
                       long long anchor_end, const void *d_pcm, void *d_anchors, cudaStream_t stream);
 // slides: tcgen05 GEMM over hop/2 pairs + recurrence + Hann + dB for every frame, per-(chain, range, slot) min/max
-// for the 64-frame groups [group_begin, group_end), which start in segment seg_begin
-// d_file_done (optional, zeroed by the caller): per-file count of finished (chain, range, emit warp) units, published
-// with release semantics; a file is complete at 2 * groups(file) * tc_units_per_chain().  Given it, the 96-register
-// build of the kernel runs, which leaves room on the SM for two CTAs of the tiling kernel that follows it; every
-// CTA bumps *d_started on entry and *grid_out is the number of CTAs launched (the follower waits for all of them).
+// for the 64-frame groups [group_begin, group_end), which start in segment seg_begin.  Pixels below their frame's flag
+// level (written to d_flag_db[(chain, range, emit warp)]: rel_db below the largest |R| the rows carried along the chain) are
+// appended to d_cand as blocks (pack_group; at most cand_cap, *d_cand_count counts every
+// attempt) and left out of the min/max partials; see refine_groups_kernel.
 int tc_launch_slides(const TcPlan *pl, const SegDesc *d_segs, int n_segs, int seg_begin, int group_begin, int group_end,
                      const void *d_pcm, float *d_spec, float2 *d_tile_mm, const void *d_anchors,
-                     unsigned int *d_file_done, unsigned int *d_started, int *grid_out, cudaStream_t stream);
-int tc_units_per_chain(const TcPlan *pl);
+                     float *d_flag_db, float rel_db, unsigned long long *d_cand, unsigned int *d_cand_count,
+                     unsigned int cand_cap, cudaStream_t stream);
 
 }  // namespace nbm

@@ -163,18 +163,96 @@ nms_scan_kernel(const unsigned long long *__restrict__ mask, const int *__restri
 
 static inline int nms_words(int N) { return (N + 63) / 64; }
 
+// The same resolution for N <= 2048 (32 words) when the image's bit matrix fits in shared memory -- every call of
+// the detector (500 proposals, <= 50 final boxes, a file's merge list): the matrix is staged once, then ONE WARP walks
+// the chunks with no block barrier.  Lane w owns word w of the removed-mask; the 64-box diagonal is resolved by
+// following the alive bits (find-first-set, broadcast read of that row's diagonal word), so its cost is the number of
+// boxes KEPT in the chunk, not 64; the kept rows are then OR-ed into the later words lane-parallel from shared memory.
+constexpr int NMS_SMALL_THREADS = 128;
+__global__ void __launch_bounds__(NMS_SMALL_THREADS)
+nms_scan_small_kernel(const unsigned long long *__restrict__ mask, const int *__restrict__ n_valid,
+                      const int *__restrict__ n_cap, int N, int words, int *__restrict__ keep_idx,
+                      int *__restrict__ keep_cnt) {
+    extern __shared__ unsigned long long sm[];           // [n][words], upper triangle
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    int n = n_valid ? n_valid[b] : N;
+    if (n_cap) n = min(n, *n_cap);
+    n = min(n, N);
+    const unsigned long long *m = mask + (long long)b * N * words;
+    const int chunks = (n + 63) / 64;
+    for (int idx = tid; idx < n * words; idx += NMS_SMALL_THREADS) {
+        const int row = idx / words, w = idx - row * words;
+        if (w >= (row >> 6) && w < chunks) sm[idx] = m[idx];      // words left of the diagonal were never written
+    }
+    __syncthreads();
+    if (tid >= 32) return;
+    unsigned long long removed = 0, kept = 0;            // word `lane`
+    for (int c = 0; c < chunks; ++c) {
+        const unsigned long long cur = __shfl_sync(0xffffffffu, removed, c);
+        const int lim = min(64, n - c * 64);
+        unsigned long long alive = ~cur & (lim == 64 ? ~0ull : ((1ull << lim) - 1ull));
+        unsigned long long kb = 0;
+        const unsigned long long *rows = sm + (size_t)c * 64 * words;
+        while (alive) {                                  // warp-uniform
+            const int t = __ffsll((long long)alive) - 1;
+            kb |= 1ull << t;
+            alive &= ~(rows[(size_t)t * words + c] | (1ull << t));
+        }
+        if (lane == c) kept = kb;
+        const bool mine = lane > c && lane < chunks;
+        unsigned long long acc = 0, bits = kb;
+        while (bits) {
+            const int t = __ffsll((long long)bits) - 1;
+            bits &= bits - 1;
+            if (mine) acc |= rows[(size_t)t * words + lane];
+        }
+        removed |= acc;
+    }
+    // compaction: ascending kept indices; exclusive prefix of the per-word counts over the lanes
+    const int pc = lane < chunks ? __popcll(kept) : 0;
+    int off = pc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, off, o);
+        if (lane >= o) off += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, off, 31);
+    off -= pc;
+    while (kept) {
+        const int t = __ffsll((long long)kept) - 1;
+        kept &= kept - 1;
+        keep_idx[(long long)b * N + off++] = lane * 64 + t;
+    }
+    if (lane == 0) keep_cnt[b] = total;
+    for (int i = total + lane; i < N; i += 32) keep_idx[(long long)b * N + i] = -1;
+}
+constexpr size_t NMS_SMALL_SMEM_MAX = 200 * 1024;
+
 static int launch_nms(const float *d_boxes, const int *d_n, const int *d_cap, int B, int N, float thresh,
                       int *d_keep_idx, int *d_keep_cnt, void *ws, size_t ws_bytes, cudaStream_t s) {
     const int words = nms_words(N);
     const size_t need = (size_t)B * N * words * sizeof(unsigned long long);
     if (ws_bytes < need) { set_error("nms workspace too small: %zu < %zu", ws_bytes, need); return NBM_ERR_WORKSPACE; }
+    dim3 grid(words, words, B);
+    nms_mask_kernel<<<grid, 64, 0, s>>>(reinterpret_cast<const float4 *>(d_boxes), d_n, d_cap, N, thresh,
+                                        reinterpret_cast<unsigned long long *>(ws), words);
+    const size_t smem_small = (size_t)N * words * sizeof(unsigned long long);
+    if (words <= 32 && smem_small <= NMS_SMALL_SMEM_MAX) {
+        static bool attr_set = false;                   // per function, not per call
+        if (!attr_set) {
+            NBM_CUDA(cudaFuncSetAttribute(nms_scan_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)NMS_SMALL_SMEM_MAX));
+            attr_set = true;
+        }
+        nms_scan_small_kernel<<<B, NMS_SMALL_THREADS, smem_small, s>>>(reinterpret_cast<const unsigned long long *>(ws), d_n,
+                                                                      d_cap, N, words, d_keep_idx, d_keep_cnt);
+        NBM_CUDA(cudaGetLastError());
+        return NBM_OK;
+    }
     const size_t smem = (size_t)2 * words * sizeof(unsigned long long);
     NBM_REQUIRE(smem <= 200 * 1024, "N too large for the NMS scan kernel");
     if (smem > 48 * 1024)
         NBM_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(words, words, B);
-    nms_mask_kernel<<<grid, 64, 0, s>>>(reinterpret_cast<const float4 *>(d_boxes), d_n, d_cap, N, thresh,
-                                        reinterpret_cast<unsigned long long *>(ws), words);
     nms_scan_kernel<<<B, 256, smem, s>>>(reinterpret_cast<const unsigned long long *>(ws), d_n, d_cap, N, words,
                                          d_keep_idx, d_keep_cnt);
     NBM_CUDA(cudaGetLastError());
@@ -275,9 +353,18 @@ final_detections_kernel(const float *__restrict__ bbox_reg, const float *__restr
     __syncthreads();
     if (r < R) {
         // rank in the stable descending order (ties: lower index first)
+        // The order must be TOTAL or two rows share a rank and a slot of s_pos stays unwritten: NaN scores (a diverged
+        // head) sort first, as torch.argsort(descending=True) places them, ties among them by index.
         const float me = s_score[r];
+        const bool me_nan = me != me;
         int rank = 0;
-        for (int j = 0; j < R; ++j) { const float v = s_score[j]; rank += (v > me) || (v == me && j < r); }
+        for (int j = 0; j < R; ++j) {
+            const float v = s_score[j];
+            const bool v_nan = v != v;
+            const bool before = (v_nan || me_nan) ? (v_nan && !me_nan) : (v > me);
+            const bool same = (v_nan && me_nan) || v == me;
+            rank += before || (same && j < r);
+        }
         s_pos[rank] = r;
     }
     __syncthreads();

@@ -104,6 +104,11 @@ def prepare_dataset(directory, out_directory, freq_accuracy=33.3, dt=0.003, over
         img_db, _ = fp.process_file(freq_accuracy=freq_accuracy, dt=dt, overlap_spectro=overlap_spectro, w_pix=w_pix)
         if img_db is None:
             continue
+        if isinstance(img_db, list):
+            # recording longer than 3401 s: one image list per piece (prepare_dataset.py:187-225); the images are numbered
+            # consecutively across the pieces as the reference's cumulative `lengths` do (:59-61, :77-80).  (Upstream,
+            # the unlabelled case then dies in np.concatenate([]) at :63; the labelled one works.)
+            img_db = torch.cat([t for t in img_db if len(t)], dim=0)
         n_img = len(img_db)
         os.makedirs(out_neg_dir, exist_ok=True)                     # no labels: every image is a negative (:66-74)
         keep = min(n_img, 1000)                                     # `elif i <= 999` (:87)

@@ -20,8 +20,7 @@ import os
 import numpy as np
 import torch
 
-from . import _lib
-from .synth import read_wav_pcm16
+from . import _lib, audio_io
 
 STFT_CHUNK = int(5e7)                                   # prepare_dataset.py:234
 LONG_FILE_SAMPLES = int(15e7) - int(15e7) % 44100       # prepare_dataset.py:194
@@ -51,7 +50,13 @@ def _stream_ptr(stream) -> int:
 
 
 class FrontendPlan:
-    """Owns an ``nbm_frontend_plan`` (device twiddle tables) plus a reusable torch workspace."""
+    """Owns an ``nbm_frontend_plan`` (device twiddle tables) plus a reusable torch workspace.
+
+    A plan is SINGLE-CALLER: its workspace (descriptors, dB band, candidate list), its side stream and its events are
+    shared by every run, and a run only orders itself after the stream it is given.  Two runs of the same plan must
+    therefore be issued to the same stream (or be separated by an event / synchronisation); callers that overlap
+    front-end work with other work on another stream create a plan of their own (``pipeline.DetectionPipeline`` does).
+    ``get_plan`` returns the process-wide plan used by ``File_Processor`` on the current stream."""
 
     def __init__(self, freq_accuracy=33.3, dt=0.003, overlap_spectro=0.2, w_pix=1024,
                  sample_rate=44100, h_pix=375, low_freq=500, device=None, stft_chunk=STFT_CHUNK):
@@ -163,6 +168,12 @@ class FrontendPlan:
         _lib.check(_lib.lib().nbm_frontend_get_profile_kernels(self._h, ms, C.byref(n)), "nbm_frontend_get_profile_kernels")
         return dict(zip(("anchor", "stft", "minmax", "tile"), list(ms))), n.value
 
+    def last_listed(self):
+        """(blocks listed for float64 refinement by the last run, capacity of the list); waits for that run."""
+        n, cap = C.c_int64(), C.c_int64()
+        _lib.check(_lib.lib().nbm_frontend_last_listed(self._h, C.byref(n), C.byref(cap)), "nbm_frontend_last_listed")
+        return n.value, cap.value
+
     def run_batch_from_host(self, host_pcm: torch.Tensor, sample_offsets, out=None, files_per_chunk=64):
         """run_batch for mono PCM16 in PINNED host memory: the files are copied to the device in chunks on a
         side stream while the previous chunk is being transformed (two device staging buffers), so the
@@ -241,18 +252,21 @@ class File_Processor:
         self.filepath = filepath
 
     def load(self):
-        """PCM16 wav -> pinned int16 host tensor (the /32768 scaling and mono mix happen on the
-        device).  Returns None on failure like the reference (prepare_dataset.py:160-165)."""
+        """wav -> pinned host tensor: int16 for PCM16 (the /32768 scaling and the mono mix happen on the device), float32
+        with libsndfile's scaling for the other encodings (audio_io.read_wav).  Returns None on failure like the
+        reference (prepare_dataset.py:160-165).  A file that is not at 44.1 kHz is converted the way the reference's
+        ffmpeg call converts it -- mono, 44.1 kHz, PCM16 (prepare_dataset.py:166-182) -- by audio_io.resample_pcm16."""
         try:
-            pcm, sr = read_wav_pcm16(self.filepath)
+            pcm, sr = audio_io.read_wav(self.filepath)
         except Exception:
             print("File loading failed")
             return None
         if sr != self.FREQ:
-            # the reference shells out to ffmpeg here (prepare_dataset.py:166-182)
-            raise ValueError(f"{self.filepath}: sample rate {sr} != {self.FREQ}; resample first (no ffmpeg path)")
-        t = torch.empty(pcm.shape, dtype=torch.int16, pin_memory=torch.cuda.is_available())
-        t.numpy()[...] = pcm            # one copy, decoded bytes -> pinned memory
+            print(f"{self.filepath}: {sr} Hz -> {self.FREQ} Hz mono PCM16 (polyphase resampler in place of the reference's ffmpeg call)")
+            pcm = audio_io.resample_pcm16(pcm, sr, self.FREQ)
+        t = torch.empty(pcm.shape, dtype=torch.int16 if pcm.dtype == np.int16 else torch.float32,
+                        pin_memory=torch.cuda.is_available())
+        t.numpy()[...] = pcm            # one copy, decoded samples -> pinned memory
         return t
 
     def process_file(self, freq_accuracy=33.3, dt=0.003, overlap_spectro=0.2, w_pix=1024):

@@ -66,6 +66,9 @@ def detect_directory(model, model_args, audio_dir, bird_dict="bird_dict.json", m
             counts["t_post_us"] += int(tm["post_s"] * 1e6)
     torch.cuda.synchronize()
     counts["t_wall_us"] = int((time.perf_counter() - t_wall) * 1e6)
+    counts["failed"] = len(files) - counts["files"]
+    if counts["failed"]:
+        print(f"[rank {rank}] {counts['failed']} of {len(files)} files FAILED and have no .txt (see above)")
     return counts
 
 
@@ -106,6 +109,8 @@ def main(argv=None):
         print(json.dumps({"per_rank": per_rank, "totals": sharding.totals(per_rank)}))
     if world > 1:
         torch.distributed.destroy_process_group()
+    if counts.get("failed"):
+        raise SystemExit(3)         # some of this rank's files have no output
 
 
 if __name__ == "__main__":

@@ -26,10 +26,8 @@ from __future__ import annotations
 import json
 import os
 import queue
-import struct
 import threading
 import time
-import wave
 from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass, field
 from types import SimpleNamespace
@@ -37,8 +35,8 @@ from types import SimpleNamespace
 import numpy as np
 import torch
 
-from . import postproc
-from .frontend import LONG_FILE_SAMPLES, STFT_CHUNK, derive_constants, get_plan
+from . import audio_io, postproc
+from .frontend import LONG_FILE_SAMPLES, STFT_CHUNK, FrontendPlan, derive_constants
 from .run_detection import detect_tiles, run_detection
 
 
@@ -61,35 +59,22 @@ class WavInfo:
     channels: int = 1
     sample_rate: int = 0
     error: str | None = None
-
-
-def _data_chunk(path: str):
-    """(offset, bytes) of the RIFF 'data' chunk as the header states them."""
-    with open(path, "rb") as f:
-        head = f.read(12)
-        if len(head) < 12 or head[:4] != b"RIFF" or head[8:12] != b"WAVE":
-            raise ValueError("not a RIFF/WAVE file")
-        while True:
-            h = f.read(8)
-            if len(h) < 8:
-                raise ValueError("no data chunk")
-            size = struct.unpack("<I", h[4:])[0]
-            if h[:4] == b"data":
-                return f.tell(), size
-            f.seek(size + (size & 1), os.SEEK_CUR)
+    pcm16: bool = True          # False: another PCM width or float samples (decoded on the one-file path)
 
 
 def probe_wav(path: str) -> WavInfo:
     """Header only (no sample data is read).  n_samples counts the whole frames actually present: a truncated file is
-    processed up to where it ends, as the one-file path (synth.read_wav_pcm16) and libsndfile do."""
+    processed up to where it ends, as the one-file path (audio_io.read_wav) and libsndfile do."""
     try:
-        with wave.open(path, "rb") as w:
-            if w.getsampwidth() != 2 or w.getcomptype() != "NONE":
-                return WavInfo(path, error="only uncompressed PCM16 wav is supported")
-            ch, sr, n = w.getnchannels(), w.getframerate(), w.getnframes()
-        off, _ = _data_chunk(path)
-        held = max(0, os.path.getsize(path) - off) // (2 * ch)
-        return WavInfo(path, min(n, held), ch, sr)
+        with open(path, "rb") as f:
+            h = audio_io.parse_wav_header(f)
+        ch, bits = h["channels"], h["bits"]
+        if ch < 1 or bits % 8 or bits == 0:
+            return WavInfo(path, error="File loading failed (bad fmt chunk)")
+        if (h["format"], bits) not in ((1, 8), (1, 16), (1, 24), (1, 32), (3, 32), (3, 64)):
+            return WavInfo(path, error=f"File loading failed (unsupported wav encoding: format {h['format']}, {bits} bits)")
+        held = max(0, min(h["data_bytes"], os.path.getsize(path) - h["data_offset"])) // (bits // 8 * ch)
+        return WavInfo(path, held, ch, h["sample_rate"], pcm16=(h["format"] == 1 and bits == 16))
     except Exception as e:          # the reference prints 'File loading failed' and returns None (prepare_dataset.py:163-165)
         return WavInfo(path, error=f"File loading failed ({e})")
 
@@ -119,6 +104,7 @@ def group_budget(index: int, max_group_tiles: int, first_group_tiles: int | None
 
 
 LONG_REASON = "long recording (> 3401 s): processed on its own after the batched groups"
+SOLO_REASON = "not 44.1 kHz PCM16: decoded / resampled on the one-file path after the batched groups"
 
 
 def plan_groups(infos, const, max_group_tiles: int, stft_chunk: int = STFT_CHUNK, first_group_tiles: int | None = None):
@@ -130,8 +116,8 @@ def plan_groups(infos, const, max_group_tiles: int, stft_chunk: int = STFT_CHUNK
     for info in infos:
         if info.error:
             rejected.append((info, info.error)); continue
-        if info.sample_rate != 44100:
-            rejected.append((info, f"sample rate {info.sample_rate} != 44100; resample first (no ffmpeg path)")); continue
+        if info.sample_rate != 44100 or not info.pcm16:
+            rejected.append((info, SOLO_REASON)); continue
         if info.n_samples > LONG_FILE_SAMPLES:
             rejected.append((info, LONG_REASON)); continue
         fr, nt = count_frames_tiles(info.n_samples, const["HOP_LENGTH"], const["W_PIX"], const["HOP_SPECTRO"], stft_chunk)
@@ -145,8 +131,9 @@ def plan_groups(infos, const, max_group_tiles: int, stft_chunk: int = STFT_CHUNK
 
 def read_into(info: WavInfo, dst: np.ndarray) -> None:
     """Decode one wav's int16 samples (interleaved if multi-channel) into `dst` (a slice of the pinned buffer)."""
-    with wave.open(info.path, "rb") as w:
-        raw = w.readframes(info.n_samples)
+    with open(info.path, "rb") as f:
+        h = audio_io.parse_wav_header(f)
+        raw = f.read(info.n_samples * info.channels * 2)
     a = np.frombuffer(raw, dtype="<i2")
     if a.size != dst.size:
         raise IOError(f"{info.path}: header promised {dst.size} values, file holds {a.size}")
@@ -173,6 +160,10 @@ class DetectionPipeline:
         self.reverse_dict = {idx: name for name, idx in birds.items()}
         self.counts = dict(files=0, tiles=0, detections=0, frames=0, t_front_us=0, t_model_us=0, t_post_us=0)
         self.failed: list = []
+        # A plan owns ONE workspace and one side stream: it serves one caller at a time.  The pipeline runs its front-end
+        # on a stream of its own while the caller's stream (and possibly File_Processor / run_detection calls on the
+        # process-wide plan of frontend.get_plan) is busy with the detector, so it gets a private plan.
+        self._plan = None
 
     # reader side: fills pinned buffers, two groups ahead at most
     def _reader(self, groups, out_q: queue.Queue, free_q: queue.Queue, pool: ThreadPoolExecutor):
@@ -201,15 +192,18 @@ class DetectionPipeline:
             out_q.put(e)
 
     def run(self, paths):
-        plan = get_plan(*self.fe_args)
+        if self._plan is None:
+            self._plan = FrontendPlan(*self.fe_args)
+        plan = self._plan
         infos = [probe_wav(p) for p in paths]
         groups, rejected = plan_groups(infos, self.const, self.max_group_tiles, first_group_tiles=self.first_group_tiles)
-        long_files = [info.path for info, why in rejected if why == LONG_REASON]
-        self.failed += [(info.path, why) for info, why in rejected if why != LONG_REASON]
+        long_files = [info.path for info, why in rejected if why in (LONG_REASON, SOLO_REASON)]
+        self.failed += [(info.path, why) for info, why in rejected if why not in (LONG_REASON, SOLO_REASON)]
         if groups:
             yield from self._run_groups(plan, groups)
         # recordings longer than 3401 s: File_Processor cuts them into pieces that are one front-end batch already
-        # (frontend.File_Processor._process_long); they go through run_detection one at a time, after the groups
+        # (frontend.File_Processor._process_long); files at another sample rate or sample format need the host decode /
+        # resample stage of File_Processor.load.  Both go through run_detection one at a time, after the groups
         for path in long_files:
             tm = {}
             try:

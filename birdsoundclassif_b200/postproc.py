@@ -81,35 +81,56 @@ def bbox_reg_to_coord(bbox_pred: torch.Tensor, anchors: torch.Tensor) -> torch.T
 
 
 # ----------------------------------------------------------------------------------- NMS ------
-def nms_keep(boxes: torch.Tensor, thresh: float, n_valid: torch.Tensor | None = None):
-    """boxes [B,N,4] in priority order -> (keep_idx int32 [B,N] (first keep_cnt[b] valid), keep_cnt int32 [B])."""
+_WS: dict = {}          # (device, stream) -> grow-only scratch tensor for the NMS bit matrix
+
+
+def _scratch(dev, nbytes: int) -> torch.Tensor:
+    """Scratch memory reused across calls on the same stream (same-stream calls are ordered, so one buffer serves
+    them all; the reference's nms allocates eight N x N temporaries per call, nets_utils.py:193-205)."""
+    key = (dev, _stream())
+    t = _WS.get(key)
+    if t is None or t.numel() < nbytes:
+        t = _WS[key] = torch.empty((max(int(nbytes * 1.5), 1 << 16),), dtype=torch.uint8, device=dev)
+    return t
+
+
+def nms_keep(boxes: torch.Tensor, thresh: float, n_valid: torch.Tensor | None = None, packed: bool = False):
+    """boxes [B,N,4] in priority order -> (keep_idx int32 [B,N] (first keep_cnt[b] valid), keep_cnt int32 [B]);
+    with ``packed`` also the int32 buffer [B + B*N] holding both (counts first), for a single device-to-host copy."""
     _need_cuda(boxes)
     boxes = _f32c(boxes)
     B, N = boxes.shape[0], boxes.shape[1]
-    keep_idx = torch.empty((B, max(N, 1)), dtype=torch.int32, device=boxes.device)
-    keep_cnt = torch.empty((B,), dtype=torch.int32, device=boxes.device)
+    Nn = max(N, 1)
+    buf = torch.empty((B * (Nn + 1),), dtype=torch.int32, device=boxes.device)
+    keep_cnt, keep_idx = buf[:B], buf[B:].view(B, Nn)
     ws_bytes = _lib.lib().nbm_nms_workspace_bytes(B, N)
-    ws = torch.empty((max(ws_bytes, 8),), dtype=torch.uint8, device=boxes.device)
+    ws = _scratch(boxes.device, max(ws_bytes, 8))
     with torch.cuda.device(boxes.device):
         _lib.check(_lib.lib().nbm_nms_greedy(boxes.data_ptr(), n_valid.data_ptr() if n_valid is not None else None,
                                              B, N, float(thresh), keep_idx.data_ptr(), keep_cnt.data_ptr(),
                                              ws.data_ptr(), ws.numel(), _stream()), "nbm_nms_greedy")
-    return keep_idx, keep_cnt
+    return (keep_idx, keep_cnt, buf) if packed else (keep_idx, keep_cnt)
 
 
 def nms(bbox_pred: torch.Tensor, scores: torch.Tensor, nms_thresh=0.7, post_nms_topN=300, return_idx=False):
     """Drop-in for nets_utils.nms.  Greedy IN INPUT ORDER (no sort), IoU >= thresh suppresses,
     every row truncated to min(min_b len(keep_b), post_nms_topN); with return_idx the untruncated
-    keep lists come back as list[list[int]] (callers fancy-index with them, layers.py:746)."""
-    keep_idx, keep_cnt = nms_keep(bbox_pred, nms_thresh)
-    cnt = keep_cnt.tolist()
+    keep lists come back as list[list[int]] (callers fancy-index with them, layers.py:746).  One device-to-host
+    copy per call (the counts, or counts + index table with return_idx)."""
+    keep_idx, keep_cnt, buf = nms_keep(bbox_pred, nms_thresh, packed=True)
+    B = keep_cnt.shape[0]
+    if return_idx:
+        host = buf.cpu().numpy()
+        cnt = host[:B].tolist()
+        rows = host[B:].reshape(B, -1)
+    else:
+        cnt = keep_cnt.tolist()
     m = min(min(cnt), int(post_nms_topN))
     sel = keep_idx[:, :m].long()
     out_scores = torch.gather(scores, 1, sel)
     out_boxes = torch.gather(bbox_pred, 1, sel[..., None].expand(-1, -1, 4))
     if return_idx:
-        rows = keep_idx.cpu().tolist()
-        return out_boxes, out_scores, [rows[b][:cnt[b]] for b in range(len(cnt))]
+        return out_boxes, out_scores, [rows[b, :cnt[b]].tolist() for b in range(B)]
     return out_boxes, out_scores
 
 
@@ -270,8 +291,7 @@ def merge_flat(boxes, scores, classes, tiles, n_tiles, w_pix, hop_spectro, spect
     os_ = torch.empty((n,), dtype=torch.float32, device=dev)
     oc = torch.empty((n,), dtype=torch.int32, device=dev)
     cnt = torch.empty((1,), dtype=torch.int32, device=dev)
-    ws_bytes = _lib.lib().nbm_merge_workspace_bytes(n)
-    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    ws = _scratch(dev, _lib.lib().nbm_merge_workspace_bytes(n))
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().nbm_merge_detections(boxes.data_ptr(), scores.data_ptr(), classes.data_ptr(),
                                                    tiles.data_ptr(), n, int(n_tiles), int(w_pix), int(hop_spectro),

@@ -112,6 +112,11 @@ int nbm_frontend_get_profile(nbm_frontend_plan *plan, double *stft_ms, double *t
 /* The same, per kernel: ms4 = {anchor GEMM, slide/STFT kernel, whole-file min/max, tiling}. */
 int nbm_frontend_get_profile_kernels(nbm_frontend_plan *plan, double *ms4, int64_t *runs);
 
+/* Diagnostics of the float64 refinement pass of the LAST run (waits for it; valid while that run's workspace is alive):
+ * *listed = pixel blocks the transform put on the refinement list (counted even when the list was full),
+ * *capacity = entries the list could hold.  listed > capacity means some pixels kept their float32 values. */
+int nbm_frontend_last_listed(nbm_frontend_plan *plan, int64_t *listed, int64_t *capacity);
+
 /* Dataset images from detector tiles: out = uint8(round_half_even(tile * 255)), the quantisation
  * prepare_dataset() applies before writing a PNG (prepare_dataset.py:85).  d_tiles 16-byte aligned,
  * n_values = number of pixels (any count), asynchronous on `stream`. */

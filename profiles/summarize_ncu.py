@@ -1,5 +1,6 @@
 """Turn an .ncu-rep (read with `ncu -i`) into the short text summary committed under profiles/.
-usage: python profiles/summarize_ncu.py gpurun_out/prof.ncu-rep > profiles/<name>.txt"""
+usage: python profiles/summarize_ncu.py gpurun_out/prof.ncu-rep ["note, e.g. frames = 1282944 per launch"] > profiles/<name>.txt
+(bench.py reads `frames = N` from the note to turn the DRAM byte counters into bytes per frame)"""
 import csv
 import subprocess
 import sys
@@ -25,7 +26,9 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "smsp__average_warps_issue_stalled_sleeping_per_issue_active.ratio"]
 
 
-def main(path):
+def main(path, note=None):
+    if note:
+        print("# capture:", note)
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
@@ -39,4 +42,4 @@ def main(path):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None)

@@ -1,15 +1,12 @@
 """GPU front-end (libnbm_b200 through the File_Processor mirror) against the CPU oracle,
 the committed golden vectors, and size-independent properties.
 
-Tolerance (stated, see DESIGN.md "Oracle and parity status").  The reference computes the STFT in
-float64 and stores complex64; the kernel computes in float32 (fp16-split tensor-core products,
-fp32 accumulation), so its error is ABSOLUTE in linear magnitude (about 5e-7 of the frame's RMS bin
-magnitude).  In dB that is far below 1e-4 of the image range everywhere except in deep spectral
-nulls (|X| < ~1e-3 of the RMS), about one pixel per million on white-noise backgrounds.  The
-whole-file minimum -- itself the deepest null, and an offset of every pixel -- is recomputed in
-float64 on the device (refine_minmax_kernel), so on the normalised [0,1] tiles we require
-    |gpu - oracle| <= 1e-4   (= 1e-4 (s_max - s_min) dB, about 0.01 dB) for >= 99.9998 % of pixels,
-    |gpu - oracle| <= 1e-3   for every pixel (the deep-null outliers),  rms error <= 2e-6,
+Tolerance (stated, see DESIGN.md "Oracle and parity status"; SURVEY.md 8d).  The reference computes the STFT in
+float64 and stores complex64; the kernel computes in float32 (fp16-split tensor-core products, fp32 accumulation), so
+its error is ABSOLUTE in linear magnitude (about 5e-7 of the frame's RMS bin magnitude).  In dB that only shows in deep
+spectral nulls, so every pixel more than ~45 dB below its frame's level is recomputed on the device the way the
+reference computes it (float64; refine_pixels_kernel), the file minimum included.  On the normalised [0,1] tiles:
+    |gpu - oracle| <= 1e-4 for EVERY pixel (= 1e-4 (s_max - s_min) dB),  rms error <= 2e-6,
     s_min and s_max within 1e-4 dB.
 """
 import numpy as np
@@ -21,9 +18,7 @@ from tests import helpers as H
 
 pytestmark = pytest.mark.gpu
 
-TOL_TILE = 1e-4          # per pixel, all but TOL_OUTLIER_FRAC of them
-TOL_OUTLIER_FRAC = 2e-6
-TOL_TILE_WORST = 1e-3    # every pixel
+TOL_TILE = 1e-4          # every pixel
 TOL_RMS = 2e-6
 TOL_SMIN_DB = 1e-4
 TOL_SMAX_DB = 1e-4
@@ -31,11 +26,9 @@ TOL_SMAX_DB = 1e-4
 
 def assert_tiles_close(t, ref, what=""):
     err = np.abs(np.asarray(t, dtype=np.float64) - np.asarray(ref, dtype=np.float64))
-    frac = float((err > TOL_TILE).mean())
     rms = float(np.sqrt((err ** 2).mean()))
-    msg = f"{what} max {err.max():.3e} frac>{TOL_TILE:g} {frac:.2e} rms {rms:.2e}"
-    assert err.max() <= TOL_TILE_WORST, msg
-    assert frac <= max(TOL_OUTLIER_FRAC, 1.5 / err.size), msg
+    msg = f"{what} max {err.max():.3e} rms {rms:.2e}"
+    assert err.max() <= TOL_TILE, msg
     assert rms <= TOL_RMS, msg
 
 
@@ -60,6 +53,8 @@ def test_against_golden_and_oracle(fe, case):
     name, _, _, kw = case
     pcm = H.frontend_pcm(case, gold)
     fp, tiles = _gpu_tiles(fe, pcm, **kw)
+    # every case, the n_fft 4410 / hop 44 stress parameters of BASELINE configs[4] included, runs on the tcgen05 kernels
+    assert fe.get_plan(**kw).impl == "tcgen05"
     t = tiles.cpu().numpy()
     assert t.shape[0] == int(gold[name + "/n_tiles"]) and t.shape[1:] == (375, 1024) and t.dtype == np.float32
     assert fp.spectrogram_length == int(gold[name + "/spectrogram_length"])
@@ -90,7 +85,7 @@ def test_db_spectrogram_before_normalisation(fe):
     assert db.shape == ref.shape
     e = np.abs(db - ref)
     print(f"dB error: max {e.max():.4f} p99.9 {np.quantile(e, 0.999):.2e} median {np.median(e):.2e}")
-    assert e.max() <= 0.3                           # dB, the deepest nulls
+    assert e.max() <= 1e-4 * (ref.max() - ref.min())       # dB: the deep nulls are recomputed in float64
     assert np.quantile(e, 0.999) <= 1e-3 and np.median(e) <= 2e-5
 
 
@@ -196,7 +191,7 @@ def test_errors(fe):
 
 def test_leading_silence_and_exact_minimum(fe):
     """Digital silence puts many pixels on the -100 dB floor (prepare_dataset.py:228-230): s_min is the
-    floor, the candidate list of the exact-minimum pass overflows harmlessly, tiles stay in [0, 1]."""
+    floor (silent frames flag nothing; the frames at the transition are recomputed), tiles stay in [0, 1]."""
     from oracle import frontend_oracle as fo
     pcm = synth.synth_pcm(3.0, 21).copy()
     pcm[:44100] = 0
@@ -225,23 +220,6 @@ def test_run_batch_from_host_equals_run_batch(fe):
         assert off == ref_off and torch.equal(tiles, ref_tiles) and torch.equal(mm, ref_mm)
 
 
-def test_sub_batched_overlap_path_equals_plain(fe, monkeypatch):
-    """NBM_FRONTEND_OVERLAP=1 splits a batch into sub-batches (transform on a priority stream, tiling behind
-    events): same bits as the plain launch sequence, also across an STFT-chunk seam."""
-    pcms = [synth.synth_pcm(s, 80 + i) for i, s in enumerate([3.0, 2.3, 4.1, 3.0, 1.5, 2.2])]
-    flat = torch.from_numpy(np.concatenate(pcms)).cuda()
-    offs = np.concatenate([[0], np.cumsum([len(p) for p in pcms])]).tolist()
-    plain = fe.FrontendPlan(stft_chunk=100_100)
-    ref_tiles, ref_off, ref_mm = plain.run_batch(flat, offs)
-    monkeypatch.setenv("NBM_FRONTEND_OVERLAP", "1")
-    monkeypatch.setenv("NBM_FRONTEND_SUB_GROUPS", "4")
-    sub = fe.FrontendPlan(stft_chunk=100_100)
-    tiles, off, mm = sub.run_batch(flat, offs)
-    torch.cuda.synchronize()
-    assert off == ref_off and torch.equal(tiles, ref_tiles) and torch.equal(mm, ref_mm)
-    plain.close(); sub.close()
-
-
 @pytest.mark.parametrize("n", [1, 131, 132, 133, 661, 1324, 4224, 8447, 8448, 8449])
 def test_tiny_files(fe, n):
     """Files shorter than a window / a chain / a 64-frame group (all centre padding on one or both sides)."""
@@ -255,23 +233,6 @@ def test_tiny_files(fe, n):
     ref = np.stack(r.tiles)
     if np.isfinite(ref).all():
         assert_tiles_close(tiles.cpu().numpy(), ref, f"n={n}")
-
-
-def test_fused_tiling_follows_transform_equals_plain(fe, monkeypatch):
-    """NBM_FRONTEND_FUSED=1: the tiling kernel runs beside the slide kernel and follows it file by file through
-    release/acquire flags (min/max refinement inside): same bits as the plain launch sequence."""
-    pcms = [synth.synth_pcm(s, 85 + i) for i, s in enumerate([3.0, 2.3, 0.4, 4.1, 3.0, 1.5, 2.2, 6.0])]
-    flat = torch.from_numpy(np.concatenate(pcms)).cuda()
-    offs = np.concatenate([[0], np.cumsum([len(p) for p in pcms])]).tolist()
-    plain = fe.FrontendPlan(stft_chunk=100_100)
-    ref_tiles, ref_off, ref_mm = plain.run_batch(flat, offs)
-    monkeypatch.setenv("NBM_FRONTEND_FUSED", "1")
-    fused = fe.FrontendPlan(stft_chunk=100_100)
-    for _ in range(3):
-        tiles, off, mm = fused.run_batch(flat, offs)
-        torch.cuda.synchronize()
-        assert off == ref_off and torch.equal(mm, ref_mm) and torch.equal(tiles, ref_tiles)
-    plain.close(); fused.close()
 
 
 def test_long_recording_is_cut_into_independent_pieces(fe, monkeypatch):

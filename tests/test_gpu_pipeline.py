@@ -84,8 +84,8 @@ def test_sharded_directory_union_equals_single(audio_dir, tmp_path):
 def test_pipelined_directory_equals_file_by_file(tmp_path, group_tiles):
     """pipeline.DetectionPipeline (reader threads -> batched front-end on its own stream -> detector, overlapped
     across groups of files) writes the same .txt as the reference-shaped one-file-at-a-time loop: ragged mono
-    files, a stereo pair (its own group), a file shorter than one window, an unreadable file and a wrong-rate file
-    (both skipped by both drivers)."""
+    files, a stereo pair (its own group), a file shorter than one window, an unreadable file (skipped by both drivers),
+    and a 48 kHz file and a 24-bit file (decoded / resampled on the one-file path by both drivers)."""
     from birdsoundclassif_b200 import nbm_detect
     d = tmp_path
     for i, secs in enumerate([9.0, 0.01, 12.5, 2.0, 7.7, 30.0, 3.3]):
@@ -96,7 +96,12 @@ def test_pipelined_directory_equals_file_by_file(tmp_path, group_tiles):
     raw = open(str(d / "rec_02.wav"), "rb").read()
     (d / "rec_05_truncated.wav").write_bytes(raw[:len(raw) // 3 + 1])      # processed up to where it ends, by both drivers
     (d / "rec_20_broken.wav").write_bytes(b"RIFFjunk")
-    synth.write_wav(str(d / "rec_21_48k.wav"), synth.synth_pcm(1.0, 740), sample_rate=48000)
+    synth.write_wav(str(d / "rec_21_48k.wav"), synth.synth_pcm(4.0, 740), sample_rate=48000)
+    import struct
+    pcm24 = synth.synth_pcm(3.5, 741).astype(np.int32) * 256 + 77
+    body = b"".join(int(v & 0xFFFFFF).to_bytes(3, "little") for v in pcm24)
+    hdr = b"WAVEfmt " + struct.pack("<IHHIIHH", 16, 1, 1, 44100, 44100 * 3, 3, 24) + b"data" + struct.pack("<I", len(body))
+    (d / "rec_22_s24.wav").write_bytes(b"RIFF" + struct.pack("<I", len(hdr) + len(body)) + hdr + body)
     bird = str(d / "bird_dict.json")
     with open(bird, "w") as f:
         json.dump({f"Species {i}": i for i in range(1, 151)}, f)
@@ -112,7 +117,8 @@ def test_pipelined_directory_equals_file_by_file(tmp_path, group_tiles):
 
     c_seq, t_seq = run(False)
     c_pipe, t_pipe = run(True)
-    assert len(t_seq) == 10 and t_pipe == t_seq
+    assert len(t_seq) == 12 and t_pipe == t_seq and "rec_21_48k.txt" in t_seq and "rec_22_s24.txt" in t_seq
+    assert c_seq["failed"] == c_pipe["failed"] == 1
     for k in ("files", "tiles", "detections", "frames"):
         assert c_pipe[k] == c_seq[k], k
     assert c_pipe["detections"] > 0

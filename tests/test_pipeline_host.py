@@ -77,7 +77,10 @@ def test_plan_groups_channels_and_rejects():
     assert [g.channels for g in groups] == [1, 2, 1]
     assert groups[1].n_values == 2 * 2 * 3 * 44100
     assert [r[0].path for r in rejected] == ["f005.wav", "f006.wav", "long.wav"]
-    assert "48000" in rejected[0][1] and rejected[2][1] == pl.LONG_REASON
+    assert rejected[0][1] == pl.SOLO_REASON and rejected[2][1] == pl.LONG_REASON
+    # another sample format goes the same way as another rate: decoded on the one-file path
+    g2, r2 = pl.plan_groups([pl.WavInfo("f24.wav", 44100, 1, 44100, pcm16=False), _info(1, 3)], CONST, 1000)
+    assert [f.path for g in g2 for f in g.files] == ["f001.wav"] and r2[0][1] == pl.SOLO_REASON
 
 
 def test_probe_and_read_into(tmp_path):
@@ -101,7 +104,8 @@ def test_probe_and_read_into(tmp_path):
     assert "File loading failed" in pl.probe_wav(str(bad)).error
     with wave.open(str(tmp_path / "u8.wav"), "wb") as w:
         w.setnchannels(1); w.setsampwidth(1); w.setframerate(44100); w.writeframes(bytes(100))
-    assert "PCM16" in pl.probe_wav(str(tmp_path / "u8.wav")).error
+    iu = pl.probe_wav(str(tmp_path / "u8.wav"))
+    assert iu.error is None and not iu.pcm16 and iu.n_samples == 100      # decodable, but not on the batched PCM16 path
     # truncated data (header promises more than the file holds, cut in the middle of a frame): both readers yield the
     # whole frames that are there
     raw = open(pm, "rb").read()
@@ -111,7 +115,9 @@ def test_probe_and_read_into(tmp_path):
     got = np.zeros(1000, dtype=np.int16)
     pl.read_into(ic, got)
     seq, _ = synth.read_wav_pcm16(str(tmp_path / "cut.wav"))
-    assert np.array_equal(got, mono[:1000]) and np.array_equal(seq, mono[:1000])
+    from birdsoundclassif_b200 import audio_io
+    seq2, sr2 = audio_io.read_wav(str(tmp_path / "cut.wav"))
+    assert np.array_equal(got, mono[:1000]) and np.array_equal(seq, mono[:1000]) and np.array_equal(seq2, mono[:1000]) and sr2 == 44100
 
 
 def test_pipeline_needs_cuda(tmp_path):
