@@ -75,6 +75,8 @@ def parse():
     ap.add_argument("--detect-files", type=int, default=2, help="ten-minute wavs per GPU in the detect leg's night slice")
     ap.add_argument("--detect-ref-files", type=int, default=16, help="cfg0 files the unpatched reference flow is timed on (N = 1)")
     ap.add_argument("--no-detect-reference", action="store_true")
+    ap.add_argument("--no-stress", action="store_true", help="skip the BASELINE configs[4] leg (n_fft 4410 / hop 44 front-end, NMS at N = 500 / 5 000 / 20 000)")
+    ap.add_argument("--stress-clips", type=int, default=128)
     ap.add_argument("--parity-clips", type=int, default=8, help="clips of the batch checked against the oracle after timing")
     ap.add_argument("--cpu-clips", type=int, default=0, help="clips in the CPU baseline sample (0 = 8 per core; 4 per core and step for --impl reference)")
     return ap.parse_args()
@@ -258,6 +260,88 @@ def bind_near_gpu(index: int):
     return None
 
 
+# ------------------------------------------------------------------ stress leg ----------------
+def stress_leg(a, dev):
+    """BASELINE configs[4]: process_file(freq_accuracy=10.0, dt=0.001) -> n_fft 4410 / hop 44 (prepare_dataset.py:108,
+    125-126) on `--stress-clips` 60 s clips with dense call bursts (20 calls/s), and the greedy NMS on dense synthetic
+    candidate boxes at N = 4 x 500 (RPN), 5 000 and 20 000 (file merge).  Device-resident inputs, CUDA events."""
+    import torch
+    from birdsoundclassif_b200 import frontend, postproc, synth
+    from oracle import frontend_oracle as fo, postproc_oracle as po
+    out = {}
+    kw = dict(freq_accuracy=10.0, dt=0.001)
+    plan = frontend.FrontendPlan(**kw)
+    n = int(round(a.seconds * SAMPLE_RATE))
+    base = [torch.from_numpy(synth.synth_pcm(a.seconds, 4000 + i, calls_per_s=20.0)[:n]).to(dev) for i in range(4)]
+    pcm = torch.cat([base[i % 4] for i in range(a.stress_clips)])
+    offs = [i * n for i in range(a.stress_clips + 1)]
+    n_frames, tile_off, _ = plan.query_batch([n] * a.stress_clips)
+    frames = int(sum(n_frames))
+    tiles = torch.empty((tile_off[-1], 1, plan.n_bins, plan.w_pix), dtype=torch.float32, device=dev)
+    for _ in range(3):
+        plan.run_batch(pcm, offs, out=tiles)
+    torch.cuda.synchronize()
+    plan.set_profiling(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k = 5
+    e0.record()
+    for _ in range(k):
+        plan.run_batch(pcm, offs, out=tiles)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / k
+    kern, runs = plan.get_profile_kernels()
+    plan.set_profiling(False)
+    listed, cap, n_px = plan.last_listed()
+    peak, _ = peaks()
+    bpf = 2 * plan.const["HOP_LENGTH"] + 4 * plan.n_bins
+    ref = np.stack(fo.process(base[0].cpu().numpy(), fo.derive_params(**kw)).tiles)
+    err = np.abs(tiles[tile_off[0]:tile_off[1], 0].cpu().numpy().astype(np.float64) - ref)
+    hours = a.stress_clips * a.seconds / 3600.0
+    out["frontend"] = {"workload": f"{a.stress_clips} x {a.seconds:g} s clips, 20 calls/s, n_fft {plan.const['WIN_LENGTH']} / hop "
+                                   f"{plan.const['HOP_LENGTH']} (process_file(freq_accuracy=10, dt=0.001))", "impl": plan.impl,
+                       "audio_hours_per_s": hours / (ms / 1e3), "ms_per_step": ms, "frames": frames, "tiles": int(tile_off[-1]),
+                       "kernels_ms": {kk: v / max(runs, 1) for kk, v in kern.items()},
+                       "algorithmic_bytes_per_frame": bpf,
+                       "slide_kernel_gbs": frames * bpf / (kern["stft"] / max(runs, 1) / 1e3) / 1e9,
+                       "slide_kernel_frac_of_hbm_peak": frames * bpf / (kern["stft"] / max(runs, 1) / 1e3) / 1e9 / peak,
+                       "frontend_frac_of_hbm_peak": frames * bpf / (ms / 1e3) / 1e9 / peak,
+                       "refine_blocks_listed": listed, "refine_list_capacity": cap, "refine_pixels_recomputed": n_px,
+                       "parity": {"clip": 0, "max_abs_err_norm": float(err.max()), "tolerance": 1e-4, "ok": bool(err.max() <= 1e-4)}}
+    del tiles, pcm
+    plan.close()
+    torch.cuda.empty_cache()
+    # ---- NMS on dense boxes: a burst of overlapping candidates around a few hundred call sites
+    rng = np.random.default_rng(4)
+    nms = {}
+    for name, B, N, th in (("rpn_4x500_t0.7", 4, 500, 0.7), ("merge_1x5000_t0.3", 1, 5000, 0.3), ("merge_1x20000_t0.3", 1, 20000, 0.3)):
+        cx = rng.integers(0, 1024 if B > 1 else 200000, (B, max(1, N // 40), 1)).repeat(40, axis=2).reshape(B, -1)[:, :N]
+        cy = rng.integers(20, 350, cx.shape)
+        x1 = cx + rng.integers(-12, 12, cx.shape); y1 = cy + rng.integers(-12, 12, cx.shape)
+        boxes = np.stack([x1, y1, x1 + rng.integers(5, 90, cx.shape), y1 + rng.integers(5, 60, cx.shape)], -1).astype(np.float32)
+        scores = rng.random(cx.shape).astype(np.float32)
+        tb = torch.from_numpy(boxes).to(dev)
+        for _ in range(3):
+            keep_idx, keep_cnt = postproc.nms_keep(tb, th)
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        f0.record()
+        for _ in range(reps):
+            keep_idx, keep_cnt = postproc.nms_keep(tb, th)
+        f1.record()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        want = po.nms(boxes, scores, th, N, True)[2]
+        cpu_us = (time.perf_counter() - t0) * 1e6
+        cnt = keep_cnt.tolist()
+        got = [keep_idx[b, :cnt[b]].tolist() for b in range(B)]
+        nms[name] = {"gpu_us": f0.elapsed_time(f1) / reps * 1e3, "cpu_oracle_us": cpu_us, "kept": cnt,
+                     "keep_lists_identical": got == [list(w) for w in want]}
+    out["nms"] = nms
+    return out
+
+
 # ------------------------------------------------------------------ B200 arm ------------------
 def run_b200(a):
     import torch
@@ -357,10 +441,25 @@ def run_b200(a):
         parity = {"clips": pick, "pixels": cnt, "max_abs_err_norm": worst, "frac_gt_1e-4": over / cnt,
                   "rms": float(np.sqrt(sq / cnt)), "tolerance": 1e-4, "ok": worst <= 1e-4}
 
+    # ---- BASELINE configs[4]: stress parameters (rank 0, N = 1) -----------------------------------------------
+    stress = None
+    if not a.no_stress and world == 1:
+        n_tiles_total, n_out_bytes, n_in_bytes = int(tile_off[-1]), tiles.numel() * 4, pcm.numel() * 2
+        del tiles, pcm
+        plan._ws = None
+        torch.cuda.empty_cache()
+        try:
+            stress = stress_leg(a, dev)
+        except Exception as e:
+            import traceback
+            stress = {"error": f"{type(e).__name__}: {e}", "trace": traceback.format_exc()[-1500:]}
+        tiles = pcm = torch.empty(0, device=dev)
+
     # ---- audio-hours/s THROUGH nbm_detect (wav files -> reference CNN -> .txt), files sharded over the ranks ----
     detect = None
     if not a.no_detect:
-        n_tiles_total, n_out_bytes, n_in_bytes = int(tile_off[-1]), tiles.numel() * 4, pcm.numel() * 2
+        if stress is None:
+            n_tiles_total, n_out_bytes, n_in_bytes = int(tile_off[-1]), tiles.numel() * 4, pcm.numel() * 2
         del tiles, pcm
         plan._ws = None
         torch.cuda.empty_cache()
@@ -370,7 +469,7 @@ def run_b200(a):
         except Exception as e:                              # the headline must still be printed
             import traceback
             detect = {"error": f"{type(e).__name__}: {e}", "trace": traceback.format_exc()[-1500:]}
-    else:
+    elif stress is None:
         n_tiles_total, n_out_bytes, n_in_bytes = int(tile_off[-1]), tiles.numel() * 4, pcm.numel() * 2
 
     # ---- gather: max time over ranks, totals (NCCL all_gather of a small vector) ----------------
@@ -439,6 +538,8 @@ def run_b200(a):
                        "note": "FrontendPlan.run_batch_from_host: pinned host PCM16 -> H2D in 64-file chunks on a side stream, "
                                "overlapped with the front-end; tiles stay on the device for the detector; "
                                "per-file (s_min, s_max) read back"}
+    if stress is not None:
+        line["stress"] = stress
     if detect is not None:
         line["detect"] = detect
     if not a.no_cpu_baseline and world == 1:          # rank 0 at N = 1 only: at N > 1 the ranks share the host cores

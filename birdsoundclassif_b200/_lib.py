@@ -42,7 +42,7 @@ SIGNATURES = {
     "nbm_frontend_set_profiling": (C.c_int, [_p, _i32]),
     "nbm_frontend_get_profile": (C.c_int, [_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64)]),
     "nbm_frontend_get_profile_kernels": (C.c_int, [_p, C.POINTER(C.c_double), C.POINTER(_i64)]),
-    "nbm_frontend_last_listed": (C.c_int, [_p, C.POINTER(_i64), C.POINTER(_i64)]),
+    "nbm_frontend_last_listed": (C.c_int, [_p, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "nbm_tiles_to_u8": (C.c_int, [_p, _i64, _p, _p]),
     "nbm_make_anchors": (C.c_int, [_i32, C.POINTER(C.c_double), _i32, C.POINTER(_i64), _i32, _i32, _i32, _i32, _p]),
     "nbm_decode_boxes": (C.c_int, [_p, _p, _i32, _i32, _i32, _f32, _f32, _f32, _p, _p, _p]),

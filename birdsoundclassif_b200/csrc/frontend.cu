@@ -349,21 +349,49 @@ __device__ __forceinline__ double warp_sum(double v) {
 // broadcast load from the float64 table per step), the lane's own factor is applied once at the end.  Per sample and lane
 // that leaves four float64 operations: the int16 sample becomes a double by the 2^52 trick (no conversion unit), times the
 // window (exactly the reference's float32 x float64 product, rounded once), and two fused multiply-adds.
-__global__ void __launch_bounds__(256)
+struct GroupKey {
+    int seg, bin0, rows, nfr, frame0;
+    __device__ explicit GroupKey(unsigned long long key)
+        : seg((int)(key >> 42)), bin0((int)((key >> 32) & 1023)), rows((int)((key >> 28) & 15) + 1),
+          nfr((int)((key >> 27) & 1) + 1), frame0((int)(key & GROUP_MAX_FRAME)) {}
+};
+
+__global__ void __launch_bounds__(256, 3)
 refine_groups_kernel(RefineParams R, const SegDesc *__restrict__ segs, const unsigned long long *__restrict__ cand,
                      const unsigned int *__restrict__ cand_count, unsigned int cand_cap, const float *__restrict__ flag_db,
                      float *__restrict__ spec, const void *__restrict__ pcm, int dtype, int channels,
-                     unsigned int *__restrict__ file_min) {
+                     unsigned int *__restrict__ file_min, unsigned int *__restrict__ n_recomputed) {
     const int lane = threadIdx.x & 31;
     const unsigned int n = min(*cand_count, cand_cap);
     const unsigned int warps = gridDim.x * (blockDim.x >> 5);
     const bool fast = dtype == NBM_PCM_INT16 && channels == 1;
     constexpr double MAGIC = 4503601774854144.0;            // 2^52 + 2^31
-    for (unsigned int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < n; c += warps) {
-        const unsigned long long key = cand[c];
-        const int seg = (int)(key >> 42), bin0 = (int)((key >> 32) & 1023), rows = (int)((key >> 28) & 15) + 1;
-        const int nfr = (int)((key >> 27) & 1) + 1, frame0 = (int)(key & GROUP_MAX_FRAME);
-        const SegDesc sd = segs[seg];
+    const float floor_mag = (float)R.min_level;
+    unsigned int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    unsigned long long key = c < n ? cand[c] : 0ull;
+    // The kernel is latency-bound (a block's pixels and its 2.9 KB of samples are scattered reads that left L2 long ago):
+    // while a block is being worked on, the next one's samples and pixel rows are pulled into L2.
+    auto prefetch = [&](unsigned long long k2) {
+        const GroupKey g(k2);
+        const SegDesc sd = segs[g.seg];
+        const long long s_lo = (long long)g.frame0 * R.hop - R.N / 2;
+        const long long a = max(s_lo, 0ll), b = min(s_lo + R.N + R.hop, sd.n_samples);
+        const size_t esz = (dtype == NBM_PCM_INT16 ? 2 : 4) * (size_t)channels;
+        const char *p0 = reinterpret_cast<const char *>(pcm) + (size_t)(sd.pcm_start + a) * esz;
+        const long long bytes = (b - a) * (long long)esz;
+        for (long long o = (long long)lane * 128; o < bytes; o += 32 * 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + o));
+        if (lane < g.rows)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(spec + sd.spec_off + (long long)(g.bin0 + lane) * sd.row_stride + g.frame0));
+    };
+    if (c < n) prefetch(key);
+    while (c < n) {
+        const unsigned int cn = c + warps;
+        const unsigned long long key_next = cn < n ? cand[cn] : 0ull;
+        if (cn < n) prefetch(key_next);
+        const GroupKey g(key);
+        const int bin0 = g.bin0, frame0 = g.frame0;
+        const SegDesc sd = segs[g.seg];
         // tensor-core blocks: the level their emit warp used; single pixels (CUDA-core kernel) were tested against their own
         // bin's level already and are recomputed unconditionally
         float th = INFINITY;
@@ -372,11 +400,12 @@ refine_groups_kernel(RefineParams R, const SegDesc *__restrict__ segs, const uns
             th = flag_db[((2 * (size_t)sd.group0 + frame0 / (GF / 2)) * R.n_ranges + bin0 / bpr) * 4 + (bin0 % bpr) / R.bins_per_slot];
         }
         const int row = lane >> 1, e = lane & 1;
-        const bool mine = row < rows && e < nfr;
+        const bool mine = row < g.rows && e < g.nfr;
         float *px = spec + sd.spec_off + (long long)(bin0 + row) * sd.row_stride + frame0 + e;
         float v = mine ? *px : INFINITY;
         unsigned int todo = __ballot_sync(0xffffffffu, mine && v < th);
         const short *p16 = reinterpret_cast<const short *>(pcm) + sd.pcm_start;
+        if (lane == 0 && todo) atomicAdd(n_recomputed, (unsigned int)__popc(todo));
         while (todo) {
             const int l = __ffs((int)todo) - 1;
             todo &= todo - 1;
@@ -385,28 +414,53 @@ refine_groups_kernel(RefineParams R, const SegDesc *__restrict__ segs, const uns
             const int qstep = (int)((k * 32) % R.N);
             int q = 0;                                       // (32 j k) mod N
             double ar = 0.0, ai = 0.0;
-            constexpr int UB = 6;                           // samples in flight per lane
-            for (int i0 = lane; i0 < R.N; i0 += 32 * UB) {
-                double x[UB];
+            constexpr int UB = 14;                          // samples in flight per lane: three rounds for n_fft = 1324
+            if (fast && s0 >= 0 && s0 + R.N <= sd.n_samples) {
+                // window inside the segment (all but its first and last five frames): no per-sample bounds tests, pointers
+                // that advance by a constant, loads of a whole round issued before the first use
+                const short *ps = p16 + s0 + lane;
+                const double *ph = R.hann64 + lane;
+                const double2 *tw = R.tw64;
+                int i = lane;
+                for (; i + 32 * (UB - 1) < R.N; i += 32 * UB, ps += 32 * UB, ph += 32 * UB) {
+                    int xi[UB];
+                    double h[UB];
 #pragma unroll
-                for (int u = 0; u < UB; ++u) {
-                    const int i = i0 + 32 * u;
+                    for (int u = 0; u < UB; ++u) xi[u] = __ldg(ps + 32 * u);
+#pragma unroll
+                    for (int u = 0; u < UB; ++u) h[u] = ph[32 * u];
+#pragma unroll
+                    for (int u = 0; u < UB; ++u) {
+                        const double2 w = tw[q];            // same address in every lane
+                        const double x = (__hiloint2double(0x43300000, xi[u] ^ 0x80000000) - MAGIC) * h[u];
+                        ar = fma(x, w.x, ar);
+                        ai = fma(-x, w.y, ai);
+                        q += qstep;
+                        q -= q >= R.N ? R.N : 0;
+                    }
+                }
+                for (; i < R.N; i += 32, ps += 32, ph += 32) {
+                    const double2 w = tw[q];
+                    const double x = (__hiloint2double(0x43300000, (int)__ldg(ps) ^ 0x80000000) - MAGIC) * ph[0];
+                    ar = fma(x, w.x, ar);
+                    ai = fma(-x, w.y, ai);
+                    q += qstep;
+                    q -= q >= R.N ? R.N : 0;
+                }
+            } else {
+                for (int i = lane; i < R.N; i += 32) {
                     const long long sx = s0 + i;
-                    x[u] = 0.0;
-                    if (i < R.N && sx >= 0 && sx < sd.n_samples) {    // centre padding, pad_mode='constant'
+                    if (sx >= 0 && sx < sd.n_samples) {     // centre padding, pad_mode='constant'
                         // the reference multiplies the float32 sample (int16 / 32768, exact) by the float64 window: one rounding
                         const double xs = fast ? __hiloint2double(0x43300000, (int)__ldg(p16 + sx) ^ 0x80000000) - MAGIC
                                                : 32768.0 * (double)load_sample(pcm, dtype, channels, sd.pcm_start + sx);
-                        x[u] = xs * R.hann64[i];            // hann64 = window / 32768 (a power of two: still one rounding)
+                        const double x = xs * R.hann64[i];  // hann64 = window / 32768 (a power of two: still one rounding)
+                        const double2 w = R.tw64[q];
+                        ar = fma(x, w.x, ar);
+                        ai = fma(-x, w.y, ai);
                     }
-                }
-#pragma unroll
-                for (int u = 0; u < UB; ++u) {
-                    const double2 w = R.tw64[q];            // same address in every lane
-                    ar = fma(x[u], w.x, ar);
-                    ai = fma(-x[u], w.y, ai);
                     q += qstep;
-                    if (q >= R.N) q -= R.N;
+                    q -= q >= R.N ? R.N : 0;
                 }
             }
             {
@@ -418,14 +472,18 @@ refine_groups_kernel(RefineParams R, const SegDesc *__restrict__ segs, const uns
             ar = warp_sum(ar);
             ai = warp_sum(ai);
             const float re = (float)ar, im = (float)ai;                             // stored complex64
-            const float mag = (float)hypot((double)re, (double)im);                // np.abs -> float32
-            const float db = (float)(20.0 * log10(fmax(R.min_level, (double)mag)));
+            // np.abs -> float32 (re^2 + im^2 is exact in double), then 20 log10(max(min_level, .)): the dB value only has to
+            // be good to float32 (it is normalised and handed to the model as float32), so log2f, not the float64 routine
+            const float mag = (float)sqrt((double)re * (double)re + (double)im * (double)im);
+            const float db = 6.0205999132796239f * log2f(fmaxf(floor_mag, mag));
             if (lane == l) { v = db; *px = db; }
         }
         // the block's exact minimum (it was left out of the min/max partial)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
         if (lane == 0) atomicMin(file_min + sd.file, float_to_ordered(v));
+        c = cn;
+        key = key_next;
     }
 }
 
@@ -800,7 +858,7 @@ int build_layout(const nbm_frontend_plan *pl, const int64_t *sizes, const int64_
     B.o_segs = take(B.segs.size() * sizeof(SegDesc));
     B.o_files = take(B.files.size() * sizeof(FileDesc));
     B.upload_bytes = o;
-    B.o_cnt = take(((size_t)n_files + 1) * sizeof(unsigned int));    // per-file exact minimum (ordered uint) | candidates listed
+    B.o_cnt = take(((size_t)n_files + 2) * sizeof(unsigned int));    // per-file exact minimum (ordered uint) | blocks listed | pixels recomputed
     B.o_mm = take((size_t)B.groups * (pl->tc ? (GF / tc_chain_frames()) * tc_n_ranges(pl->tc) * tc_slots_per_range() : 1) *
                   sizeof(float2));                                  // min/max partials
     B.o_flag = take(pl->tc ? (size_t)B.groups * 2 * tc_n_ranges(pl->tc) * tc_slots_per_range() * sizeof(float) : 0);   // flag level per (chain, range, emit warp)
@@ -1077,7 +1135,7 @@ extern "C" int nbm_frontend_run_batch(const nbm_frontend_plan *cpl, const void *
     cudaStream_t sc = pl->s_hi;
     NBM_CUDA(cudaStreamWaitEvent(sc, pl->ev_in, 0));
     NBM_CUDA(cudaMemsetAsync(d_file_min, 0xff, (size_t)n_files * sizeof(unsigned int), sc));
-    NBM_CUDA(cudaMemsetAsync(d_cand_count, 0, sizeof(unsigned int), sc));
+    NBM_CUDA(cudaMemsetAsync(d_cand_count, 0, 2 * sizeof(unsigned int), sc));
     if (prof) NBM_CUDA(cudaEventRecord(pl->ev[0], sc));
     if (use_tc) {
         // globally numbered anchors: segment s owns group0[s] + s .. group0[s] + s + tiles[s]
@@ -1097,8 +1155,8 @@ extern "C" int nbm_frontend_run_batch(const nbm_frontend_plan *cpl, const void *
     {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
-        refine_groups_kernel<<<sms * 4, 256, 0, sc>>>(rp, d_segs, d_cand, d_cand_count, B.cand_cap, d_flag, d_spec, d_pcm,
-                                                     pcm_dtype, channels, d_file_min);
+        refine_groups_kernel<<<sms * 3, 256, 0, sc>>>(rp, d_segs, d_cand, d_cand_count, B.cand_cap, d_flag, d_spec, d_pcm,
+                                                     pcm_dtype, channels, d_file_min, d_cand_count + 1);
         minmax_kernel<<<n_files, 256, 0, sc>>>(rp, d_segs, d_files, d_tile_mm, d_file_min, d_spec, d_pcm, pcm_dtype, channels,
                                                d_minmax, 0);
     }
@@ -1114,15 +1172,16 @@ extern "C" int nbm_frontend_run_batch(const nbm_frontend_plan *cpl, const void *
     return NBM_OK;
 }
 
-extern "C" int nbm_frontend_last_listed(nbm_frontend_plan *pl, int64_t *listed, int64_t *capacity) {
+extern "C" int nbm_frontend_last_listed(nbm_frontend_plan *pl, int64_t *listed, int64_t *capacity, int64_t *recomputed) {
     NBM_REQUIRE(pl && listed && capacity, "null argument");
     std::lock_guard<std::mutex> lock(pl->mu);
     NBM_REQUIRE(pl->last_count, "no run yet");
-    unsigned int n = 0;
+    unsigned int n[2] = {0, 0};
     NBM_CUDA(cudaStreamSynchronize(pl->last_stream));
-    NBM_CUDA(cudaMemcpy(&n, pl->last_count, sizeof(n), cudaMemcpyDeviceToHost));
-    *listed = n;
+    NBM_CUDA(cudaMemcpy(n, pl->last_count, sizeof(n), cudaMemcpyDeviceToHost));
+    *listed = n[0];
     *capacity = pl->last_cap;
+    if (recomputed) *recomputed = n[1];
     return NBM_OK;
 }
 

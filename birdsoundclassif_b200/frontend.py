@@ -169,10 +169,11 @@ class FrontendPlan:
         return dict(zip(("anchor", "stft", "minmax", "tile"), list(ms))), n.value
 
     def last_listed(self):
-        """(blocks listed for float64 refinement by the last run, capacity of the list); waits for that run."""
-        n, cap = C.c_int64(), C.c_int64()
-        _lib.check(_lib.lib().nbm_frontend_last_listed(self._h, C.byref(n), C.byref(cap)), "nbm_frontend_last_listed")
-        return n.value, cap.value
+        """(blocks listed for float64 refinement by the last run, capacity of the list, pixels recomputed); waits for
+        that run."""
+        n, cap, px = C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.check(_lib.lib().nbm_frontend_last_listed(self._h, C.byref(n), C.byref(cap), C.byref(px)), "nbm_frontend_last_listed")
+        return n.value, cap.value, px.value
 
     def run_batch_from_host(self, host_pcm: torch.Tensor, sample_offsets, out=None, files_per_chunk=64):
         """run_batch for mono PCM16 in PINNED host memory: the files are copied to the device in chunks on a
@@ -242,6 +243,7 @@ class File_Processor:
     H_PIX = 375      # px          prepare_dataset.py:96
     LOW_FREQ = 500   # hz          prepare_dataset.py:97
     FREQ = 44100     # hz          prepare_dataset.py:98
+    requantise_long = True      # long recordings: the pieces pass through PCM16 temp files upstream (see _process_long)
 
     def __init__(self, filepath, extra_str_label="", labels=None):
         if labels is not None:
@@ -302,6 +304,17 @@ class File_Processor:
         if cuts[-1] == cuts[-2]:
             cuts.pop()
         ch = 1 if dev.dim() == 1 else dev.shape[1]
+        if self.requantise_long:
+            # The reference writes every piece with soundfile.write(outp, float32 data, 44100) -- for .wav that is subtype
+            # PCM_16, libsndfile's float -> short conversion lrintf(x * 0x7FFF) (pcm.c, norm_float on) -- and reads it back
+            # as int16 / 32768 (prepare_dataset.py:199, 162).  x = s / 32768 for a PCM16 source, so samples with
+            # |s| >= 16384 come back one LSB smaller.  Restated here in the same float32 arithmetic (libsndfile is not in
+            # this image, so this line is unpinned; requantise_long = False keeps the source samples).
+            x = dev.to(torch.float32) / 32768.0 if dev.dtype == torch.int16 else dev
+            if ch > 1:
+                x = x.mean(dim=1)                                   # librosa.load mixes to mono before the split
+                ch = 1
+            dev = torch.round(x * 32767.0).clamp_(-32768, 32767).to(torch.int16)
         tiles, tile_off, minmax = plan.run_batch(dev.reshape(-1), cuts, channels=ch)
         self.piece_spectrogram_lengths = [plan.query(cuts[k + 1] - cuts[k])[0] for k in range(len(cuts) - 1)]
         self.piece_samples = L

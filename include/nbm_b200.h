@@ -114,8 +114,9 @@ int nbm_frontend_get_profile_kernels(nbm_frontend_plan *plan, double *ms4, int64
 
 /* Diagnostics of the float64 refinement pass of the LAST run (waits for it; valid while that run's workspace is alive):
  * *listed = pixel blocks the transform put on the refinement list (counted even when the list was full),
- * *capacity = entries the list could hold.  listed > capacity means some pixels kept their float32 values. */
-int nbm_frontend_last_listed(nbm_frontend_plan *plan, int64_t *listed, int64_t *capacity);
+ * *capacity = entries the list could hold (listed > capacity means some pixels kept their float32 values),
+ * *recomputed (optional) = pixels of those blocks that were below the flag level and recomputed in float64. */
+int nbm_frontend_last_listed(nbm_frontend_plan *plan, int64_t *listed, int64_t *capacity, int64_t *recomputed);
 
 /* Dataset images from detector tiles: out = uint8(round_half_even(tile * 255)), the quantisation
  * prepare_dataset() applies before writing a PNG (prepare_dataset.py:85).  d_tiles 16-byte aligned,

@@ -23,7 +23,7 @@ flat = torch.from_numpy(np.concatenate(pcms)).cuda()
 offs = np.concatenate([[0], np.cumsum([len(p) for p in pcms])]).tolist()
 big = flat.repeat(max(1, 256 // n_clips))
 big_offs = (np.arange(big.numel() // len(pcms[0]) + 1) * len(pcms[0])).tolist()
-for rel in ("-200", "-66", "-64", "-62", "-60", "-58"):
+for rel in ("-64", "-62", "-60"):
     os.environ["NBM_REFINE_REL_DB"] = rel
     plan = frontend.FrontendPlan()
     tiles, toff, mm = plan.run_batch(flat, offs)
@@ -40,8 +40,8 @@ for rel in ("-200", "-66", "-64", "-62", "-60", "-58"):
         plan.run_batch(big, big_offs, out=out)
     k, runs = plan.get_profile_kernels()
     plan.set_profiling(False)
-    listed, cap = plan.last_listed()
+    listed, cap, n_px = plan.last_listed()
     print(f"rel {rel:>5s} dB: worst {worst:.3e}  >1e-4: {over:6d} of {cnt}  rms {np.sqrt(sq / cnt):.2e} | {len(big_offs) - 1} clips: "
-          f"anchors {k['anchor'] / runs:.2f} slides {k['stft'] / runs:.2f} refine+minmax {k['minmax'] / runs:.3f} tiles {k['tile'] / runs:.2f} ms, {listed} blocks listed (cap {cap})")
+          f"anchors {k['anchor'] / runs:.2f} slides {k['stft'] / runs:.2f} refine+minmax {k['minmax'] / runs:.3f} tiles {k['tile'] / runs:.2f} ms, {listed} blocks listed (cap {cap}), {n_px} pixels recomputed")
     del out
     plan.close()

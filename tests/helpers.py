@@ -69,3 +69,12 @@ def dets_to_flat(dets, num_classes):
                 ss.append(sc.reshape(-1).astype(np.float32))
     return counts, (np.concatenate(bb) if bb else np.zeros((0, 4), np.float32)), \
         (np.concatenate(ss) if ss else np.zeros((0,), np.float32))
+
+
+def requant_piece(p):
+    """What a piece of a > 3401 s recording becomes on its way through the reference's temp wav file
+    (prepare_dataset.py:199: soundfile.write of float32 data as PCM_16 = lrintf(x * 0x7FFF); read back / 32768)."""
+    x = p.astype(np.float32) / np.float32(32768.0)
+    if x.ndim == 2:
+        x = x.mean(axis=1, dtype=np.float32)
+    return np.clip(np.rint(x * np.float32(32767.0)), -32768, 32767).astype(np.int16)

@@ -246,8 +246,9 @@ def test_long_recording_is_cut_into_independent_pieces(fe, monkeypatch):
     img_db, ann = fp.process_pcm(torch.from_numpy(pcm).cuda())
     assert isinstance(img_db, list) and len(img_db) == 3 and ann == []
     assert (fp.W_PIX, fp.HOP_SPECTRO, fp.piece_samples) == (1024, 819, L)
+    assert (np.abs(pcm.astype(np.int32)) >= 16384).any()           # the requantisation is not the identity on this clip
     for k, tiles in enumerate(img_db):
-        piece = pcm[k * L:(k + 1) * L]
+        piece = H.requant_piece(pcm[k * L:(k + 1) * L])             # the pieces pass through PCM16 temp files upstream
         r = fo.process(piece, fo.derive_params())
         assert fp.piece_spectrogram_lengths[k] == r.spectrogram_length and len(tiles) == len(r.tiles)
         assert_tiles_close(tiles.cpu().numpy(), np.stack(r.tiles), f"piece {k}")
@@ -261,8 +262,14 @@ def test_long_recording_is_cut_into_independent_pieces(fe, monkeypatch):
     # stereo
     st = np.stack([pcm, synth.synth_pcm(5.3, 62)], axis=1)
     img4, _ = fe.File_Processor("s.wav").process_pcm(torch.from_numpy(st).cuda())
-    _, alone = _gpu_tiles(fe, st[L:2 * L])
+    _, alone = _gpu_tiles(fe, H.requant_piece(st[L:2 * L]))
     assert len(img4) == 3 and torch.equal(img4[1], alone)
+    # requantise_long = False keeps the source samples
+    fp5 = fe.File_Processor("k.wav")
+    fp5.requantise_long = False
+    img5, _ = fp5.process_pcm(torch.from_numpy(pcm).cuda())
+    _, alone = _gpu_tiles(fe, pcm[L:2 * L])
+    assert torch.equal(img5[1], alone)
 
 
 def test_full_size_batch_properties(fe):

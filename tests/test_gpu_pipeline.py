@@ -137,8 +137,9 @@ def test_long_recording_detection(tmp_path, monkeypatch):
     synth.write_wav(str(tmp_path / "b_short.wav"), synth.synth_pcm(3.0, 811))
     pieces = tmp_path / "pieces"
     pieces.mkdir()
+    from tests import helpers as H
     for k in range(3):
-        synth.write_wav(str(pieces / f"p{k}.wav"), pcm[k * L:(k + 1) * L])
+        synth.write_wav(str(pieces / f"p{k}.wav"), H.requant_piece(pcm[k * L:(k + 1) * L]))
     bird = str(tmp_path / "bird_dict.json")
     with open(bird, "w") as f:
         json.dump({f"Species {i}": i for i in range(1, 151)}, f)
