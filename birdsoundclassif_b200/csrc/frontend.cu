@@ -74,7 +74,7 @@ __device__ __forceinline__ void fold_idx(int L, int j, int &hi, int &lo) {
 __global__ void __launch_bounds__(512, 1)
 stft_db_kernel(KParams P, const SegDesc *__restrict__ segs, int n_segs, const void *__restrict__ pcm,
                int dtype, int channels, float *__restrict__ spec, float2 *__restrict__ tile_mm, int group_begin,
-               float rel_db, unsigned long long *__restrict__ cand,
+               float rel_db, uint4 *__restrict__ cand,
                unsigned int *__restrict__ cand_count, unsigned int cand_cap) {
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
@@ -278,7 +278,7 @@ stft_db_kernel(KParams P, const SegDesc *__restrict__ segs, int n_segs, const vo
                 if (v < th) {
                     const unsigned int at = atomicAdd(cand_count, 1u);
                     if (at < cand_cap) {
-                        cand[at] = pack_group(lo_s, b, 1, 1, col0 + c);
+                        cand[at] = list_entry(pack_group(lo_s, b, 1, 1, col0 + c), INFINITY);   // tested against its own bin's level already
                         listed = true;
                     }
                 }
@@ -356,9 +356,9 @@ struct GroupKey {
           nfr((int)((key >> 27) & 1) + 1), frame0((int)(key & GROUP_MAX_FRAME)) {}
 };
 
-__global__ void __launch_bounds__(256, 3)
-refine_groups_kernel(RefineParams R, const SegDesc *__restrict__ segs, const unsigned long long *__restrict__ cand,
-                     const unsigned int *__restrict__ cand_count, unsigned int cand_cap, const float *__restrict__ flag_db,
+__global__ void __launch_bounds__(256, 4)
+refine_groups_kernel(RefineParams R, const SegDesc *__restrict__ segs, const uint4 *__restrict__ cand,
+                     const unsigned int *__restrict__ cand_count, unsigned int cand_cap,
                      float *__restrict__ spec, const void *__restrict__ pcm, int dtype, int channels,
                      unsigned int *__restrict__ file_min, unsigned int *__restrict__ n_recomputed) {
     const int lane = threadIdx.x & 31;
@@ -368,11 +368,11 @@ refine_groups_kernel(RefineParams R, const SegDesc *__restrict__ segs, const uns
     constexpr double MAGIC = 4503601774854144.0;            // 2^52 + 2^31
     const float floor_mag = (float)R.min_level;
     unsigned int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    unsigned long long key = c < n ? cand[c] : 0ull;
+    uint4 ent = c < n ? cand[c] : make_uint4(0, 0, 0, 0);
     // The kernel is latency-bound (a block's pixels and its 2.9 KB of samples are scattered reads that left L2 long ago):
     // while a block is being worked on, the next one's samples and pixel rows are pulled into L2.
-    auto prefetch = [&](unsigned long long k2) {
-        const GroupKey g(k2);
+    auto prefetch = [&](const uint4 &e2) {
+        const GroupKey g(entry_key(e2));
         const SegDesc sd = segs[g.seg];
         const long long s_lo = (long long)g.frame0 * R.hop - R.N / 2;
         const long long a = max(s_lo, 0ll), b = min(s_lo + R.N + R.hop, sd.n_samples);
@@ -384,21 +384,15 @@ refine_groups_kernel(RefineParams R, const SegDesc *__restrict__ segs, const uns
         if (lane < g.rows)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(spec + sd.spec_off + (long long)(g.bin0 + lane) * sd.row_stride + g.frame0));
     };
-    if (c < n) prefetch(key);
+    if (c < n) prefetch(ent);
     while (c < n) {
         const unsigned int cn = c + warps;
-        const unsigned long long key_next = cn < n ? cand[cn] : 0ull;
-        if (cn < n) prefetch(key_next);
-        const GroupKey g(key);
+        const uint4 ent_next = cn < n ? cand[cn] : make_uint4(0, 0, 0, 0);
+        if (cn < n) prefetch(ent_next);
+        const GroupKey g(entry_key(ent));
         const int bin0 = g.bin0, frame0 = g.frame0;
         const SegDesc sd = segs[g.seg];
-        // tensor-core blocks: the level their emit warp used; single pixels (CUDA-core kernel) were tested against their own
-        // bin's level already and are recomputed unconditionally
-        float th = INFINITY;
-        if (R.n_ranges > 0) {
-            const int bpr = R.bins_per_range;
-            th = flag_db[((2 * (size_t)sd.group0 + frame0 / (GF / 2)) * R.n_ranges + bin0 / bpr) * 4 + (bin0 % bpr) / R.bins_per_slot];
-        }
+        const float th = __uint_as_float(ent.z);         // the level the transform kernel tested the block against
         const int row = lane >> 1, e = lane & 1;
         const bool mine = row < g.rows && e < g.nfr;
         float *px = spec + sd.spec_off + (long long)(bin0 + row) * sd.row_stride + frame0 + e;
@@ -414,21 +408,22 @@ refine_groups_kernel(RefineParams R, const SegDesc *__restrict__ segs, const uns
             const int qstep = (int)((k * 32) % R.N);
             int q = 0;                                       // (32 j k) mod N
             double ar = 0.0, ai = 0.0;
-            constexpr int UB = 14;                          // samples in flight per lane: three rounds for n_fft = 1324
+            constexpr int UB = 11;                          // samples in flight per lane: four rounds for n_fft = 1324
             if (fast && s0 >= 0 && s0 + R.N <= sd.n_samples) {
                 // window inside the segment (all but its first and last five frames): no per-sample bounds tests, pointers
                 // that advance by a constant, loads of a whole round issued before the first use
                 const short *ps = p16 + s0 + lane;
                 const double *ph = R.hann64 + lane;
                 const double2 *tw = R.tw64;
-                int i = lane;
-                for (; i + 32 * (UB - 1) < R.N; i += 32 * UB, ps += 32 * UB, ph += 32 * UB) {
+                for (int i = lane; i < R.N; i += 32 * UB, ps += 32 * UB, ph += 32 * UB) {
                     int xi[UB];
                     double h[UB];
 #pragma unroll
-                    for (int u = 0; u < UB; ++u) xi[u] = __ldg(ps + 32 * u);
-#pragma unroll
-                    for (int u = 0; u < UB; ++u) h[u] = ph[32 * u];
+                    for (int u = 0; u < UB; ++u) {          // the last round is partial: a zero weight drops the sample
+                        const bool in = i + 32 * u < R.N;
+                        xi[u] = in ? (int)__ldg(ps + 32 * u) : 0;
+                        h[u] = in ? ph[32 * u] : 0.0;
+                    }
 #pragma unroll
                     for (int u = 0; u < UB; ++u) {
                         const double2 w = tw[q];            // same address in every lane
@@ -438,14 +433,6 @@ refine_groups_kernel(RefineParams R, const SegDesc *__restrict__ segs, const uns
                         q += qstep;
                         q -= q >= R.N ? R.N : 0;
                     }
-                }
-                for (; i < R.N; i += 32, ps += 32, ph += 32) {
-                    const double2 w = tw[q];
-                    const double x = (__hiloint2double(0x43300000, (int)__ldg(ps) ^ 0x80000000) - MAGIC) * ph[0];
-                    ar = fma(x, w.x, ar);
-                    ai = fma(-x, w.y, ai);
-                    q += qstep;
-                    q -= q >= R.N ? R.N : 0;
                 }
             } else {
                 for (int i = lane; i < R.N; i += 32) {
@@ -483,7 +470,7 @@ refine_groups_kernel(RefineParams R, const SegDesc *__restrict__ segs, const uns
         for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
         if (lane == 0) atomicMin(file_min + sd.file, float_to_ordered(v));
         c = cn;
-        key = key_next;
+        ent = ent_next;
     }
 }
 
@@ -776,7 +763,7 @@ namespace {
 // Everything the host derives from the per-file sample counts: STFT chunks (prepare_dataset.py:236),
 // detector windows (:266) with the last window's valid width (:268-278 incl. the seam quirk), the
 // 64-frame groups, and the workspace carve-up
-//   [segs | files | per-file exact minima + candidate counter | min/max partials | flag levels | candidates | anchors | dB bands].
+//   [segs | files | per-file exact minima + list counters | min/max partials | refinement list | anchors | dB bands].
 struct BatchLayout {
     std::vector<SegDesc> segs;
     std::vector<FileDesc> files;
@@ -784,7 +771,7 @@ struct BatchLayout {
     size_t spec_floats = 0;
     long long tiles = 0, n_anchors = 0;
     int groups = 0;
-    size_t o_segs = 0, o_files = 0, o_cnt = 0, o_mm = 0, o_flag = 0, o_cand = 0, o_anchors = 0, o_spec = 0, total = 0;
+    size_t o_segs = 0, o_files = 0, o_cnt = 0, o_mm = 0, o_cand = 0, o_anchors = 0, o_spec = 0, total = 0;
     unsigned int cand_cap = 0;
     size_t upload_bytes = 0;       // segs and files are uploaded from the host
 };
@@ -861,9 +848,8 @@ int build_layout(const nbm_frontend_plan *pl, const int64_t *sizes, const int64_
     B.o_cnt = take(((size_t)n_files + 2) * sizeof(unsigned int));    // per-file exact minimum (ordered uint) | blocks listed | pixels recomputed
     B.o_mm = take((size_t)B.groups * (pl->tc ? (GF / tc_chain_frames()) * tc_n_ranges(pl->tc) * tc_slots_per_range() : 1) *
                   sizeof(float2));                                  // min/max partials
-    B.o_flag = take(pl->tc ? (size_t)B.groups * 2 * tc_n_ranges(pl->tc) * tc_slots_per_range() * sizeof(float) : 0);   // flag level per (chain, range, emit warp)
     B.cand_cap = (unsigned int)std::min<double>(64.0 * 1024 * 1024, std::max<double>(65536.0, pl->cand_frac * (double)B.spec_floats));
-    B.o_cand = take((size_t)B.cand_cap * sizeof(unsigned long long));
+    B.o_cand = take((size_t)B.cand_cap * sizeof(uint4));
     B.o_anchors = take(pl->tc ? tc_anchor_bytes(pl->tc, B.n_anchors) : 0);
     B.o_spec = take(B.spec_floats * sizeof(float) + 16);
     B.total = o;
@@ -1125,8 +1111,7 @@ extern "C" int nbm_frontend_run_batch(const nbm_frontend_plan *cpl, const void *
     rp.n_ranges = use_tc ? tc_n_ranges(pl->tc) : 0;
     rp.tw64 = pl->d_tw64;
     rp.hann64 = pl->d_hann64;
-    float *d_flag = reinterpret_cast<float *>(ws + B.o_flag);
-    auto *d_cand = reinterpret_cast<unsigned long long *>(ws + B.o_cand);
+    auto *d_cand = reinterpret_cast<uint4 *>(ws + B.o_cand);
     unsigned int *d_file_min = reinterpret_cast<unsigned int *>(ws + B.o_cnt), *d_cand_count = d_file_min + n_files;
 
     // caller's stream: descriptors ............................................................. | tiles
@@ -1143,7 +1128,7 @@ extern "C" int nbm_frontend_run_batch(const nbm_frontend_plan *cpl, const void *
         if (rc != NBM_OK) return rc;
         if (prof) NBM_CUDA(cudaEventRecord(pl->ev[1], sc));
         rc = tc_launch_slides(pl->tc, d_segs, (int)B.segs.size(), 0, 0, B.groups, d_pcm, d_spec, d_tile_mm,
-                              ws + B.o_anchors, d_flag, pl->flag_rel_db, d_cand, d_cand_count, B.cand_cap, sc);
+                              ws + B.o_anchors, pl->flag_rel_db, d_cand, d_cand_count, B.cand_cap, sc);
         if (rc != NBM_OK) return rc;
     } else {
         if (prof) NBM_CUDA(cudaEventRecord(pl->ev[1], sc));
@@ -1155,7 +1140,7 @@ extern "C" int nbm_frontend_run_batch(const nbm_frontend_plan *cpl, const void *
     {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
-        refine_groups_kernel<<<sms * 3, 256, 0, sc>>>(rp, d_segs, d_cand, d_cand_count, B.cand_cap, d_flag, d_spec, d_pcm,
+        refine_groups_kernel<<<sms * 4, 256, 0, sc>>>(rp, d_segs, d_cand, d_cand_count, B.cand_cap, d_spec, d_pcm,
                                                      pcm_dtype, channels, d_file_min, d_cand_count + 1);
         minmax_kernel<<<n_files, 256, 0, sc>>>(rp, d_segs, d_files, d_tile_mm, d_file_min, d_spec, d_pcm, pcm_dtype, channels,
                                                d_minmax, 0);

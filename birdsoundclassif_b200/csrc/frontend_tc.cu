@@ -512,14 +512,13 @@ constexpr int PS = 4;                       // shifted-path vectors per fill lan
 // chain -- the recurrence is an integrator, so what a loud call leaves behind when it sweeps through a bin stays in that
 // bin until the next anchor.  In dB this is invisible unless the pixel itself lies ~60 dB below that magnitude (a deep
 // null, or a quiet frame right after a loud one).  The recurrence therefore tracks max |R| per bin (one FMNMX3 per step);
-// each emit warp takes the largest over its 32 rows and their halo as its reference, writes the resulting level
-// flag_db[(chain, range, warp)] for the refinement pass, and a thread whose minimum falls below it puts its block of pixels
-// on the `cand` list (pack_group) and leaves it out of the warp's min/max partial.  When the list is full the block keeps
+// each emit warp takes the largest over its 32 rows and their halo up to the thread's quarter of the chain as its
+// reference, and a thread whose minimum falls below the resulting level puts its block of pixels, with that level, on the
+// `cand` list (list_entry) and leaves it out of the warp's min/max partial.  When the list is full the block keeps
 // its float32 values (and stays in the partial).
 struct FlagArgs {
-    float *flag_db;                         // [chains][n_ranges][4] flag level of every (chain, range, emit warp), written here
     float rel_db;                           // how far below the reference magnitude a pixel is flagged (negative)
-    unsigned long long *cand;
+    uint4 *cand;                            // list_entry(pack_group(...), level)
     unsigned int *cand_count;
     unsigned int cand_cap;
 };
@@ -532,7 +531,7 @@ slide_ws_body(const TcParams &P, const SegDesc *__restrict__ segs, int n_segs, i
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t acc_full[G], b_ready[G], s_full[G], s_free[G];
     __shared__ uint32_t tmem_base_s;
-    __shared__ float rmax_s[G][4];          // largest |R| of the chain per worker warp (32 bin rows), recur -> emit
+    __shared__ float rmax_s[G][4][4];       // [warp = 32 bin rows][quarter of the chain]: largest |R| carried up to there, recur -> emit
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool is_worker = warp < 4 * G, is_mma_warp = warp == 4 * G;
     const int g = is_worker ? warp >> 2 : (is_mma_warp ? 0 : warp - 4 * G - 1);    // group served
@@ -913,6 +912,10 @@ slide_ws_body(const TcParams &P, const SegDesc *__restrict__ segs, int n_segs, i
                         mR = fmaxf(mR, fmaxf(fabsf(nr), fabsf(ni)));
                         if (c & 1) { pr = Rr; pi = Ri; }                       // column c+1 even: first of a pair
                         else st4[c >> 1] = make_float4(pr, pi, Rr, Ri);       // columns (c, c+1)
+                        if (i == 7) {                                          // 8 (24) steps from the anchor
+                            const unsigned int m = __reduce_max_sync(0xffffffffu, __float_as_uint(mR));   // |R| >= 0: uint order
+                            if (lane == 0) rmax_s[g][wq][2 * hh] = __uint_as_float(m);
+                        }
                     }
                 } else {
                     // frames t0+31 down to t0 ; column c from column c+1 with D_c ; column 32 is the anchor
@@ -932,12 +935,17 @@ slide_ws_body(const TcParams &P, const SegDesc *__restrict__ segs, int n_segs, i
                         mR = fmaxf(mR, fmaxf(fabsf(nr), fabsf(ni)));
                         if (c & 1) { pr = Rr; pi = Ri; }                       // odd column: second of a pair
                         else st4[c >> 1] = make_float4(Rr, Ri, pr, pi);       // columns (c, c+1)
+                        if (i == 8) {
+                            const unsigned int m = __reduce_max_sync(0xffffffffu, __float_as_uint(mR));
+                            if (lane == 0) rmax_s[g][wq][2 * hh] = __uint_as_float(m);
+                        }
                     }
                 }
+                {                                                              // 16 (32) steps from the anchor
+                    const unsigned int m = __reduce_max_sync(0xffffffffu, __float_as_uint(mR));
+                    if (lane == 0) rmax_s[g][wq][2 * hh + 1] = __uint_as_float(m);
+                }
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) mR = fmaxf(mR, __shfl_xor_sync(0xffffffffu, mR, o));
-            if (lane == 0) rmax_s[g][wq] = mR;
             tc_fence_before();
         }
         WS_MARK(2);
@@ -960,10 +968,12 @@ slide_ws_body(const TcParams &P, const SegDesc *__restrict__ segs, int n_segs, i
                 const int stride = cw.sd.row_stride;
                 char *out = reinterpret_cast<char *>(spec + cw.sd.spec_off + (long long)(range * BINS_PER_RANGE + ra - 1) * stride + t0 + fc);
                 const long long stride_b = (long long)stride * 4;
-                // flag level of this warp's rows (r_lo .. r_lo + 31 and their halo live in recur warps wq and wq + 1):
-                // 20 log10(|R|max) + rel_db; -inf for a silent chain
-                const float th = fmaf(fast_log2(fmaxf(rmax_s[g][wq], rmax_s[g][min(wq + 1, 3)])), 6.0205999132796239f, FA.rel_db);
-                if (lane == 0) FA.flag_db[((size_t)chain * P.n_ranges + range) * 4 + wq] = th;
+                // Flag level of this thread's two frames: 20 log10(|R|max) + rel_db, -inf for a silent chain.  |R|max is the
+                // largest magnitude the warp's rows (r_lo .. r_lo + 31 and their halo: recur warps wq and wq + 1) carried
+                // from the anchor up to the end of the frames' quarter of the chain -- what comes later on the way cannot
+                // have left an error in them.  Column c is c steps from the anchor in a forward chain, 32 - c in a backward one.
+                const int qi = fwd ? fc >> 3 : (31 - fc) >> 3;
+                const float th = fmaf(fast_log2(fmaxf(rmax_s[g][wq][qi], rmax_s[g][min(wq + 1, 3)][qi])), 6.0205999132796239f, FA.rel_db);
                 const bool pair_ok = (cw.sd.spec_off & 1) == 0;          // a later STFT chunk of a long file may start on an odd column
                 // 4 X = 2 R[k] - (R[k-1] + R[k+1]);  10 log10(|X|^2) = 10 log10(|4X|^2) - 10 log10(16)
                 auto row_db = [&](const float4 &nx, float &db0, float &db1) {
@@ -1017,7 +1027,7 @@ slide_ws_body(const TcParams &P, const SegDesc *__restrict__ segs, int n_segs, i
                     // group wait for this one at the barrier below.
                     const unsigned int at = atomicAdd(FA.cand_count, 1u);
                     if (at < FA.cand_cap) {
-                        FA.cand[at] = pack_group(cw.seg_idx, range * BINS_PER_RANGE + ra - 1, rb - ra, nfr > 1 ? 2 : 1, t0 + fc);
+                        FA.cand[at] = list_entry(pack_group(cw.seg_idx, range * BINS_PER_RANGE + ra - 1, rb - ra, nfr > 1 ? 2 : 1, t0 + fc), th);
                         vmin = INFINITY;
                     }
                 }
@@ -1208,12 +1218,11 @@ int nbm::tc_launch_anchors(const TcPlan *pl, const SegDesc *d_segs, int seg_lo, 
 
 int nbm::tc_launch_slides(const TcPlan *pl, const SegDesc *d_segs, int n_segs, int seg_begin, int group_begin, int group_end,
                           const void *d_pcm, float *d_spec, float2 *d_tile_mm, const void *d_anchors,
-                          float *d_flag_db, float rel_db, unsigned long long *d_cand, unsigned int *d_cand_count,
-                          unsigned int cand_cap, cudaStream_t stream) {
+                          float rel_db, uint4 *d_cand, unsigned int *d_cand_count, unsigned int cand_cap, cudaStream_t stream) {
     const TcParams &k = pl->p;
     const int chain_begin = 2 * group_begin, chain_end = 2 * group_end;
     const int grid = std::min(pl->grid_slide, std::max(1, chain_end - chain_begin) * k.n_ranges);
-    FlagArgs fa{d_flag_db, rel_db, d_cand, d_cand_count, cand_cap};
+    FlagArgs fa{rel_db, d_cand, d_cand_count, cand_cap};
     slide_ws_kernel<<<(grid / k.n_ranges) * k.n_ranges, WS_THREADS, pl->smem_slide, stream>>>(
         k, d_segs, n_segs, seg_begin, chain_begin, chain_end, reinterpret_cast<const short *>(d_pcm),
         reinterpret_cast<const float2 *>(d_anchors), d_spec, d_tile_mm, fa);

@@ -23,6 +23,18 @@ __host__ __device__ inline unsigned long long pack_group(int seg, int bin0, int 
            ((unsigned long long)(nfr - 1) << 27) | (unsigned long long)(unsigned int)frame;
 }
 constexpr int GROUP_MAX_FRAME = (1 << 27) - 1;
+// list entry = the packed block + the flag level it was tested against (the refinement pass tests the block's pixels
+// against the same level)
+__host__ __device__ inline uint4 list_entry(unsigned long long key, float level) {
+#ifdef __CUDA_ARCH__
+    return make_uint4((unsigned int)key, (unsigned int)(key >> 32), __float_as_uint(level), 0u);
+#else
+    unsigned int b;
+    memcpy(&b, &level, 4);
+    return make_uint4((unsigned int)key, (unsigned int)(key >> 32), b, 0u);
+#endif
+}
+__host__ __device__ inline unsigned long long entry_key(const uint4 &e) { return ((unsigned long long)e.y << 32) | e.x; }
 
 struct TcPlan;
 
@@ -43,12 +55,11 @@ int tc_launch_anchors(const TcPlan *pl, const SegDesc *d_segs, int seg_lo, int s
                       long long anchor_end, const void *d_pcm, void *d_anchors, cudaStream_t stream);
 // slides: tcgen05 GEMM over hop/2 pairs + recurrence + Hann + dB for every frame, per-(chain, range, slot) min/max
 // for the 64-frame groups [group_begin, group_end), which start in segment seg_begin.  Pixels below their frame's flag
-// level (written to d_flag_db[(chain, range, emit warp)]: rel_db below the largest |R| the rows carried along the chain) are
-// appended to d_cand as blocks (pack_group; at most cand_cap, *d_cand_count counts every
-// attempt) and left out of the min/max partials; see refine_groups_kernel.
+// level (rel_db below the largest |R| the rows carried along the chain so far) are appended to d_cand as blocks together with
+// that level (list_entry; at most cand_cap, *d_cand_count counts every attempt) and left out of the min/max partials;
+// see refine_groups_kernel.
 int tc_launch_slides(const TcPlan *pl, const SegDesc *d_segs, int n_segs, int seg_begin, int group_begin, int group_end,
                      const void *d_pcm, float *d_spec, float2 *d_tile_mm, const void *d_anchors,
-                     float *d_flag_db, float rel_db, unsigned long long *d_cand, unsigned int *d_cand_count,
-                     unsigned int cand_cap, cudaStream_t stream);
+                     float rel_db, uint4 *d_cand, unsigned int *d_cand_count, unsigned int cand_cap, cudaStream_t stream);
 
 }  // namespace nbm
