@@ -501,6 +501,13 @@ __device__ unsigned long long ws_dbg[32];
 //   warp  4G          MMA issuer for every group (one elected thread)
 //   warps 4G+1 .. +G  one fill warp per group: PCM16 of the group's next chain -> shared memory
 constexpr int WS_G = 3;
+#ifndef NBM_WORKER_WAIT_NS
+#define NBM_WORKER_WAIT_NS 32
+#endif
+#ifndef NBM_MMA_WAIT_NS
+#define NBM_MMA_WAIT_NS 256
+#endif
+constexpr int WS_WORKER_WAIT_NS = NBM_WORKER_WAIT_NS, WS_MMA_WAIT_NS = NBM_MMA_WAIT_NS;   // sleep between polls of an mbarrier
 constexpr int WS_THREADS = 32 * (4 * WS_G + 1 + WS_G);
 constexpr int PV = 11;                      // 16-byte PCM vectors per fill lane per round (two rounds per chain)
 
@@ -605,7 +612,7 @@ slide_ws_body(const TcParams &P, const SegDesc *__restrict__ segs, int n_segs, i
 #pragma unroll 1
             for (int gg = 0; gg < G; ++gg) {
                 if (q0 + (it * G + gg) * qstride >= total_chains) break;
-                mbar_wait_long<256>(&b_ready[gg], it & 1);
+                mbar_wait_long<WS_MMA_WAIT_NS>(&b_ready[gg], it & 1);
                 tc_fence_after();
                 WS_MARK(0);
                 if (elect_one()) {
@@ -847,7 +854,7 @@ slide_ws_body(const TcParams &P, const SegDesc *__restrict__ segs, int n_segs, i
     };
     // B operand of the group's chain `it`; hands the operand to the MMA warp and the samples back to the fill warp
     auto build = [&](int it) {
-        mbar_wait_long<32>(&s_full[g], it & 1);
+        mbar_wait_long<WS_WORKER_WAIT_NS>(&s_full[g], it & 1);
         const int n_full = P.npH / 8;                               // units with all 8 pairs live
         for (int jg = wq; jg < n_full; jg += 4) build_unit(jg);
         if (n_full < njg && wq == (it & 3)) build_tail(n_full);
@@ -879,7 +886,7 @@ slide_ws_body(const TcParams &P, const SegDesc *__restrict__ segs, int n_segs, i
         WS_MARK(0);
         // ---- recur: accumulators -> registers -> 32-step recurrence -> stage, 16 columns at a time ----------
         {
-            mbar_wait_long<32>(&acc_full[g], it & 1);
+            mbar_wait_long<WS_WORKER_WAIT_NS>(&acc_full[g], it & 1);
             WS_MARK(1);
             tc_fence_after();
             float4 *st4 = reinterpret_cast<float4 *>(stage + (size_t)gt * ST_LD);
@@ -909,7 +916,9 @@ slide_ws_body(const TcParams &P, const SegDesc *__restrict__ segs, int n_segs, i
                             nr = tr;
                         }
                         Rr = nr; Ri = ni;
+#ifndef NBM_NO_FLAG
                         mR = fmaxf(mR, fmaxf(fabsf(nr), fabsf(ni)));
+#endif
                         if (c & 1) { pr = Rr; pi = Ri; }                       // column c+1 even: first of a pair
                         else st4[c >> 1] = make_float4(pr, pi, Rr, Ri);       // columns (c, c+1)
                         if (i == 7) {                                          // 8 (24) steps from the anchor
@@ -932,7 +941,9 @@ slide_ws_body(const TcParams &P, const SegDesc *__restrict__ segs, int n_segs, i
                             nr = tr;
                         }
                         Rr = nr; Ri = ni;
+#ifndef NBM_NO_FLAG
                         mR = fmaxf(mR, fmaxf(fabsf(nr), fabsf(ni)));
+#endif
                         if (c & 1) { pr = Rr; pi = Ri; }                       // odd column: second of a pair
                         else st4[c >> 1] = make_float4(Rr, Ri, pr, pi);       // columns (c, c+1)
                         if (i == 8) {
@@ -1019,7 +1030,11 @@ slide_ws_body(const TcParams &P, const SegDesc *__restrict__ segs, int n_segs, i
                         pv = cu; cu = nx;
                     }
                 }
+#ifdef NBM_NO_FLAG
+                if (false) {
+#else
                 if (vmin < th) {
+#endif
                     // rare: some pixel of this thread lies below the chain's flag level.  The thread's block of pixels
                     // (rb - ra rows x min(nfr, 2) frames) goes on the list as ONE entry -- refine_groups_kernel finds the
                     // flagged pixels in it, recomputes them in float64 and folds the block's exact minimum into the file's --
