@@ -72,7 +72,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-detect", action="store_true", help="skip the nbm_detect leg (audio-h/s through the real detector)")
-    ap.add_argument("--detect-files", type=int, default=2, help="ten-minute wavs per GPU in the detect leg's night slice")
+    ap.add_argument("--detect-files", type=int, default=4, help="ten-minute wavs per GPU in the detect leg's night slice")
     ap.add_argument("--detect-ref-files", type=int, default=16, help="cfg0 files the unpatched reference flow is timed on (N = 1)")
     ap.add_argument("--no-detect-reference", action="store_true")
     ap.add_argument("--no-stress", action="store_true", help="skip the BASELINE configs[4] leg (n_fft 4410 / hop 44 front-end, NMS at N = 500 / 5 000 / 20 000)")
@@ -355,7 +355,8 @@ def run_b200(a):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
 
     n = int(round(a.seconds * SAMPLE_RATE))
     plan = frontend.get_plan()
@@ -469,6 +470,7 @@ def run_b200(a):
         except Exception as e:                              # the headline must still be printed
             import traceback
             detect = {"error": f"{type(e).__name__}: {e}", "trace": traceback.format_exc()[-1500:]}
+
     elif stress is None:
         n_tiles_total, n_out_bytes, n_in_bytes = int(tile_off[-1]), tiles.numel() * 4, pcm.numel() * 2
 

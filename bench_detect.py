@@ -52,24 +52,47 @@ def _write_files(dirpath, n_files, seconds, seed0, distinct=4):
 def _rm_outputs(dirpath):
     for f in os.listdir(dirpath):
         if f.endswith(".txt"):
-            os.remove(os.path.join(dirpath, f))
+            try:
+                os.remove(os.path.join(dirpath, f))
+            except FileNotFoundError:
+                pass
 
 
 def run(a, rank, world, local, dist):
-    """Returns the `detect` dict on rank 0 (None elsewhere)."""
+    """Returns the `detect` dict on rank 0 (None elsewhere).  Exceptions never escape between two collectives: a rank that
+    fails keeps taking part in them and every rank learns about the failure at the next `all_ok` (a rank that ran away
+    would leave the others in a barrier until the NCCL watchdog fires)."""
+    import traceback
     import torch
     ref_root = find_reference_root()
     if ref_root is None:
         return {"unavailable": "no reference checkout (nbm_model.nets) on this machine"} if rank == 0 else None
-    for p in (ref_root,):
-        if p not in sys.path:
-            sys.path.insert(0, p)
+    if ref_root not in sys.path:
+        sys.path.insert(0, ref_root)
     from birdsoundclassif_b200 import nbm_detect, run_detection as rd, sharding, synth
+    dev = torch.device("cuda", local)
+    errors = []
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def all_ok(ok: bool) -> bool:
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def guarded(fn, *args, **kw):
+        try:
+            return True, fn(*args, **kw)
+        except Exception as e:
+            errors.append(f"rank {rank}: {type(e).__name__}: {e} | {traceback.format_exc()[-600:]}")
+            return False, None
+
+    def fail(what):
+        return {"error": what, "details": errors[:2]} if rank == 0 else None
 
     base = os.environ.get("NBM_BENCH_TMP") or ("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir())
     work = os.path.join(base, f"nbm_bench_{os.environ.get('MASTER_PORT', '0')}_{os.getppid() if world > 1 else os.getpid()}")
@@ -78,70 +101,87 @@ def run(a, rank, world, local, dist):
     cfg0_dir = os.path.join(work, "cfg0")
     night_dir = os.path.join(work, f"night_r{rank}")
     out = {}
-    try:
-        if rank == 0:
-            os.makedirs(work, exist_ok=True)
-            synth.write_standin_checkpoint(ckpt, seed=0, sharpen=400.0)
-            _write_files(cfg0_dir, 16, 30.0, 1000 * 0)
-        barrier()
+    state = {}
+
+    def setup_shared():
+        os.makedirs(work, exist_ok=True)
+        synth.write_standin_checkpoint(ckpt, seed=0, sharpen=400.0)
+        _write_files(cfg0_dir, 16, 30.0, 1000 * 0)
+
+    def setup_rank():
+        from birdsoundclassif_b200.graphed import GraphedDetector
         _write_files(night_dir, a.detect_files, 600.0, 1000 * 2 + 10 * rank, distinct=2)
         model, margs = rd.load_model(ckpt)
         rd.patch_reference()
         rd.accelerate_model(model)
-        dev = torch.device("cuda", local)
+        state.update(model=model, margs=margs, graphed=GraphedDetector(model))
 
-        from birdsoundclassif_b200.graphed import GraphedDetector
-        graphed = GraphedDetector(model)
-
-        def leg(dirpath, r, w, repeats, det=None):
-            best = None
-            for _ in range(repeats):
+    def leg(dirpath, r, w, repeats, det=None):
+        """Best of `repeats` passes over the directory: (wall = max over ranks, per-rank counts) or None if a rank failed."""
+        best = None
+        for _ in range(repeats):
+            barrier()                                      # every rank has finished the previous pass over this directory
+            if w == 1 or rank == 0:                        # a shared directory is cleaned by one rank only
                 _rm_outputs(dirpath)
-                barrier()
-                c = nbm_detect.detect_directory(det or graphed, margs, dirpath, bird_dict, min_score=0.2, bs=4, rank=r,
-                                                world=w, verbose=False)
-                per_rank = sharding.gather_counts(c, device=dev)
-                wall = max(x["t_wall_us"] for x in per_rank) / 1e6
-                if best is None or wall < best[0]:
-                    best = (wall, per_rank)
-            return best
+            barrier()
+            ok, c = guarded(nbm_detect.detect_directory, det or state["graphed"], state["margs"], dirpath, bird_dict,
+                            min_score=0.2, bs=4, rank=r, world=w, verbose=False)
+            if ok and c.get("failed"):
+                errors.append(f"rank {rank}: {c['failed']} files failed in {dirpath}")
+                ok = False
+            per_rank = sharding.gather_counts(c if ok else {}, device=dev)
+            if not all_ok(ok):
+                return None
+            wall = max(x["t_wall_us"] for x in per_rank) / 1e6
+            if best is None or wall < best[0]:
+                best = (wall, per_rank)
+        return best
 
+    def stages(per_rank):
+        return {k: sum(x[k] for x in per_rank) / 1e6 for k in ("t_front_us", "t_model_us", "t_post_us")}
+
+    try:
+        ok = guarded(setup_shared)[0] if rank == 0 else True
+        if not all_ok(ok):
+            return fail("setting up the stand-in checkpoint / cfg0 files failed")
+        if not all_ok(guarded(setup_rank)[0]):
+            return fail("loading the detector failed")
+        model = state.get("model")
         # warm-up: cuDNN heuristics, the allocator's pools, the front-end plan, graph capture
-        leg(cfg0_dir, rank, world, 1)
-        leg(cfg0_dir, rank, world, 1, det=model)
+        if leg(cfg0_dir, rank, world, 1) is None or leg(cfg0_dir, rank, world, 1, det=model) is None:
+            return fail("detect_directory failed on a rank")
         hours = 16 * 30.0 / 3600.0
         for name, det in (("cfg0", None), ("cfg0_eager", model)):
-            wall, per_rank = leg(cfg0_dir, rank, world, 2, det=det)
+            res = leg(cfg0_dir, rank, world, 2, det=det)
+            if res is None:
+                return fail("detect_directory failed on a rank")
+            wall, per_rank = res
             tot = sharding.totals(per_rank)
-            assert tot["files"] == 16
             out[name] = {"workload": "BASELINE configs[0]: 16 x 30 s wavs -> .txt, one directory sharded over the ranks, "
                                      "min_score 0.2, bs 4, reference CNN + stand-in checkpoint, detector forward "
                                      + ("launched eagerly" if det is not None else "replayed from CUDA graphs"),
                          "audio_hours_per_s": hours / wall, "wall_s": wall, "files": tot["files"], "tiles": tot["tiles"],
-                         "detections": tot["detections"], "scaling": "strong",
-                         "stage_s_sum_over_ranks": {k: sum(x[k] for x in per_rank) / 1e6 for k in ("t_front_us", "t_model_us", "t_post_us")}}
-        wall, per_rank = leg(night_dir, 0, 1, 1)
+                         "detections": tot["detections"], "scaling": "strong", "stage_s_sum_over_ranks": stages(per_rank)}
+        res = leg(night_dir, 0, 1, 1)
+        if res is None:
+            return fail("detect_directory failed on a rank (night slice)")
+        wall, per_rank = res
         tot = sharding.totals(per_rank)
         hours = tot["files"] * 600.0 / 3600.0
         out["night"] = {"workload": f"BASELINE configs[2]/[3] shape: {a.detect_files} x 10-min wavs per GPU -> .txt, "
-                                    "min_score 0.2, bs 4, reference CNN + stand-in checkpoint",
+                                    "min_score 0.2, bs 4, reference CNN + stand-in checkpoint, CUDA graphs",
                         "audio_hours_per_s": hours / wall, "wall_s": wall, "files": tot["files"], "tiles": tot["tiles"],
-                        "detections": tot["detections"], "scaling": "weak",
-                        "stage_s_sum_over_ranks": {k: sum(x[k] for x in per_rank) / 1e6 for k in ("t_front_us", "t_model_us", "t_post_us")},
+                        "detections": tot["detections"], "scaling": "weak", "stage_s_sum_over_ranks": stages(per_rank),
                         "per_rank_wall_s": [x["t_wall_us"] / 1e6 for x in per_rank]}
         rd.unpatch_reference()
         if world == 1 and not a.no_detect_reference:
-            out["reference"] = _reference_flow(ckpt, cfg0_dir, bird_dict, a.detect_ref_files)
-        barrier()
-    finally:
-        if world > 1:
-            try:
-                dist.barrier()
-            except Exception:
-                pass
-        shutil.rmtree(night_dir, ignore_errors=True)
+            ok, ref = guarded(_reference_flow, ckpt, cfg0_dir, bird_dict, a.detect_ref_files)
+            out["reference"] = ref if ok else {"error": errors[-1]}
+        barrier()                                          # nobody reads the shared directory any more
         if rank == 0:
             shutil.rmtree(work, ignore_errors=True)
+    finally:
+        shutil.rmtree(night_dir, ignore_errors=True)       # no collective here
     return out if rank == 0 else None
 
 

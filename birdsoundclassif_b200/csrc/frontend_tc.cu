@@ -910,7 +910,12 @@ slide_ws_body(const TcParams &P, const SegDesc *__restrict__ segs, int n_segs, i
                         const float gi = gF.y * gc[i] - gF.x * gs[i];
                         float nr = fmaf(cf.x, Rr, fmaf(-cf.y, Ri, gr));
                         float ni = fmaf(cf.x, Ri, fmaf(cf.y, Rr, gi));
-                        if ((i & (FIX_EVERY - 1)) == FIX_EVERY - 1) {          // R *= rho^FIX_EVERY = 1 + cfx
+#ifndef NBM_NO_CFIX
+                        if ((i & (FIX_EVERY - 1)) == FIX_EVERY - 1)
+#else
+                        if (false)
+#endif
+                        {          // R *= rho^FIX_EVERY = 1 + cfx
                             const float tr = fmaf(cfx.x, nr, fmaf(-cfx.y, ni, nr));
                             ni = fmaf(cfx.x, ni, fmaf(cfx.y, nr, ni));
                             nr = tr;
@@ -935,7 +940,12 @@ slide_ws_body(const TcParams &P, const SegDesc *__restrict__ segs, int n_segs, i
                         const float gi = gB.x * gs[i] + gB.y * gc[i];
                         float nr = fmaf(cf.x, Rr, fmaf(cf.y, Ri, gr));
                         float ni = fmaf(cf.x, Ri, fmaf(-cf.y, Rr, gi));
-                        if ((i & (FIX_EVERY - 1)) == 0) {                      // R *= conj(rho)^FIX_EVERY
+#ifndef NBM_NO_CFIX
+                        if ((i & (FIX_EVERY - 1)) == 0)
+#else
+                        if (false)
+#endif
+                        {                      // R *= conj(rho)^FIX_EVERY
                             const float tr = fmaf(cfx.x, nr, fmaf(cfx.y, ni, nr));
                             ni = fmaf(cfx.x, ni, fmaf(-cfx.y, nr, ni));
                             nr = tr;

@@ -138,9 +138,12 @@ class GraphedDetector:
         return s2
 
     # ------------------------------------------------------------------ call
-    @torch.no_grad()
-    def __call__(self, samples, nms_thresh=0.3, min_score=0.5):
+    def _launch(self, samples, nms_thresh, min_score, while_waiting=None):
+        """Enqueue both graphs for one batch.  `while_waiting` (the host half of the PREVIOUS batch) runs while graph 1 of
+        this one executes.  Returns what `_finish` needs, or the finished dictionaries when running eagerly."""
         if self._eager_only:
+            if while_waiting is not None:
+                while_waiting()
             return self.model(samples, nms_thresh=nms_thresh, min_score=min_score)
         if not samples.is_cuda:
             raise postproc._lib.NbmError("GraphedDetector needs CUDA tensors (no CPU fallback)")
@@ -154,10 +157,12 @@ class GraphedDetector:
                 torch.cuda.synchronize(dev)
                 warnings.warn(f"GraphedDetector: capture failed ({type(e).__name__}: {e}); running the eager accelerated model")
                 self._eager_only = True
-                return self.model(samples, nms_thresh=nms_thresh, min_score=min_score)
+                return self._launch(samples, nms_thresh, min_score, while_waiting)
             self._s1[key] = s1
         s1.x.copy_(samples)
         s1.graph.replay()
+        if while_waiting is not None:
+            while_waiting()
         torch.cuda.current_stream(dev).synchronize()
         M = int(s1.M_host[0])
         if M < 0:                            # layers.py:288-290; the reference then fails inside ROIPooling on the empty RoIs
@@ -167,10 +172,36 @@ class GraphedDetector:
         if s2 is None:
             s2 = s1.stage2[M] = self._capture2(s1, M, nms_thresh, min_score)
         s2.graph.replay()
-        torch.cuda.current_stream(dev).synchronize()
-        a = self.args
         # the records live in the graph's static buffers and are overwritten by the next replay: the dictionaries
-        # (which callers keep until the per-file merge) get their own copies, one clone per tensor per batch
+        # (which callers keep until the per-file merge) get their own copies, enqueued behind the replay
         boxes, scores, classes, _ = (t.clone() for t in s2.rec)
-        return postproc.records_build_dicts(s2.skey_host.numpy().copy(), s2.sb.clone(), s2.ss.clone(), boxes, scores,
-                                            classes, a.num_classes, a.proposal_number)
+        done = torch.cuda.Event()
+        done.record()
+        return (s2, boxes, scores, classes, s2.sb.clone(), s2.ss.clone(), done)
+
+    def _finish(self, pending):
+        if isinstance(pending, list):        # eager: already the dictionaries
+            return pending
+        s2, boxes, scores, classes, sb, ss, done = pending
+        done.synchronize()                   # graph 2 and its copy of the sorted class keys to the host have finished
+        a = self.args
+        return postproc.records_build_dicts(s2.skey_host.numpy().copy(), sb, ss, boxes, scores, classes, a.num_classes,
+                                            a.proposal_number)
+
+    @torch.no_grad()
+    def __call__(self, samples, nms_thresh=0.3, min_score=0.5):
+        return self._finish(self._launch(samples, nms_thresh, min_score))
+
+    @torch.no_grad()
+    def detect_tiles(self, tiles, min_score, bs, nms_thresh=0.3):
+        """`run_detection.detect_tiles` for this detector: the reference's batching (run_detection.py:47-67), with the host
+        half of batch i (building its dictionaries) done while graph 1 of batch i+1 runs."""
+        outputs, pending = [], None
+        for s in range(0, len(tiles), bs):
+            prev, box = pending, []
+            pending = self._launch(tiles[s:s + bs][:, None], nms_thresh, min_score,
+                                   (lambda: box.append(self._finish(prev))) if prev is not None else None)
+            outputs.extend(box)
+        if pending is not None:
+            outputs.append(self._finish(pending))
+        return outputs

@@ -146,6 +146,8 @@ def load_model(mod_p, device=None):
 def detect_tiles(model, tiles: torch.Tensor, min_score: float, bs: int) -> list:
     """Run the detector over device-resident tiles [n, H, W] in the reference's batching
     (run_detection.py:47-67).  Returns the list of per-batch outputs."""
+    if hasattr(model, "detect_tiles"):          # graphed.GraphedDetector overlaps its host work with the next batch
+        return model.detect_tiles(tiles, min_score, bs)
     outputs = []
     n_img = len(tiles)
     for s in range(0, n_img, bs):

@@ -23,7 +23,7 @@ flat = torch.from_numpy(np.concatenate(pcms)).cuda()
 offs = np.concatenate([[0], np.cumsum([len(p) for p in pcms])]).tolist()
 big = flat.repeat(max(1, 256 // n_clips))
 big_offs = (np.arange(big.numel() // len(pcms[0]) + 1) * len(pcms[0])).tolist()
-for rel in ("-62",):
+for rel in ("-200", "-62"):
     os.environ["NBM_REFINE_REL_DB"] = rel
     plan = frontend.FrontendPlan()
     tiles, toff, mm = plan.run_batch(flat, offs)
