@@ -68,7 +68,11 @@ __device__ __forceinline__ float box_area(float4 b) {
 }
 
 // mask[b][i][w] bit j' set  <=>  j = 64 w + j' > i, j < n, IoU(i, j) >= thresh.   Upper triangle only.
-__global__ void __launch_bounds__(64)
+// Block = one 64 x 64 tile of the matrix, 256 threads: four adjacent lanes share a row and take 16 columns each (the
+// serial loop of IEEE divisions per thread is what this kernel's time consists of), their 16-bit pieces are joined by
+// two shuffles.
+constexpr int NMS_MASK_THREADS = 256;
+__global__ void __launch_bounds__(NMS_MASK_THREADS)
 nms_mask_kernel(const float4 *__restrict__ boxes, const int *__restrict__ n_valid, const int *__restrict__ n_cap,
                 int N, float thresh, unsigned long long *__restrict__ mask, int words) {
     const int b = blockIdx.z, rb = blockIdx.y, cb = blockIdx.x;
@@ -82,17 +86,22 @@ nms_mask_kernel(const float4 *__restrict__ boxes, const int *__restrict__ n_vali
     const float4 *bx = boxes + (long long)b * N;
     const int t = threadIdx.x;
     const int j0 = cb * 64;
-    if (j0 + t < n) { cbox[t] = bx[j0 + t]; carea[t] = box_area(cbox[t]); }
+    if (t < 64 && j0 + t < n) { cbox[t] = bx[j0 + t]; carea[t] = box_area(cbox[t]); }
     __syncthreads();
-    const int i = rb * 64 + t;
-    if (i >= n) return;
-    const float4 me = bx[i];
-    const float ma = box_area(me);
+    const int r = t >> 2, q = t & 3;
+    const int i = rb * 64 + r;
     unsigned long long bits = 0;
-    const int lim = min(64, n - j0);
-    for (int jj = (cb == rb ? t + 1 : 0); jj < lim; ++jj)
-        if (iou_ge(cbox[jj], me, carea[jj], ma, thresh)) bits |= 1ull << jj;
-    mask[((long long)b * N + i) * words + cb] = bits;
+    if (i < n) {
+        const float4 me = bx[i];
+        const float ma = box_area(me);
+        const int lim = min(64, n - j0);
+        const int lo = max(16 * q, cb == rb ? r + 1 : 0), hi = min(16 * q + 16, lim);
+        for (int jj = lo; jj < hi; ++jj)
+            if (iou_ge(cbox[jj], me, carea[jj], ma, thresh)) bits |= 1ull << jj;
+    }
+    bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
+    bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
+    if (q == 0 && i < n) mask[((long long)b * N + i) * words + cb] = bits;
 }
 
 // Sequential greedy resolution, one block per image, 64 boxes per step.
@@ -180,33 +189,57 @@ nms_scan_small_kernel(const unsigned long long *__restrict__ mask, const int *__
     n = min(n, N);
     const unsigned long long *m = mask + (long long)b * N * words;
     const int chunks = (n + 63) / 64;
-    for (int idx = tid; idx < n * words; idx += NMS_SMALL_THREADS) {
-        const int row = idx / words, w = idx - row * words;
-        if (w >= (row >> 6) && w < chunks) sm[idx] = m[idx];      // words left of the diagonal were never written
+    {
+        // stage rows [0, n): words left of the diagonal were never written by nms_mask_kernel and are never read here, so
+        // the copy need not tell them apart -- plain 16-byte vectors, four in flight per thread
+        const int n16 = n * words / 2;                   // words is even or the matrix is copied word by word below
+        if ((words & 1) == 0) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(m);
+            uint4 *dst = reinterpret_cast<uint4 *>(sm);
+            int i = tid;
+            for (; i + 3 * NMS_SMALL_THREADS < n16; i += 4 * NMS_SMALL_THREADS) {
+                const uint4 v0 = src[i], v1 = src[i + NMS_SMALL_THREADS], v2 = src[i + 2 * NMS_SMALL_THREADS], v3 = src[i + 3 * NMS_SMALL_THREADS];
+                dst[i] = v0; dst[i + NMS_SMALL_THREADS] = v1; dst[i + 2 * NMS_SMALL_THREADS] = v2; dst[i + 3 * NMS_SMALL_THREADS] = v3;
+            }
+            for (; i < n16; i += NMS_SMALL_THREADS) dst[i] = src[i];
+        } else {
+            for (int i = tid; i < n * words; i += NMS_SMALL_THREADS) sm[i] = m[i];
+        }
     }
     __syncthreads();
     if (tid >= 32) return;
     unsigned long long removed = 0, kept = 0;            // word `lane`
     for (int c = 0; c < chunks; ++c) {
-        const unsigned long long cur = __shfl_sync(0xffffffffu, removed, c);
+        unsigned long long cur = __shfl_sync(0xffffffffu, removed, c);
         const int lim = min(64, n - c * 64);
-        unsigned long long alive = ~cur & (lim == 64 ? ~0ull : ((1ull << lim) - 1ull));
-        unsigned long long kb = 0;
+        if (lim < 64) cur |= ~0ull << lim;               // boxes past the end count as removed
         const unsigned long long *rows = sm + (size_t)c * 64 * words;
-        while (alive) {                                  // warp-uniform
-            const int t = __ffsll((long long)alive) - 1;
-            kb |= 1ull << t;
-            alive &= ~(rows[(size_t)t * words + c] | (1ull << t));
+        // The 64-box diagonal, in input order: box t is kept iff no kept earlier box of the chunk (nor an earlier chunk)
+        // removed it.  Row t only has bits above t, so bit t of `cur` is final once step t - 1 is done and the kept set is
+        // simply ~cur at the end.  The diagonal words are fetched ahead of the dependent chain (broadcast reads, 16 at a
+        // time); a step of the chain is a bit test and a predicated OR.
+        // (rows past `lim` hold stale shared memory, but their own bit in `cur` is set, so they are never OR-ed in)
+        const unsigned long long *dg = rows + c;
+#pragma unroll
+        for (int t0 = 0; t0 < 64; t0 += 16) {            // fully unrolled: bit positions are immediates
+            unsigned long long d[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) d[u] = dg[(size_t)(t0 + u) * words];
+#pragma unroll
+            for (int u = 0; u < 16; ++u)
+                if (!((cur >> (t0 + u)) & 1ull)) cur |= d[u];
         }
+        const unsigned long long kb = ~cur;
         if (lane == c) kept = kb;
-        const bool mine = lane > c && lane < chunks;
-        unsigned long long acc = 0, bits = kb;
-        while (bits) {
-            const int t = __ffsll((long long)bits) - 1;
-            bits &= bits - 1;
-            if (mine) acc |= rows[(size_t)t * words + lane];
+        // OR the kept rows into the later words.  Lane l contributes rows l and l + 32 of the chunk; the OR over the lanes is
+        // a warp reduction (redux.sync on the two halves), so a word costs a dozen instructions, not a walk over 64 rows.
+        const bool k0 = (kb >> lane) & 1ull, k1 = (kb >> (lane + 32)) & 1ull;
+        for (int w = c + 1; w < chunks; ++w) {
+            unsigned long long v = (k0 ? rows[(size_t)lane * words + w] : 0ull) | (k1 ? rows[(size_t)(lane + 32) * words + w] : 0ull);
+            const unsigned int lo = __reduce_or_sync(0xffffffffu, (unsigned int)v);
+            const unsigned int hi = __reduce_or_sync(0xffffffffu, (unsigned int)(v >> 32));
+            if (lane == w) removed |= ((unsigned long long)hi << 32) | lo;
         }
-        removed |= acc;
     }
     // compaction: ascending kept indices; exclusive prefix of the per-word counts over the lanes
     const int pc = lane < chunks ? __popcll(kept) : 0;
@@ -234,9 +267,9 @@ static int launch_nms(const float *d_boxes, const int *d_n, const int *d_cap, in
     const size_t need = (size_t)B * N * words * sizeof(unsigned long long);
     if (ws_bytes < need) { set_error("nms workspace too small: %zu < %zu", ws_bytes, need); return NBM_ERR_WORKSPACE; }
     dim3 grid(words, words, B);
-    nms_mask_kernel<<<grid, 64, 0, s>>>(reinterpret_cast<const float4 *>(d_boxes), d_n, d_cap, N, thresh,
+    nms_mask_kernel<<<grid, NMS_MASK_THREADS, 0, s>>>(reinterpret_cast<const float4 *>(d_boxes), d_n, d_cap, N, thresh,
                                         reinterpret_cast<unsigned long long *>(ws), words);
-    const size_t smem_small = (size_t)N * words * sizeof(unsigned long long);
+    const size_t smem_small = (size_t)words * 64 * words * sizeof(unsigned long long);   // whole 64-row chunks: the resolve reads full chunks
     if (words <= 32 && smem_small <= NMS_SMALL_SMEM_MAX) {
         static bool attr_set = false;                   // per function, not per call
         if (!attr_set) {
