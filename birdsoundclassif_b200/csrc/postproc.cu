@@ -294,25 +294,151 @@ static int launch_nms(const float *d_boxes, const int *d_n, const int *d_cap, in
 
 // --------------------------------------------------------------------------- proposals -------
 // scores/deltas from the RPN's [B, C, H, W] layout (layers.py:264-267), decode + clamp + min-size.
-__global__ void rpn_decode_kernel(const float *__restrict__ cls, const float *__restrict__ reg,
-                                  const float4 *__restrict__ anchors, int B, int A, int H, int W, float clip_w,
-                                  float clip_h, float min_size, float4 *__restrict__ boxes, float *__restrict__ keys,
-                                  int *__restrict__ idx, int *__restrict__ n_valid) {
-    const int N = A * H * W;
-    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= (long long)B * N) return;
-    const int b = (int)(g / N), n = (int)(g % N);
-    const int a = n % A, cell = n / A;           // cell = y*W + x
-    const long long hw = (long long)H * W;
-    const float *rb = reg + ((long long)b * 4 * A + 4 * a) * hw + cell;
-    const float4 d = make_float4(rb[0], rb[hw], rb[2 * hw], rb[3 * hw]);
-    const float score = cls[((long long)b * 2 * A + 2 * a + 1) * hw + cell];
-    const float4 bx = clamp_box(decode_one(d, anchors[n]), clip_w, clip_h);
-    boxes[g] = bx;
-    const bool ok = big_enough(bx, min_size);
-    keys[g] = ok ? score : -INFINITY;            // invalid boxes sort last (scores are probabilities)
-    idx[g] = n;
-    if (ok) atomicAdd(n_valid + b, 1);
+// Block = RPN_CELLS consecutive cells of one image.  The RPN tensors are [B, C, H, W]: the 5 A planes a box needs (4 A
+// deltas, A foreground scores) are read as rows of RPN_CELLS floats (coalesced) into shared memory; then the boxes are
+// decoded and written in the reference's order n = cell * A + a (consecutive threads, consecutive n).
+constexpr int RPN_CELLS = 64, RPN_THREADS = 256;
+__global__ void __launch_bounds__(RPN_THREADS)
+rpn_decode_kernel(const float *__restrict__ cls, const float *__restrict__ reg,
+                  const float4 *__restrict__ anchors, int B, int A, int H, int W, float clip_w,
+                  float clip_h, float min_size, float4 *__restrict__ boxes, float *__restrict__ keys,
+                  int *__restrict__ idx, int *__restrict__ n_valid) {
+    extern __shared__ float planes[];                    // [5 A][RPN_CELLS]: reg planes 0 .. 4A-1, then the fg score planes
+    const int hw = H * W, N = A * hw;
+    const int b = blockIdx.y, c0 = blockIdx.x * RPN_CELLS, nc = min(RPN_CELLS, hw - c0);
+    const float *rb = reg + (long long)b * 4 * A * hw + c0;
+    const float *cb = cls + (long long)b * 2 * A * hw + c0;
+    for (int i = threadIdx.x; i < 5 * A * RPN_CELLS; i += RPN_THREADS) {
+        const int pl = i / RPN_CELLS, c = i - pl * RPN_CELLS;
+        if (c < nc) planes[i] = pl < 4 * A ? rb[(long long)pl * hw + c] : cb[(long long)(2 * (pl - 4 * A) + 1) * hw + c];
+    }
+    __syncthreads();
+    int ok_cnt = 0;
+    for (int l = threadIdx.x; l < nc * A; l += RPN_THREADS) {
+        const int c = l / A, a = l - c * A;
+        const int n = c0 * A + l;
+        const float4 d = make_float4(planes[(4 * a + 0) * RPN_CELLS + c], planes[(4 * a + 1) * RPN_CELLS + c],
+                                     planes[(4 * a + 2) * RPN_CELLS + c], planes[(4 * a + 3) * RPN_CELLS + c]);
+        const float score = planes[(4 * A + a) * RPN_CELLS + c];
+        const float4 bx = clamp_box(decode_one(d, anchors[n]), clip_w, clip_h);
+        const long long g = (long long)b * N + n;
+        boxes[g] = bx;
+        const bool ok = big_enough(bx, min_size);
+        keys[g] = ok ? score : -INFINITY;        // invalid boxes sort last (scores are probabilities)
+        if (idx) idx[g] = n;
+        ok_cnt += ok ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ok_cnt += __shfl_xor_sync(0xffffffffu, ok_cnt, o);
+    if ((threadIdx.x & 31) == 0 && ok_cnt) atomicAdd(n_valid + b, ok_cnt);
+}
+
+// Top-K of one image's scores in stable descending order (ties: lower index first) -- what the reference gets from
+// argsort(descending) + filter + [:pre_nms_topN] (layers.py:292-297) -- without sorting all A*H*W candidates: one block
+// per image keeps the keys in shared memory, finds the K-th largest by an 8-bit radix select (4 histogram passes), collects
+// the keys above it plus the lowest-index ties, and bitonic-sorts those K <= TOPK_MAX.
+constexpr int TOPK_THREADS = 1024, TOPK_MAX = 1024;
+__global__ void __launch_bounds__(TOPK_THREADS)
+proposal_topk_kernel(const float4 *__restrict__ boxes, const float *__restrict__ keys, const int *__restrict__ pre, int N, int cap,
+                     float4 *__restrict__ out_boxes, float *__restrict__ out_scores) {
+    extern __shared__ unsigned int skey[];               // [N] order-preserving keys
+    __shared__ unsigned long long cand[TOPK_MAX];        // (~key) << 32 | index: ascending = score descending, index ascending
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned int s_prefix, s_want;
+    __shared__ unsigned int wsum_gt[32], wsum_eq[32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = min(min(*pre, cap), TOPK_MAX);
+    if (K <= 0) return;
+    const float *kb = keys + (long long)b * N;
+    for (int i = tid; i < N; i += TOPK_THREADS) skey[i] = float_to_ordered(kb[i]);
+    if (tid == 0) { s_prefix = 0; s_want = (unsigned int)K; }
+    __syncthreads();
+    // ---- radix select: after the pass for `shift`, s_prefix holds the top bits of the K-th largest key --------------
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        for (int i = tid; i < 256; i += TOPK_THREADS) hist[i] = 0;
+        __syncthreads();
+        const unsigned int prefix = s_prefix, himask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+        for (int i = tid; i < N; i += TOPK_THREADS) {
+            const unsigned int k = skey[i];
+            if ((k & himask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // lane l owns bins 255 - 8 l .. 248 - 8 l (descending); the K-th largest lies in the first bin where the running
+            // count from the top reaches `want`
+            unsigned int h[8], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { h[j] = hist[255 - 8 * lane - j]; sum += h[j]; }
+            unsigned int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            const unsigned int want = s_want;
+            unsigned int above = incl - sum;             // keys in higher bins
+            const bool here = above < want && incl >= want;
+            if (here) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (above + h[j] >= want) {
+                        s_prefix = prefix | ((unsigned int)(255 - 8 * lane - j) << shift);
+                        s_want = want - above;           // rank inside that bin
+                        break;
+                    }
+                    above += h[j];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const unsigned int T = s_prefix, need_eq = s_want;   // K-th largest key; that many of the keys == T belong to the top K
+    // ---- collect: thread t scans a contiguous index range, so ranks inside the tie class follow the index order ----------
+    const int chunk = (N + TOPK_THREADS - 1) / TOPK_THREADS;
+    const int i0 = min(tid * chunk, N), i1 = min(i0 + chunk, N);
+    unsigned int n_gt = 0, n_eq = 0;
+    for (int i = i0; i < i1; ++i) { const unsigned int k = skey[i]; n_gt += k > T; n_eq += k == T; }
+    unsigned int inc_gt = n_gt, inc_eq = n_eq;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int a = __shfl_up_sync(0xffffffffu, inc_gt, o), e = __shfl_up_sync(0xffffffffu, inc_eq, o);
+        if (lane >= o) { inc_gt += a; inc_eq += e; }
+    }
+    if (lane == 31) { wsum_gt[warp] = inc_gt; wsum_eq[warp] = inc_eq; }
+    __syncthreads();
+    if (warp == 0) {
+        unsigned int a = wsum_gt[lane], e = wsum_eq[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int va = __shfl_up_sync(0xffffffffu, a, o), ve = __shfl_up_sync(0xffffffffu, e, o);
+            if (lane >= o) { a += va; e += ve; }
+        }
+        wsum_gt[lane] = a; wsum_eq[lane] = e;            // inclusive over warps
+    }
+    __syncthreads();
+    const unsigned int total_gt = wsum_gt[31];           // == K - need_eq
+    unsigned int at_gt = inc_gt - n_gt + (warp ? wsum_gt[warp - 1] : 0u);
+    unsigned int at_eq = inc_eq - n_eq + (warp ? wsum_eq[warp - 1] : 0u);
+    for (int i = i0; i < i1; ++i) {
+        const unsigned int k = skey[i];
+        if (k > T) cand[at_gt++] = ((unsigned long long)(~k) << 32) | (unsigned int)i;
+        else if (k == T) { if (at_eq < need_eq) cand[total_gt + at_eq] = ((unsigned long long)(~k) << 32) | (unsigned int)i; ++at_eq; }
+    }
+    for (int i = K + tid; i < TOPK_MAX; i += TOPK_THREADS) cand[i] = ~0ull;
+    __syncthreads();
+    // ---- bitonic sort of the TOPK_MAX slots, ascending --------------------------------------------------------------------
+    for (int k2 = 2; k2 <= TOPK_MAX; k2 <<= 1)
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            const int ixj = tid ^ j;
+            if (ixj > tid) {
+                const unsigned long long x = cand[tid], y = cand[ixj];
+                const bool up = (tid & k2) == 0;
+                if ((x > y) == up) { cand[tid] = y; cand[ixj] = x; }
+            }
+            __syncthreads();
+        }
+    if (tid < K) {
+        const int i = (int)(unsigned int)cand[tid];
+        out_boxes[(long long)b * cap + tid] = boxes[(long long)b * N + i];
+        out_scores[(long long)b * cap + tid] = kb[i];
+    }
 }
 
 __global__ void fill_offsets_kernel(int *seg, int n, int stride) {
@@ -618,18 +744,34 @@ int proposals_impl(const nbm_proposal_params *p, const float *d_cls, const float
     auto *keep_idx = reinterpret_cast<int *>(ws + w.keep_idx);
     auto *keep_cnt = reinterpret_cast<int *>(ws + w.keep_cnt);
 
-    fill_offsets_kernel<<<(B + 1 + 127) / 128, 128, 0, s>>>(seg, B + 1, N);
     NBM_CUDA(cudaMemsetAsync(n_valid, 0, sizeof(int) * B, s));
     const long long total = (long long)B * N;
-    rpn_decode_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
-        d_cls, d_reg, reinterpret_cast<const float4 *>(d_anchors), B, p->A, p->H, p->W, p->img_width, p->img_height,
-        p->min_size, boxes, keys, idx, n_valid);
+    const size_t topk_smem = (size_t)N * sizeof(unsigned int);
+    const bool use_topk = cap <= TOPK_MAX && topk_smem <= 160 * 1024;      // else: full segmented sort (cub)
+    {
+        const size_t smem = (size_t)5 * p->A * RPN_CELLS * sizeof(float);
+        NBM_REQUIRE(smem <= 48 * 1024, "too many anchors per cell for rpn_decode_kernel");
+        dim3 gd((p->H * p->W + RPN_CELLS - 1) / RPN_CELLS, B);
+        rpn_decode_kernel<<<gd, RPN_THREADS, smem, s>>>(
+            d_cls, d_reg, reinterpret_cast<const float4 *>(d_anchors), B, p->A, p->H, p->W, p->img_width, p->img_height,
+            p->min_size, boxes, keys, use_topk ? nullptr : idx, n_valid);
+    }
     proposal_pre_kernel<<<1, 1, 0, s>>>(n_valid, B, p->pre_nms_topN, p->rcnn_batch_size, pre, status);
-    size_t cub_bytes = w.cub_bytes;
-    NBM_CUDA(cub::DeviceSegmentedRadixSort::SortPairsDescending(ws + w.cub, cub_bytes, keys, keys_sorted, idx,
-                                                                idx_sorted, (int)total, B, seg, seg + 1, 0, 32, s));
-    dim3 gg((cap + 127) / 128, B);
-    gather_sorted_kernel<<<gg, 128, 0, s>>>(boxes, keys_sorted, idx_sorted, pre, N, cap, top_boxes, top_scores);
+    if (use_topk) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            NBM_CUDA(cudaFuncSetAttribute(proposal_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            attr_set = true;
+        }
+        proposal_topk_kernel<<<B, TOPK_THREADS, topk_smem, s>>>(boxes, keys, pre, N, cap, top_boxes, top_scores);
+    } else {
+        fill_offsets_kernel<<<(B + 1 + 127) / 128, 128, 0, s>>>(seg, B + 1, N);
+        size_t cub_bytes = w.cub_bytes;
+        NBM_CUDA(cub::DeviceSegmentedRadixSort::SortPairsDescending(ws + w.cub, cub_bytes, keys, keys_sorted, idx,
+                                                                    idx_sorted, (int)total, B, seg, seg + 1, 0, 32, s));
+        dim3 gg((cap + 127) / 128, B);
+        gather_sorted_kernel<<<gg, 128, 0, s>>>(boxes, keys_sorted, idx_sorted, pre, N, cap, top_boxes, top_scores);
+    }
     int rc = launch_nms(reinterpret_cast<const float *>(top_boxes), nullptr, pre, B, cap, p->nms_thresh, keep_idx,
                         keep_cnt, ws + w.nms, nbm_nms_workspace_bytes(B, cap), s);
     if (rc != NBM_OK) return rc;
