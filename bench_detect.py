@@ -162,7 +162,10 @@ def run(a, rank, world, local, dist):
                                      + ("launched eagerly" if det is not None else "replayed from CUDA graphs"),
                          "audio_hours_per_s": hours / wall, "wall_s": wall, "files": tot["files"], "tiles": tot["tiles"],
                          "detections": tot["detections"], "scaling": "strong", "stage_s_sum_over_ranks": stages(per_rank)}
-        res = leg(night_dir, 0, 1, 1)
+        # two passes, the faster one counts: the first also records a CUDA graph of the second stage for every RoI count M it
+        # meets (tens of milliseconds each, once per process) -- in the regime this slice stands for (thousands of files per
+        # GPU) those are long amortised
+        res = leg(night_dir, 0, 1, 2)
         if res is None:
             return fail("detect_directory failed on a rank (night slice)")
         wall, per_rank = res
