@@ -176,6 +176,7 @@ def synth_batch_gpu(clips: int, n: int, seed: int, device):
 
 # ------------------------------------------------------------------ CPU reference ------------
 _CPU_PCM: list = []         # filled in the parent BEFORE the timed pool forks: the workers inherit it, nothing is pickled
+_CPU_KIND = "port"
 
 
 def _cpu_gen(args):
@@ -183,55 +184,82 @@ def _cpu_gen(args):
     return synth.synth_pcm(*args)
 
 
+def _cpu_setup(tmpdir):
+    """The reference's own File_Processor (unmodified, from /root/reference or the oracle/_ref copy, its librosa import
+    served by oracle/ref_shims.py) when a checkout is here -- `kind: "reference"`; else the numpy port (bit-identical to it,
+    tests/test_oracle_frontend.py) -- `kind: "port"`.  Returns (kind, list of per-clip inputs)."""
+    from oracle import ref_shims
+    if not ref_shims.have_reference():
+        return "port", _CPU_PCM
+    from birdsoundclassif_b200 import synth
+    return "reference", [synth.write_wav(os.path.join(tmpdir, f"clip_{i:04d}.wav"), p) for i, p in enumerate(_CPU_PCM)]
+
+
 def _cpu_one(i):
-    from oracle import frontend_oracle as fo
     t = time.perf_counter()
-    r = fo.process(_CPU_PCM[i])
+    if _CPU_KIND == "reference":
+        from oracle import ref_shims
+        fp = ref_shims.ref("nbm_model.nbm_datasets.prepare_dataset").File_Processor(_CPU_PCM[i])
+        tiles, _ = fp.process_file()
+    else:
+        from oracle import frontend_oracle as fo
+        tiles = fo.process(_CPU_PCM[i]).tiles
     # the reference hands float32 batches to the model (run_detection.py:53)
-    _ = [np.asarray(x, dtype=np.float32) for x in r.tiles]
+    _ = [np.asarray(x, dtype=np.float32) for x in tiles]
     return time.perf_counter() - t
 
 
 def cpu_reference(seconds: float, n_clips: int, procs: int):
-    """Oracle port of the reference front-end (File_Processor.process_file restated in numpy, float64 pocketfft like
-    librosa) on `procs` host processes, one clip per task.  Only the transform is inside the timed wall: the synthetic
-    clips are generated beforehand and reach the workers by fork inheritance."""
+    """The reference front-end (File_Processor.process_file: float64 pocketfft STFT like librosa) on `procs` host
+    processes, one clip per task.  Only the transform (for the reference class: wav decode + transform, as upstream) is inside
+    the timed wall: the synthetic clips are generated beforehand and reach the workers by fork inheritance.
+    Returns (audio-hours/s, wall, mean seconds per clip, kind)."""
     import multiprocessing as mp
+    import shutil
+    import tempfile
     ctx = mp.get_context("fork")
-    global _CPU_PCM
+    global _CPU_PCM, _CPU_KIND
     with ctx.Pool(procs) as pool:
         _CPU_PCM = pool.map(_cpu_gen, [(seconds, 7000 + i) for i in range(n_clips)])
-    with ctx.Pool(procs) as pool:
-        pool.map(_cpu_one, range(min(procs, n_clips)))      # warm-up: imports, page-in
-        t = time.perf_counter()
-        per = pool.map(_cpu_one, range(n_clips), chunksize=1)
-        wall = time.perf_counter() - t
-    _CPU_PCM = []
-    return n_clips * seconds / 3600.0 / wall, wall, float(np.mean(per))
+    tmpdir = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        _CPU_KIND, _CPU_PCM = _cpu_setup(tmpdir)
+        with ctx.Pool(procs) as pool:
+            pool.map(_cpu_one, range(min(procs, n_clips)))      # warm-up: imports, page-in
+            t = time.perf_counter()
+            per = pool.map(_cpu_one, range(n_clips), chunksize=1)
+            wall = time.perf_counter() - t
+    finally:
+        shutil.rmtree(tmpdir, ignore_errors=True)
+        _CPU_PCM = []
+    return n_clips * seconds / 3600.0 / wall, wall, float(np.mean(per)), _CPU_KIND
 
 
 def run_reference(a):
-    """`--impl reference`: the reference's own CPU implementation of the path (its Python needs
-    librosa, absent here, so this is the oracle port) with all host cores."""
+    """`--impl reference`: the reference's own CPU implementation of the path with all host cores: its unmodified
+    File_Processor from the checkout (/root/reference or oracle/_ref) with librosa's calls served by the numpy
+    restatement, or the oracle port when no checkout is here."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     clips = a.cpu_clips or 4 * cores
     per_step = []
+    kind = "port"
     for i in range(a.warmup + a.steps):
-        v, wall, _ = cpu_reference(a.seconds, clips, cores)
+        v, wall, _, kind = cpu_reference(a.seconds, clips, cores)
         if i >= a.warmup:
             per_step.append((v, wall))
     v = float(np.mean([p[0] for p in per_step]))
     ms = float(np.mean([p[1] for p in per_step])) * 1e3
-    sample = f"{clips} synthetic {a.seconds:g} s clips per step, one process per core"
+    sample = f"{clips} synthetic {a.seconds:g} s clips per step, one process per core" + \
+        ("; the reference's File_Processor, unmodified (librosa.stft served by its numpy restatement)" if kind == "reference" else "")
     line = {"impl": "reference", "metric": "audio-hours/sec", "value": v, "unit": "audio-hours/s", "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"front-end alone, {a.clips} x {a.seconds:g} s clips (BASELINE configs[1]); "
                                    f"CPU arm timed on a bounded sample: {sample}"},
-            "cpu_baseline": {"value": v, "unit": "audio-hours/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "audio-hours/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "audio-hours/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -547,8 +575,8 @@ def run_b200(a):
     if not a.no_cpu_baseline and world == 1:          # rank 0 at N = 1 only: at N > 1 the ranks share the host cores
         cores = os.cpu_count() or 1
         clips = a.cpu_clips or 8 * cores
-        v, wall, per = cpu_reference(a.seconds, clips, cores)
-        line["cpu_baseline"] = {"value": v, "unit": "audio-hours/s", "cores": cores, "kind": "port",
+        v, wall, per, kind = cpu_reference(a.seconds, clips, cores)
+        line["cpu_baseline"] = {"value": v, "unit": "audio-hours/s", "cores": cores, "kind": kind,
                                 "sample": f"{clips} of the {a.seconds:g} s clips, one process per core, "
                                           f"{wall:.1f} s wall, {per:.2f} s per clip per core"}
     print(json.dumps(line))
