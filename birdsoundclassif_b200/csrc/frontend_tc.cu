@@ -214,7 +214,7 @@ __device__ __forceinline__ void umma_f16_ts_c(uint32_t tmem_d, uint32_t tmem_a, 
 // Epilogue: thread = bin, add the two accumulators, rotate to the frame-start phase reference, store float2.
 constexpr int AN = 128;                 // anchors per task (MMA N)
 constexpr int AKB = 32;                 // pairs per k-block (2 k-steps)
-constexpr int A_BUILD_WARPS = 8;
+constexpr int A_BUILD_WARPS = 4 * (AKB / 8);     // thread = (anchor, 8 pairs): AN / 32 warps per 8-pair slice of the k-block
 constexpr int A_THREADS = 32 * (A_BUILD_WARPS + 1);
 constexpr int A_MAT_BYTES = 128 * AKB * 2;          // one [128 x AKB] fp16 matrix (A: bins, B: anchors)
 constexpr int A_STAGE_BYTES = 8 * A_MAT_BYTES;      // 4 twiddle + 4 sample matrices
@@ -290,8 +290,9 @@ anchor_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, int seg_lo, int s
             __syncwarp();
         }
     } else {
-        // ================================ builders: thread = (anchor a, 16 pairs of the k-block) ===========
-        const int a = tid & (AN - 1), half16 = tid >> 7;            // half16 in {0, 1}
+        // ================================ builders: thread = (anchor a, 8 pairs of the k-block) ============
+        // (16 warps: with 8, each building 16 pairs, a k-block took twice as long to build as to multiply)
+        const int a = tid & (AN - 1), part = tid >> 7;              // part in 0 .. AKB/8 - 1
         const long long ag = ag0 + a;
         const bool live = ag < anchor_end;
         int lo_s = seg_lo, hi_s = seg_hi - 1;                       // this anchor's segment: last s with group0[s] + s <= ag
@@ -302,27 +303,27 @@ anchor_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, int seg_lo, int s
         const SegDesc sd = segs[lo_s];
         const int ai = (int)(ag - ((long long)sd.group0 + lo_s));  // frame 64 ai of the segment
         const long long c = (long long)ai * GF * P.hop;            // segment-relative index of the frame centre
-        // c and the pair offsets are multiples of 8 samples, so every 16-sample run of this thread starts `sh`
+        // c and the pair offsets are multiples of 8 samples, so every 8-sample run of this thread starts `sh`
         // samples after a 16-byte boundary (sh = 0 when the file starts on one)
         const bool vec_ok = ((reinterpret_cast<uintptr_t>(pcm) & 15) == 0) && (GF * P.hop) % 8 == 0;
         const int sh = (int)(sd.pcm_start & 7);
-        uint32_t hi_w[8], lo_w[8];          // 16 samples above / below the centre for this thread's pairs, offset binary
-        int4 raw_h[3], raw_l[3];            // their raw 16-byte loads, in flight while the previous k-block is built
+        uint32_t hi_w[4], lo_w[4];          // 8 samples above / below the centre for this thread's pairs, offset binary
+        int4 raw_h[2], raw_l[2];            // their raw 16-byte loads, in flight while the previous k-block is built
         bool fast_h = false, fast_l = false;
-        // issue the loads of samples s0 .. s0+15 (segment-relative); nothing here waits for them
-        auto issue16 = [&](long long s0, int4 (&raw)[3], bool &fastflag, uint32_t (&w)[8]) {
+        // issue the loads of samples s0 .. s0+7 (segment-relative); nothing here waits for them
+        auto issue8 = [&](long long s0, int4 (&raw)[2], bool &fastflag, uint32_t (&w)[4]) {
             const long long a0 = s0 - sh;                           // start of the aligned window (segment-relative)
-            fastflag = live && vec_ok && a0 >= 0 && a0 + (sh ? 24 : 16) <= sd.n_samples;
+            fastflag = live && vec_ok && a0 >= 0 && a0 + (sh ? 16 : 8) <= sd.n_samples;
             if (fastflag) {
                 const int4 *p4 = reinterpret_cast<const int4 *>(pcm + sd.pcm_start + a0);
-                raw[0] = __ldg(p4); raw[1] = __ldg(p4 + 1);
-                if (sh) raw[2] = __ldg(p4 + 2);
+                raw[0] = __ldg(p4);
+                if (sh) raw[1] = __ldg(p4 + 1);
             } else if (!live) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) w[i] = 0x80008000u;
+                for (int i = 0; i < 4; ++i) w[i] = 0x80008000u;
             } else {                                                // first / last anchors of a segment: centre padding
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < 4; ++i) {
                     uint32_t u[2];
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
@@ -334,25 +335,31 @@ anchor_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, int seg_lo, int s
             }
         };
         // first use of the loaded vectors: re-align (file not on a 16-byte boundary) and flip to offset binary
-        auto finish16 = [&](const int4 (&raw)[3], bool fastflag, uint32_t (&w)[8]) {
+        auto finish8 = [&](const int4 (&raw)[2], bool fastflag, uint32_t (&w)[4]) {
             if (!fastflag) return;
             if (sh == 0) {
                 w[0] = (uint32_t)raw[0].x; w[1] = (uint32_t)raw[0].y; w[2] = (uint32_t)raw[0].z; w[3] = (uint32_t)raw[0].w;
-                w[4] = (uint32_t)raw[1].x; w[5] = (uint32_t)raw[1].y; w[6] = (uint32_t)raw[1].z; w[7] = (uint32_t)raw[1].w;
             } else {
-                const uint32_t W[12] = {(uint32_t)raw[0].x, (uint32_t)raw[0].y, (uint32_t)raw[0].z, (uint32_t)raw[0].w,
-                                        (uint32_t)raw[1].x, (uint32_t)raw[1].y, (uint32_t)raw[1].z, (uint32_t)raw[1].w,
-                                        (uint32_t)raw[2].x, (uint32_t)raw[2].y, (uint32_t)raw[2].z, (uint32_t)raw[2].w};
-                realign_words<12, 8>(W, sh, w);
+                const uint32_t W[8] = {(uint32_t)raw[0].x, (uint32_t)raw[0].y, (uint32_t)raw[0].z, (uint32_t)raw[0].w,
+                                       (uint32_t)raw[1].x, (uint32_t)raw[1].y, (uint32_t)raw[1].z, (uint32_t)raw[1].w};
+                realign_words<8, 4>(W, sh, w);
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) w[i] ^= 0x80008000u;
+            for (int i = 0; i < 4; ++i) w[i] ^= 0x80008000u;
         };
         auto prefetch = [&](int kb) {
-            const int j0 = kb * AKB + 16 * half16;                  // first pair of this thread in the k-block
-            issue16(c + j0, raw_h, fast_h, hi_w);                   // pair j <-> sample c + j
-            issue16(c - j0 - 16, raw_l, fast_l, lo_w);              //            and sample c - 1 - j
+            const int j0 = kb * AKB + 8 * part;                     // first pair of this thread in the k-block
+            issue8(c + j0, raw_h, fast_h, hi_w);                    // pair j <-> sample c + j
+            issue8(c - j0 - 8, raw_l, fast_l, lo_w);                //            and sample c - 1 - j
         };
+        if (live) {
+            // the anchor's whole window (N samples around c) into L2 now: the register loads below are issued one k-block
+            // (~0.6 us) ahead, less than an HBM round trip; this thread takes every (AKB/8)-th 128-byte line
+            const long long w0 = max(c - P.N / 2, 0ll), w1 = min(c + P.N / 2, sd.n_samples);
+            const char *pb = reinterpret_cast<const char *>(pcm + sd.pcm_start + w0);
+            for (long long o = (long long)part * 128; o < (w1 - w0) * 2; o += (AKB / 8) * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + o));
+        }
         prefetch(0);
         for (int kb = 0; kb < n_kb; ++kb) {
             const int s = kb % A_STAGES, ph = (kb / A_STAGES) & 1;
@@ -363,27 +370,26 @@ anchor_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, int seg_lo, int s
                 bulk_g2s(sA, reinterpret_cast<const unsigned char *>(P.a_anchor) + ((size_t)range * n_kb + kb) * 4 * A_MAT_BYTES,
                          4 * A_MAT_BYTES, &full_a[s]);
             }
-            const int j0 = kb * AKB + 16 * half16;
-            finish16(raw_h, fast_h, hi_w);
-            finish16(raw_l, fast_l, lo_w);
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {                           // two units of 8 pairs
+            const int j0 = kb * AKB + 8 * part;
+            finish8(raw_h, fast_h, hi_w);
+            finish8(raw_l, fast_l, lo_w);
+            {
                 uint32_t ph4[4], pl4[4], mh4[4], ml4[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    // pairs j0 + 8u + 2q, +1: above the centre words hi_w[4u + q]; below: mirrored, word 7 - 4u - q reversed
-                    const uint32_t wa = hi_w[4 * u + q], wc = lo_w[7 - 4 * u - q];
+                    // pairs j0 + 2q, +1: above the centre word hi_w[q]; below: mirrored, word 3 - q reversed
+                    const uint32_t wa = hi_w[q], wc = lo_w[3 - q];
                     const __half2 ah = u32_as_h2(__byte_perm(wa, 0x64646464u, 0x4341)), al = u32_as_h2(__byte_perm(wa, 0x44444444u, 0x4240));
                     const __half2 ch = u32_as_h2(__byte_perm(wc, 0x64646464u, 0x4143)), cl = u32_as_h2(__byte_perm(wc, 0x44444444u, 0x4042));
                     // sums: (1024 + ua) + (1024 + uc) - 2304 = xa_h + xc_h (signed high bytes);  (4 + la) + (4 + lc) - 8 = la + lc
                     uint32_t v0 = h2_as_u32(__hadd2(ah, __hsub2(ch, __float2half2_rn(2304.0f))));
                     uint32_t v1 = h2_as_u32(__hadd2(al, __hsub2(cl, __float2half2_rn(8.0f))));
                     uint32_t v2 = h2_as_u32(__hsub2(ah, ch)), v3 = h2_as_u32(__hsub2(al, cl));
-                    const int j = j0 + 8 * u + 2 * q;
+                    const int j = j0 + 2 * q;
                     const uint32_t keep = (j < P.npN ? 0x0000ffffu : 0u) | (j + 1 < P.npN ? 0xffff0000u : 0u);
                     ph4[q] = v0 & keep; pl4[q] = v1 & keep; mh4[q] = v2 & keep; ml4[q] = v3 & keep;
                 }
-                const size_t o = umma_off(a, 16 * half16 + 8 * u, AKB);
+                const size_t o = umma_off(a, 8 * part, AKB);
                 *reinterpret_cast<uint4 *>(sBm + 0 * A_MAT_BYTES + o) = make_uint4(ph4[0], ph4[1], ph4[2], ph4[3]);
                 *reinterpret_cast<uint4 *>(sBm + 1 * A_MAT_BYTES + o) = make_uint4(pl4[0], pl4[1], pl4[2], pl4[3]);
                 *reinterpret_cast<uint4 *>(sBm + 2 * A_MAT_BYTES + o) = make_uint4(mh4[0], mh4[1], mh4[2], mh4[3]);
@@ -401,18 +407,17 @@ anchor_tc_kernel(TcParams P, const SegDesc *__restrict__ segs, int seg_lo, int s
             const int row = warp * 32 + lane;
             const uint32_t tl = tmem_base + ((uint32_t)(warp * 32) << 16);
             const float2 rot = P.rot[range * 128 + row];          // e^{-i theta (N-1)/2} x scale
-            for (int c0 = 0; c0 < AN; c0 += 32) {
-                float ac[32], as[32], v[32];
-                tmem_ld32(tl + c0, ac);
-                tmem_ld32(tl + AN + c0, as);
-                tmem_ld32(tl + 2 * AN + c0, v);
+            for (int c0 = 0; c0 < AN; c0 += 16) {          // 16 columns at a time: 17 warps are allocated registers as 20
+                float ac[16], as[16], v[16], u[16];
+                tmem_ld16_nowait(tl + c0, ac);
+                tmem_ld16_nowait(tl + AN + c0, as);
+                tmem_ld16_nowait(tl + 2 * AN + c0, v);
+                tmem_ld16_nowait(tl + 3 * AN + c0, u);
+                tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) ac[i] += v[i];
-                tmem_ld32(tl + 3 * AN + c0, v);
+                for (int i = 0; i < 16; ++i) { ac[i] += v[i]; as[i] += u[i]; }
 #pragma unroll
-                for (int i = 0; i < 32; ++i) as[i] += v[i];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
+                for (int i = 0; i < 16; ++i) {
                     const long long an = ag0 + c0 + i;
                     if (an < anchor_end) {
                         // R = (c0 - i s0)(A - iB)
