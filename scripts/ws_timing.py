@@ -4,7 +4,7 @@
 """
 import ctypes, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-DBG = os.path.join(ROOT, "scripts", "_dbg", "libnbm_b200_dbg.so")
+DBG = os.environ.get("NBM_WS_DBG", os.path.join(ROOT, "scripts", "_dbg", "libnbm_b200_dbg.so"))
 if sys.argv[1] == "build":
     sys.path.insert(0, ROOT)
     from birdsoundclassif_b200 import build as B
