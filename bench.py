@@ -61,6 +61,24 @@ def ncu_summary(kernel="slide_ws_kernel"):
     return out
 
 
+def issue_rate_probe():
+    """Issue rates (warp-instructions per clock and scheduler) of the instruction forms the slide kernel is made of, measured
+    on a B200 by scripts/ffma_rt_probe.cu and tracked as profiles/r02_ffma_rt_probe.txt (the 16-warps-per-SM rows)."""
+    import re
+    path = os.path.join(ROOT, "profiles", "r02_ffma_rt_probe.txt")
+    if not os.path.exists(path):
+        return None
+    out = {"file": os.path.relpath(path, ROOT)}
+    keys = {"FFMA x = x*a_i + b_i (3 distinct regs)": "ffma_3_registers", "FFMA x = x*imm + b_i": "ffma_immediate",
+            "FFMA x = x*m + m (2 distinct regs)": "ffma_2_registers", "PRMT": "prmt",
+            "FFMA(3 regs) + FMNMX interleaved": "ffma_3_registers+fmnmx", "FFMA(3 regs) + PRMT interleaved": "ffma_3_registers+prmt"}
+    for line in open(path):
+        m = re.match(r"(.*?)\s+warps/SM\s+16:\s+([0-9.]+) warp-instr", line)
+        if m and m.group(1).strip() in keys:
+            out[keys[m.group(1).strip()]] = float(m.group(2))
+    return out
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -542,8 +560,11 @@ def run_b200(a):
                      "frac": achieved / peak, "traffic": traffic,
                      "traffic_source": ("ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per frame, parsed from "
                                         + ncu["file"] + ", scaled to this launch") if ncu else None,
-                     "binding_unit": "instruction issue (the kernel is not HBM-bound: see issue_frac; `bound` names the "
-                                     "roofline BASELINE.json asks to be measured against)",
+                     "binding_unit": "instruction issue, through register-operand bandwidth (the kernel is not HBM-bound: see "
+                                     "issue_frac and issue_rate_probe -- a 3-register FFMA issues at 0.61 per clock and "
+                                     "scheduler, so this mix cannot reach 1.0; `bound` names the roofline BASELINE.json asks "
+                                     "to be measured against)",
+                     "issue_rate_probe": issue_rate_probe(),
                      "issue_frac": ncu["issue_frac"] if ncu else None, "tensor_frac": ncu["tensor_frac"] if ncu else None,
                      "frontend_frac": frames * BYTES_PER_FRAME / (t_ms / a.steps / 1e3) / 1e9 / peak,
                      "peak_source": peak_src,
