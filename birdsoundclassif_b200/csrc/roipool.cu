@@ -10,7 +10,10 @@
 //   pe     = AdaptiveAvgPool2d(cat(freq_pe[s y1 : s y2] broadcast over time,
 //                                  time_pe[: s (x2 - x1)] broadcast over frequency))                 :483-489
 // The averages replicate ATen's order (window summed row by row in float, then "/ kh / kw"), so results
-// are bit-identical to the reference on the same feature maps.
+// are bit-identical to the reference on the same feature maps.  That order makes every output one serial chain of
+// float additions (up to ~7 500 for a positional-encoding window), so the kernel is latency-bound and wants many
+// resident warps: blockIdx.y splits a RoI's C x pool_h x pool_w outputs over several blocks.
+#include <algorithm>
 #include "common.cuh"
 
 namespace nbm {
@@ -59,7 +62,8 @@ roi_pool_kernel(RoiPoolParams P, const float4 *__restrict__ rois, const float *_
     // ---- feature crop (python slice semantics: the end is clamped to the map) -----------------------
     const int ch = min(y2 + 1, H) - y1, cw = min(x2 + 1, W) - x1;
     const float *fm = P.feat[level] + ((size_t)b * P.C) * H * W;
-    for (int idx = threadIdx.x; idx < n_out; idx += blockDim.x) {
+    const int idx0 = blockIdx.y * blockDim.x + threadIdx.x, idx_step = gridDim.y * blockDim.x;
+    for (int idx = idx0; idx < n_out; idx += idx_step) {
         const int c = idx / per_c, oh = (idx % per_c) / P.pool_w, ow = idx % P.pool_w;
         float v = 0.f;
         if (ch > 0 && cw > 0) {
@@ -76,7 +80,7 @@ roi_pool_kernel(RoiPoolParams P, const float4 *__restrict__ rois, const float *_
     // ---- positional encoding: [C/2 frequency channels | C/2 time channels] over an (Hf, Wt) pixel box ---
     const int C2 = P.C / 2;
     const int Hf = max(0, min(s * y2, P.img_h) - min(s * y1, P.img_h)), Wt = max(0, min(s * (x2 - x1), P.img_w));
-    for (int idx = threadIdx.x; idx < n_out; idx += blockDim.x) {
+    for (int idx = idx0; idx < n_out; idx += idx_step) {
         const int c = idx / per_c, oh = (idx % per_c) / P.pool_w, ow = idx % P.pool_w;
         float v = 0.f;
         if (Hf > 0 && Wt > 0) {
@@ -116,7 +120,12 @@ extern "C" int nbm_roi_pool(const float *d_rois, int32_t B, int32_t R, const flo
         P.H[l] = l < n_layers ? heights[l] : 0; P.W[l] = l < n_layers ? widths[l] : 0; P.feat[l] = l < n_layers ? d_feat[l] : nullptr;
         if (l < n_layers) NBM_REQUIRE(P.H[l] >= 1 && P.W[l] >= 1 && P.feat[l], "bad feature map %d", l);
     }
-    roi_pool_kernel<<<B * R, 256, 0, (cudaStream_t)stream>>>(P, reinterpret_cast<const float4 *>(d_rois), d_pe_freq, d_pe_time,
+    // enough blocks for up to 8 per SM (the grid of B x R = 200 RoIs alone leaves most SMs with one block of serial chains)
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int n_out = C * pool_h * pool_w;
+    const int chunks = std::max(1, std::min((8 * sms) / (B * R), (n_out + 255) / 256));      // one wave of 256-thread blocks
+    roi_pool_kernel<<<dim3((unsigned)(B * R), (unsigned)chunks), 256, 0, (cudaStream_t)stream>>>(P, reinterpret_cast<const float4 *>(d_rois), d_pe_freq, d_pe_time,
                                                              d_pool_out, d_pe_out, d_level_out);
     NBM_CUDA(cudaGetLastError());
     return NBM_OK;
