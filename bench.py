@@ -578,7 +578,9 @@ def run_b200(a):
                                      "note": "second pass: dB band read once (4 B x 375 x frames) + tiles written once"},
                      "note": "the kernel is instruction-issue / shared-memory bound, not HBM bound (DESIGN.md 3)"},
         "clocks": clocks,
-        "gpu_launches": 7 * a.steps,      # upload, frame levels, anchors, slides, float64 refinement, min/max, tiles per step
+        # our kernels per step on the tensor-core path: upload, anchors, slides, float64 refinement, min/max, tiles
+        # (the CUDA-core path has one transform kernel instead of anchors + slides)
+        "gpu_launches": (6 if plan.impl == "tcgen05" else 5) * a.steps,
         "parity": parity,
     }
     if e2e:
