@@ -37,6 +37,17 @@ class _Stage1:
     __slots__ = ("graph", "x", "rois", "M_dev", "M_host", "fpn_out", "stage2")
 
 
+class _Lane:
+    """One replay lane: its own stream, capture stream (cuBLAS keeps one workspace per stream, and the graphs bake its
+    address in), graph memory pool and ProposalLayer workspace, so that two lanes can be in flight at the same time."""
+    __slots__ = ("stream", "cap_stream", "pool", "s1", "ws")
+
+    def __init__(self):
+        self.stream = self.cap_stream = self.pool = None
+        self.s1: dict = {}              # (shape, nms_thresh, min_score) -> _Stage1
+        self.ws: list = [None]          # ProposalLayer workspace holder (filled at the first launch)
+
+
 class _Stage2:
     __slots__ = ("graph", "rec", "skey", "sb", "ss", "skey_host")
 
@@ -45,7 +56,7 @@ class GraphedDetector:
     """``GraphedDetector(model)(batch[:, None], min_score=...)`` == ``model(batch[:, None], min_score=...)`` for a
     reference NbmModel that went through ``accelerate_model`` (inference only)."""
 
-    def __init__(self, model, warmup: int = 2):
+    def __init__(self, model, warmup: int = 2, lanes: int = 2):
         head = getattr(model, "head", None)
         if head is None or not isinstance(head.prop_layer, postproc.ProposalLayer) or \
                 not isinstance(head.fast_rcnn.roi_pooling, postproc.ROIPooling):
@@ -53,17 +64,16 @@ class GraphedDetector:
         self.model = model
         self.args = model.args
         self.warmup = warmup
-        self._s1: dict = {}          # (B, H, W, nms_thresh, min_score) -> _Stage1
+        self._lanes = [_Lane() for _ in range(max(1, int(lanes)))]
         self._pos: dict = {}
         self._eager_only = False
-        self._pool = None
         self.training = False
 
     def eval(self):
         return self
 
     # ------------------------------------------------------------------ the network, as nbm_model.py runs it
-    def _first_stage(self, samples, M_dev):
+    def _first_stage(self, samples, M_dev, ws):
         m, a = self.model, self.args
         xs = m.backbone[0](samples)                                     # backbone.py:139-142 (Joiner -> Backbone)
         features = [x for _, x in xs.items()]
@@ -76,7 +86,7 @@ class GraphedDetector:
         else:
             fpn_out = m.fpn(m.attn(features))
         cls_scores, bbox_reg = m.head.rpn(fpn_out)                      # head.py:34
-        rois, _ = m.head.prop_layer.forward_async(cls_scores, bbox_reg, M_dev)
+        rois, _ = m.head.prop_layer.forward_async(cls_scores, bbox_reg, M_dev, ws)
         return rois, fpn_out
 
     def _pos_for(self, f):
@@ -96,8 +106,10 @@ class GraphedDetector:
         return rec, postproc.records_sort_device(*rec, a.num_classes)
 
     # ------------------------------------------------------------------ capture
-    def _capture1(self, samples):
+    def _capture1(self, samples, lane):
         dev = samples.device
+        if lane.stream is None:
+            lane.stream, lane.cap_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
         s1 = _Stage1()
         s1.x = torch.empty_like(samples)
         s1.x.copy_(samples)
@@ -108,18 +120,18 @@ class GraphedDetector:
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side), torch.no_grad():
             for _ in range(self.warmup):            # cuDNN plans, workspaces, anchors, position tables: all outside the graph
-                self._first_stage(s1.x, s1.M_dev)
+                self._first_stage(s1.x, s1.M_dev, lane.ws)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         s1.graph = torch.cuda.CUDAGraph()
-        with torch.no_grad(), torch.cuda.graph(s1.graph, pool=self._pool):
-            s1.rois, s1.fpn_out = self._first_stage(s1.x, s1.M_dev)
+        with torch.no_grad(), torch.cuda.graph(s1.graph, pool=lane.pool, stream=lane.cap_stream):
+            s1.rois, s1.fpn_out = self._first_stage(s1.x, s1.M_dev, lane.ws)
             s1.M_host.copy_(s1.M_dev, non_blocking=True)
-        if self._pool is None:
-            self._pool = s1.graph.pool()
+        if lane.pool is None:
+            lane.pool = s1.graph.pool()
         return s1
 
-    def _capture2(self, s1, M, nms_thresh, min_score):
+    def _capture2(self, s1, M, nms_thresh, min_score, lane):
         dev = s1.x.device
         s2 = _Stage2()
         rois = s1.rois[:, :M]
@@ -132,52 +144,68 @@ class GraphedDetector:
         torch.cuda.synchronize(dev)
         s2.skey_host = torch.empty((rois.shape[0], M), dtype=torch.int32).pin_memory()    # not inside the capture
         s2.graph = torch.cuda.CUDAGraph()
-        with torch.no_grad(), torch.cuda.graph(s2.graph, pool=self._pool):
+        with torch.no_grad(), torch.cuda.graph(s2.graph, pool=lane.pool, stream=lane.cap_stream):
             s2.rec, (s2.skey, s2.sb, s2.ss) = self._second_stage(s1.fpn_out, rois, nms_thresh, min_score)
             s2.skey_host.copy_(s2.skey, non_blocking=True)
         return s2
 
     # ------------------------------------------------------------------ call
-    def _launch(self, samples, nms_thresh, min_score, while_waiting=None):
-        """Enqueue both graphs for one batch.  `while_waiting` (the host half of the PREVIOUS batch) runs while graph 1 of
-        this one executes.  Returns what `_finish` needs, or the finished dictionaries when running eagerly."""
+    # A batch goes through three steps; with two lanes, batch i's first graph runs on the GPU beside batch i-1's (the
+    # late layers of the network are too small at bs 4 to fill 148 SMs, and the host's read of M no longer leaves
+    # the GPU idle):
+    #   _stage1   copy the tiles into the lane's static input, replay graph 1 on the lane's stream
+    #   _stage2   wait for that lane, read M, replay graph 2 (captured at its first use for this M), copy the records
+    #             out of the graph's static buffers on the caller's stream
+    #   _finish   wait for the copies, build the reference's dictionaries on the host
+    def _stage1(self, samples, nms_thresh, min_score, lane):
         if self._eager_only:
-            if while_waiting is not None:
-                while_waiting()
             return self.model(samples, nms_thresh=nms_thresh, min_score=min_score)
         if not samples.is_cuda:
             raise postproc._lib.NbmError("GraphedDetector needs CUDA tensors (no CPU fallback)")
         key = (tuple(samples.shape), float(nms_thresh), float(min_score))
-        s1 = self._s1.get(key)
+        s1 = lane.s1.get(key)
         dev = samples.device
         if s1 is None:
             try:
-                s1 = self._capture1(samples.contiguous())
+                s1 = self._capture1(samples.contiguous(), lane)
             except Exception as e:          # a configuration whose forward still talks to the host: stay eager, say so
                 torch.cuda.synchronize(dev)
                 warnings.warn(f"GraphedDetector: capture failed ({type(e).__name__}: {e}); running the eager accelerated model")
                 self._eager_only = True
-                return self._launch(samples, nms_thresh, min_score, while_waiting)
-            self._s1[key] = s1
-        s1.x.copy_(samples)
-        s1.graph.replay()
-        if while_waiting is not None:
-            while_waiting()
-        torch.cuda.current_stream(dev).synchronize()
+                return self._stage1(samples, nms_thresh, min_score, lane)
+            lane.s1[key] = s1
+        # behind the caller's stream: the tiles come from there, and so do the copies that read this lane's static
+        # outputs for its previous batch
+        lane.stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(lane.stream):
+            s1.x.copy_(samples)
+            s1.graph.replay()
+        samples.record_stream(lane.stream)
+        return (s1, lane, nms_thresh, min_score)
+
+    def _stage2(self, started):
+        if isinstance(started, list):        # eager: already the dictionaries
+            return started
+        s1, lane, nms_thresh, min_score = started
+        lane.stream.synchronize()
         M = int(s1.M_host[0])
         if M < 0:                            # layers.py:288-290; the reference then fails inside ROIPooling on the empty RoIs
             print("Not enough possible RoIs, RPN failed")
             raise RuntimeError("RPN produced fewer than rcnn_batch_size candidate boxes (the reference crashes here too)")
         s2 = s1.stage2.get(M)
         if s2 is None:
-            s2 = s1.stage2[M] = self._capture2(s1, M, nms_thresh, min_score)
-        s2.graph.replay()
-        # the records live in the graph's static buffers and are overwritten by the next replay: the dictionaries
-        # (which callers keep until the per-file merge) get their own copies, enqueued behind the replay
+            s2 = s1.stage2[M] = self._capture2(s1, M, nms_thresh, min_score, lane)
+        with torch.cuda.stream(lane.stream):
+            s2.graph.replay()
+        main = torch.cuda.current_stream(s1.x.device)
+        main.wait_stream(lane.stream)
+        # the records live in the graph's static buffers and are overwritten by the lane's next replay: the dictionaries
+        # (which callers keep until the per-file merge) get their own copies, made on the caller's stream
         boxes, scores, classes, _ = (t.clone() for t in s2.rec)
+        sb, ss = s2.sb.clone(), s2.ss.clone()
         done = torch.cuda.Event()
-        done.record()
-        return (s2, boxes, scores, classes, s2.sb.clone(), s2.ss.clone(), done)
+        done.record(main)
+        return (s2, boxes, scores, classes, sb, ss, done)
 
     def _finish(self, pending):
         if isinstance(pending, list):        # eager: already the dictionaries
@@ -190,18 +218,30 @@ class GraphedDetector:
 
     @torch.no_grad()
     def __call__(self, samples, nms_thresh=0.3, min_score=0.5):
-        return self._finish(self._launch(samples, nms_thresh, min_score))
+        return self._finish(self._stage2(self._stage1(samples, nms_thresh, min_score, self._lanes[0])))
 
     @torch.no_grad()
     def detect_tiles(self, tiles, min_score, bs, nms_thresh=0.3):
-        """`run_detection.detect_tiles` for this detector: the reference's batching (run_detection.py:47-67), with the host
-        half of batch i (building its dictionaries) done while graph 1 of batch i+1 runs."""
-        outputs, pending = [], None
-        for s in range(0, len(tiles), bs):
-            prev, box = pending, []
-            pending = self._launch(tiles[s:s + bs][:, None], nms_thresh, min_score,
-                                   (lambda: box.append(self._finish(prev))) if prev is not None else None)
-            outputs.extend(box)
+        """`run_detection.detect_tiles` for this detector: the reference's batching (run_detection.py:47-67) as a
+        software pipeline -- graph 1 of batch i is enqueued before the host turns to batch i-1's RoI count and second
+        graph, and batch i-2's dictionaries are built while both run."""
+        outputs, started, pending = [], None, None
+        n_lanes = len(self._lanes)
+        for i, s in enumerate(range(0, len(tiles), bs)):
+            nxt = self._stage1(tiles[s:s + bs][:, None], nms_thresh, min_score, self._lanes[i % n_lanes])
+            if n_lanes == 1:                 # one lane: its static buffers are free only after the previous batch's second graph
+                if pending is not None:
+                    outputs.append(self._finish(pending))
+                pending = self._stage2(nxt)
+                continue
+            second = self._stage2(started) if started is not None else None
+            if pending is not None:
+                outputs.append(self._finish(pending))
+            started, pending = nxt, second
+        if n_lanes > 1:
+            if pending is not None:
+                outputs.append(self._finish(pending))
+            pending = self._stage2(started) if started is not None else None
         if pending is not None:
             outputs.append(self._finish(pending))
         return outputs

@@ -146,7 +146,7 @@ class ProposalLayer(nn.Module):
         self.config = config
         self._ws = None
 
-    def _launch(self, labels_pred, bbox_reg, M_dev=None):
+    def _launch(self, labels_pred, bbox_reg, M_dev=None, ws_holder=None):
         cfg = self.config
         if self.training:
             raise NotImplementedError("training-time proposals are out of scope (inference hot path only)")
@@ -162,8 +162,14 @@ class ProposalLayer(nn.Module):
                                 pre_nms_topN=int(cfg.pre_nms_topN_eval), post_nms_topN=int(cfg.post_nms_topN_eval),
                                 rcnn_batch_size=int(cfg.rcnn_batch_size))
         ws_bytes = _lib.lib().nbm_proposals_workspace_bytes(C.byref(p), B)
-        if self._ws is None or self._ws.numel() < ws_bytes or self._ws.device != dev:
-            self._ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        if ws_holder is not None:           # a caller that keeps several calls in flight brings a workspace per lane
+            if ws_holder[0] is None or ws_holder[0].numel() < ws_bytes or ws_holder[0].device != dev:
+                ws_holder[0] = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+            ws = ws_holder[0]
+        else:
+            if self._ws is None or self._ws.numel() < ws_bytes or self._ws.device != dev:
+                self._ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+            ws = self._ws
         rois = torch.empty((B, p.post_nms_topN, 4), dtype=torch.float32, device=dev)
         scores = torch.empty((B, p.post_nms_topN), dtype=torch.float32, device=dev)
         cls, reg = _f32c(labels_pred), _f32c(bbox_reg)
@@ -171,12 +177,12 @@ class ProposalLayer(nn.Module):
             if M_dev is None:
                 M = C.c_int32(0)
                 _lib.check(_lib.lib().nbm_proposals(C.byref(p), cls.data_ptr(), reg.data_ptr(), anchors.data_ptr(), B,
-                                                    rois.data_ptr(), scores.data_ptr(), C.byref(M), self._ws.data_ptr(),
-                                                    self._ws.numel(), _stream()), "nbm_proposals")
+                                                    rois.data_ptr(), scores.data_ptr(), C.byref(M), ws.data_ptr(),
+                                                    ws.numel(), _stream()), "nbm_proposals")
                 return rois, scores, M.value
             _lib.check(_lib.lib().nbm_proposals_async(C.byref(p), cls.data_ptr(), reg.data_ptr(), anchors.data_ptr(), B,
                                                       rois.data_ptr(), scores.data_ptr(), M_dev.data_ptr(),
-                                                      self._ws.data_ptr(), self._ws.numel(), _stream()),
+                                                      ws.data_ptr(), ws.numel(), _stream()),
                        "nbm_proposals_async")
         return rois, scores, M_dev
 
@@ -188,11 +194,12 @@ class ProposalLayer(nn.Module):
             return torch.tensor([]).to(dev), torch.tensor([]).to(dev)
         return rois[:, :M], scores[:, :M]
 
-    def forward_async(self, labels_pred: torch.Tensor, bbox_reg: torch.Tensor, M_dev: torch.Tensor):
+    def forward_async(self, labels_pred: torch.Tensor, bbox_reg: torch.Tensor, M_dev: torch.Tensor, ws_holder=None):
         """No host read, no synchronisation (CUDA-graph capturable): returns the FULL ``rois [B, post_nms_topN, 4]``
         and ``scores [B, post_nms_topN]``; the number of valid rows (or -1 for the reference's "RPN failed" branch)
-        is written to ``M_dev`` (int32 [1] on the device)."""
-        rois, scores, _ = self._launch(labels_pred, bbox_reg, M_dev)
+        is written to ``M_dev`` (int32 [1] on the device).  ``ws_holder`` (a one-element list) keeps the call's
+        workspace apart from the module's own, for callers with several calls in flight on different streams."""
+        rois, scores, _ = self._launch(labels_pred, bbox_reg, M_dev, ws_holder)
         return rois, scores
 
 

@@ -62,9 +62,15 @@ model, _ = rd.load_model(d)
 rd.patch_reference()
 rd.accelerate_model(model)
 timed(model, "patched + accelerated, eager")
-g = GraphedDetector(model)
-timed(g, "patched + accelerated, CUDA graphs")
-print("eager fallback:", g._eager_only)
+g1 = GraphedDetector(model, lanes=1)
+timed(g1, "CUDA graphs, one lane")
+g = GraphedDetector(model, lanes=2)
+timed(g, "CUDA graphs, two lanes")
+print("eager fallback:", g1._eager_only, g._eager_only)
+if os.environ.get("PROBE_LANES3"):
+    timed(GraphedDetector(model, lanes=3), "CUDA graphs, three lanes")
+if not os.environ.get("PROBE_CUDNN_BENCH"):
+    sys.exit(0)
 torch.backends.cudnn.benchmark = True
 model2, _ = rd.load_model(d)
 rd.accelerate_model(model2)

@@ -168,6 +168,33 @@ def test_patched_reference_model_identical_to_unpatched(gpu_case):
 
 
 @pytest.mark.gpu
+def test_two_replay_lanes_identical_to_one(gpu_case):
+    """GraphedDetector keeps two batches in flight on two streams (graphed.py `_Lane`): over a clip of a dozen batches,
+    repeated, its dictionaries equal the one-lane replay and the eager accelerated model bit for bit -- lanes share the
+    weights and nothing else (own graphs, memory pool, cuBLAS workspace, ProposalLayer workspace)."""
+    clips, args, ref, _, standin_dir = gpu_case
+    from birdsoundclassif_b200 import frontend
+    from birdsoundclassif_b200.graphed import GraphedDetector
+    model, _ = rd.load_model(standin_dir)
+    try:
+        rd.patch_reference()
+        rd.accelerate_model(model)
+        pcm = synth.synth_pcm(115.0, 43, calls_per_s=6.0)               # 47 tiles: 12 batches of 4, the last one partial
+        tiles, _ = frontend.File_Processor("c.wav").process_pcm(torch.from_numpy(pcm).cuda())
+        eager = rd.detect_tiles(model, tiles, 0.02, 4)
+        one, two = GraphedDetector(model, lanes=1), GraphedDetector(model, lanes=2)
+        n = _assert_same_tiles(eager, rd.detect_tiles(one, tiles, 0.02, 4), score_tol=0)
+        for _ in range(3):
+            assert _assert_same_tiles(eager, rd.detect_tiles(two, tiles, 0.02, 4), score_tol=0) == n
+        assert n > 100 and not one._eager_only and not two._eager_only
+        # a single call and a two-batch run go through the same lanes
+        _assert_same_tiles(eager[:1], [two(tiles[:4][:, None], min_score=0.02)], score_tol=0)
+        _assert_same_tiles(eager[:2], rd.detect_tiles(two, tiles[:8], 0.02, 4), score_tol=0)
+    finally:
+        rd.unpatch_reference()
+
+
+@pytest.mark.gpu
 def test_patched_symbols_only_without_module_swaps(gpu_case):
     """patch_reference() alone (the reference's own ProposalLayer / ROIPooling / FastRCNN.forward Python code calling
     the library-backed nms and bbox_reg_to_coord, layers.py:272,301,719,742,761) gives the same dictionaries."""
