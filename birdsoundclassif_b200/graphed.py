@@ -223,25 +223,58 @@ class GraphedDetector:
     @torch.no_grad()
     def detect_tiles(self, tiles, min_score, bs, nms_thresh=0.3):
         """`run_detection.detect_tiles` for this detector: the reference's batching (run_detection.py:47-67) as a
-        software pipeline -- graph 1 of batch i is enqueued before the host turns to batch i-1's RoI count and second
-        graph, and batch i-2's dictionaries are built while both run."""
-        outputs, started, pending = [], None, None
-        n_lanes = len(self._lanes)
-        for i, s in enumerate(range(0, len(tiles), bs)):
-            nxt = self._stage1(tiles[s:s + bs][:, None], nms_thresh, min_score, self._lanes[i % n_lanes])
-            if n_lanes == 1:                 # one lane: its static buffers are free only after the previous batch's second graph
-                if pending is not None:
-                    outputs.append(self._finish(pending))
-                pending = self._stage2(nxt)
-                continue
-            second = self._stage2(started) if started is not None else None
-            if pending is not None:
-                outputs.append(self._finish(pending))
-            started, pending = nxt, second
-        if n_lanes > 1:
-            if pending is not None:
-                outputs.append(self._finish(pending))
-            pending = self._stage2(started) if started is not None else None
-        if pending is not None:
-            outputs.append(self._finish(pending))
-        return outputs
+        software pipeline (see `detect_stream`)."""
+        for outputs in self.detect_stream([tiles], min_score, bs, nms_thresh):
+            return outputs
+
+    @torch.no_grad()             # on a generator function: grad mode is switched per resume, not left off across a yield
+    def detect_stream(self, files, min_score, bs, nms_thresh=0.3):
+        """``files``: an iterable of device tile tensors [n, H, W], one per recording.  Yields, in order, each recording's
+        list of per-batch outputs -- exactly ``detect_tiles`` of that recording (batches never span recordings:
+        run_detection.py:47-67 batches one file) -- while the lanes already run the first batches of the NEXT
+        recordings: graph 1 of batch i is enqueued before the host turns to batch i-(L-1)'s RoI count and second graph,
+        and the dictionaries of the batches before that are built while both run."""
+        lanes = self._lanes
+        L = len(lanes)
+        started, pending, open_files = [], [], []        # FIFOs; open_files: [n batches, all enqueued, outputs so far]
+        i = 0
+
+        def finish_oldest():
+            f = next(e for e in open_files if e[0] > len(e[2]))
+            f[2].append(self._finish(pending.pop(0)))
+
+        def ready():
+            while open_files and open_files[0][0] == len(open_files[0][2]) and open_files[0][1]:
+                yield open_files.pop(0)[2]
+
+        for tiles in files:
+            n_batches = (len(tiles) + bs - 1) // bs
+            entry = [n_batches, False, []]
+            open_files.append(entry)
+            for s in range(0, len(tiles), bs):
+                started.append(self._stage1(tiles[s:s + bs][:, None], nms_thresh, min_score, lanes[i % L]))
+                i += 1
+                if L == 1:
+                    # one lane: the second graph's host copy of the class keys is free only after the previous batch's
+                    # dictionaries were built from it
+                    while pending:
+                        finish_oldest()
+                    pending.append(self._stage2(started.pop(0)))
+                else:
+                    if len(started) == L:
+                        pending.append(self._stage2(started.pop(0)))
+                    while len(pending) > 1:
+                        finish_oldest()
+                if s + bs >= len(tiles):
+                    entry[1] = True
+                yield from ready()
+            if n_batches == 0:
+                entry[1] = True
+                yield from ready()
+        while started:
+            pending.append(self._stage2(started.pop(0)))
+            while len(pending) > 1:
+                finish_oldest()
+        while pending:
+            finish_oldest()
+        yield from ready()

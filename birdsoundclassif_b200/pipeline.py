@@ -37,7 +37,7 @@ import torch
 
 from . import audio_io, postproc
 from .frontend import LONG_FILE_SAMPLES, STFT_CHUNK, FrontendPlan, derive_constants
-from .run_detection import detect_tiles, run_detection
+from .run_detection import detect_stream, run_detection
 
 
 # ------------------------------------------------------------------ pure host arithmetic ------
@@ -270,12 +270,19 @@ class DetectionPipeline:
                 fe_done[slot].synchronize()
                 free_q.put(host)                                    # H2D done: the pinned buffer can be refilled
                 self.counts["t_front_us"] += int(fe_start[slot].elapsed_time(fe_done[slot]) * 1e3)
+                good = []
                 for i, info in enumerate(g.files):
                     if i in bad:
-                        self.failed.append((info.path, bad[i])); continue
-                    t0 = time.perf_counter()
-                    tiles = tiles_buf[slot][tile_off[i]:tile_off[i + 1], 0]
-                    outputs = detect_tiles(self.model, tiles, self.min_score, self.bs)
+                        self.failed.append((info.path, bad[i]))
+                    else:
+                        good.append(i)
+                # one detector stream per group: the first batches of file i+1 are already running on the detector's
+                # replay lanes while file i's boxes are merged and written
+                stream = detect_stream(self.model, (tiles_buf[slot][tile_off[i]:tile_off[i + 1], 0] for i in good),
+                                       self.min_score, self.bs)
+                t0 = time.perf_counter()
+                for i, outputs in zip(good, stream):
+                    info = g.files[i]
                     t1 = time.perf_counter()
                     fp = SimpleNamespace(W_PIX=self.const["W_PIX"], HOP_SPECTRO=self.const["HOP_SPECTRO"],
                                          spectrogram_length=g.frames[i])
@@ -286,6 +293,7 @@ class DetectionPipeline:
                     c["detections"] += sum(len(v["scores"]) for v in output.values())
                     c["t_model_us"] += int((t1 - t0) * 1e6); c["t_post_us"] += int((t2 - t1) * 1e6)
                     yield info.path, output
+                    t0 = time.perf_counter()
                 det_done[slot] = torch.cuda.Event()
                 det_done[slot].record(cur)
         finally:

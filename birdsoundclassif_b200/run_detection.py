@@ -157,6 +157,17 @@ def detect_tiles(model, tiles: torch.Tensor, min_score: float, bs: int) -> list:
     return outputs
 
 
+def detect_stream(model, files, min_score: float, bs: int):
+    """``detect_tiles`` over an iterable of per-recording tile tensors: yields each recording's outputs in order.  A
+    ``GraphedDetector`` keeps its replay lanes busy across recording boundaries (the first batches of the next
+    recording run while this one's last batch finishes and its merge runs); any other model is called file by file."""
+    if hasattr(model, "detect_stream"):
+        yield from model.detect_stream(files, min_score, bs)
+        return
+    for tiles in files:
+        yield detect_tiles(model, tiles, min_score, bs)
+
+
 def run_detection(model, config, wav_path, bird_dicts_path, min_score=0.5, bs=10, visualise_outputs=False,
                   show_sp_name=True, timings: dict | None = None):
     """Same signature and return value as the reference's run_detection (plotting is not

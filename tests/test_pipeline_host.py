@@ -129,3 +129,54 @@ def test_pipeline_needs_cuda(tmp_path):
     d.write_text(json.dumps({"A": 1}))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         pl.DetectionPipeline(None, synth.default_args("cpu"), str(d))
+
+
+@pytest.mark.parametrize("n_lanes", [1, 2, 3])
+def test_detect_stream_schedule(n_lanes):
+    """The software pipeline of GraphedDetector.detect_stream (host logic only, steps stubbed): every recording's
+    batches come back in order; a lane's static buffers are reused only after its previous batch went through the
+    second graph; and the host copy a second graph writes is read (`_finish`) before that lane's next second graph."""
+    import torch
+    from birdsoundclassif_b200.graphed import GraphedDetector, _Lane
+    det = GraphedDetector.__new__(GraphedDetector)
+    det._lanes = [_Lane() for _ in range(n_lanes)]
+    log, state = [], {"n": 0}
+    lane_of = {}
+
+    def stage1(samples, nms_thresh, min_score, lane):
+        b = state["n"]; state["n"] += 1
+        li = det._lanes.index(lane)
+        prev = [x for x in lane_of if lane_of[x] == li]
+        assert all(("s2", x) in log for x in prev), "lane reused before its previous batch's second graph"
+        lane_of[b] = li
+        log.append(("s1", b))
+        return ("started", b, int(samples.shape[0]))
+
+    def stage2(st):
+        _, b, n = st
+        assert ("s1", b) in log
+        earlier_same_lane = [x for x in lane_of if lane_of[x] == lane_of[b] and x < b]
+        assert all(("fin", x) in log for x in earlier_same_lane), "host copy overwritten before it was read"
+        log.append(("s2", b))
+        return ("pending", b, n)
+
+    def finish(p):
+        _, b, n = p
+        log.append(("fin", b))
+        return [("tile", b)] * n
+
+    det._stage1, det._stage2, det._finish = stage1, stage2, finish
+    sizes = [1, 9, 0, 6, 4, 13]
+    files = [torch.zeros((n, 2, 2)) for n in sizes]
+    got = list(det.detect_stream(iter(files), 0.2, 4))
+    assert [len(g) for g in got] == [(n + 3) // 4 for n in sizes]
+    flat = [b for g in got for out in g for (_, b) in out[:1]]
+    assert flat == list(range(sum((n + 3) // 4 for n in sizes)))           # batches in order, none lost
+    assert [len(out) for g in got for out in g] == [min(4, n - s) for n in sizes for s in range(0, n, 4)]
+    assert det.detect_tiles(files[1], 0.2, 4) is not None
+    # at most n_lanes first graphs are in flight at any time
+    inflight = 0
+    for ev, _ in log:
+        inflight += ev == "s1"
+        inflight -= ev == "s2"
+        assert inflight <= n_lanes

@@ -190,6 +190,14 @@ def test_two_replay_lanes_identical_to_one(gpu_case):
         # a single call and a two-batch run go through the same lanes
         _assert_same_tiles(eager[:1], [two(tiles[:4][:, None], min_score=0.02)], score_tol=0)
         _assert_same_tiles(eager[:2], rd.detect_tiles(two, tiles[:8], 0.02, 4), score_tol=0)
+        # detect_stream: recordings of 1, 9, 0, 6 and 4 tiles back to back through the lanes == each one on its own
+        files = [tiles[20:21], tiles[3:12], tiles[:0], tiles[30:36], tiles[40:44]]
+        want = [rd.detect_tiles(model, f, 0.02, 4) for f in files]
+        for det in (one, two, GraphedDetector(model, lanes=3), model):
+            got = list(rd.detect_stream(det, iter(files), 0.02, 4))
+            assert [len(g) for g in got] == [1, 3, 0, 2, 1]
+            for w, g in zip(want, got):
+                _assert_same_tiles(w, g, score_tol=0)
     finally:
         rd.unpatch_reference()
 
