@@ -116,7 +116,7 @@ def run(a, rank, world, local, dist):
         rd.accelerate_model(model)
         state.update(model=model, margs=margs, graphed=GraphedDetector(model))
 
-    def leg(dirpath, r, w, repeats, det=None):
+    def leg(dirpath, r, w, repeats, det=None, pipelined=True):
         """Best of `repeats` passes over the directory: (wall = max over ranks, per-rank counts) or None if a rank failed."""
         best = None
         for _ in range(repeats):
@@ -125,7 +125,7 @@ def run(a, rank, world, local, dist):
                 _rm_outputs(dirpath)
             barrier()
             ok, c = guarded(nbm_detect.detect_directory, det or state["graphed"], state["margs"], dirpath, bird_dict,
-                            min_score=0.2, bs=4, rank=r, world=w, verbose=False)
+                            min_score=0.2, bs=4, rank=r, world=w, verbose=False, pipelined=pipelined)
             if ok and c.get("failed"):
                 errors.append(f"rank {rank}: {c['failed']} files failed in {dirpath}")
                 ok = False
@@ -151,15 +151,20 @@ def run(a, rank, world, local, dist):
         if leg(cfg0_dir, rank, world, 1) is None or leg(cfg0_dir, rank, world, 1, det=model) is None:
             return fail("detect_directory failed on a rank")
         hours = 16 * 30.0 / 3600.0
-        for name, det in (("cfg0", None), ("cfg0_eager", model)):
-            res = leg(cfg0_dir, rank, world, 2, det=det)
+        legs = [("cfg0", None, True), ("cfg0_eager", model, True)]
+        if world == 1:
+            legs.append(("cfg0_file_by_file", None, False))
+        for name, det, pipelined in legs:
+            res = leg(cfg0_dir, rank, world, 2, det=det, pipelined=pipelined)
             if res is None:
                 return fail("detect_directory failed on a rank")
             wall, per_rank = res
             tot = sharding.totals(per_rank)
             out[name] = {"workload": "BASELINE configs[0]: 16 x 30 s wavs -> .txt, one directory sharded over the ranks, "
                                      "min_score 0.2, bs 4, reference CNN + stand-in checkpoint, detector forward "
-                                     + ("launched eagerly" if det is not None else "replayed from CUDA graphs"),
+                                     + ("launched eagerly" if det is not None else "replayed from CUDA graphs")
+                                     + ("" if pipelined else "; one run_detection call per file, as the reference loops "
+                                        "(no reader threads, no batched front-end, replay lanes drained at every file)"),
                          "audio_hours_per_s": hours / wall, "wall_s": wall, "files": tot["files"], "tiles": tot["tiles"],
                          "detections": tot["detections"], "scaling": "strong", "stage_s_sum_over_ranks": stages(per_rank)}
         # two passes, the faster one counts: the first also records a CUDA graph of the second stage for every RoI count M it
