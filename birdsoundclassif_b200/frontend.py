@@ -20,7 +20,7 @@ import os
 import numpy as np
 import torch
 
-from . import _lib, audio_io
+from . import _lib, audio_io, labels as labels_mod
 
 STFT_CHUNK = int(5e7)                                   # prepare_dataset.py:234
 LONG_FILE_SAMPLES = int(15e7) - int(15e7) % 44100       # prepare_dataset.py:194
@@ -237,8 +237,9 @@ def get_plan(freq_accuracy=33.3, dt=0.003, overlap_spectro=0.2, w_pix=1024, samp
 
 
 class File_Processor:
-    """Drop-in for the reference class on the inference path (labels are not supported: the
-    label joins of prepare_dataset.py:297-376 are dataset preparation, out of scope)."""
+    """Drop-in for the reference class (prepare_dataset.py:92-376).  Without ``labels`` -- the inference path --
+    ``process_file`` answers ``(tiles, None)``; with the reference's label table it answers ``(tiles, annotations)``:
+    the last tile padded by the annotated rule and one row of boxes per annotated tile (labels.py)."""
 
     H_PIX = 375      # px          prepare_dataset.py:96
     LOW_FREQ = 500   # hz          prepare_dataset.py:97
@@ -246,8 +247,6 @@ class File_Processor:
     requantise_long = True      # long recordings: the pieces pass through PCM16 temp files upstream (see _process_long)
 
     def __init__(self, filepath, extra_str_label="", labels=None):
-        if labels is not None:
-            raise NotImplementedError("label processing (training-set preparation) is out of scope")
         self.labels = labels
         self.ext = os.path.basename(filepath).split(".")[-1]
         self.filename = os.path.basename(filepath).replace("." + self.ext, "").replace(extra_str_label, "")
@@ -289,7 +288,27 @@ class File_Processor:
         tiles, minmax = plan.run(dev)
         self.spectrogram_length, _, _ = plan.query(n)
         self.s_min_max = minmax
-        return tiles[:, 0], None
+        if self.labels is None:
+            return tiles[:, 0], None
+        return self._annotate(tiles[:, 0], self.labels, self.filename, self.spectrogram_length)
+
+    def _annotate(self, tiles, table, filename, spectrogram_length):
+        """The labelled branches of split_power_spec (prepare_dataset.py:280-292: the last tile is padded in steps that
+        never mirror an annotated call into the padding) and process_file (:146-153: the per-tile box table, or
+        ``(None, None)`` when the table has no row for this recording)."""
+        rows = labels_mod.file_rows(table, filename)
+        w_last = spectrogram_length - (len(tiles) - 1) * self.HOP_SPECTRO
+        if len(rows) > 0 and w_last < self.W_PIX:
+            src = labels_mod.labelled_pad_map(w_last, self.W_PIX, labels_mod.empty_width_of(rows, spectrogram_length, self.DT))
+            pad = torch.from_numpy(src[w_last:]).to(tiles.device)
+            tiles[-1][:, w_last:] = tiles[-1][:, :w_last].index_select(1, pad)
+        c = dict(DT=self.DT, FREQ_ACCURACY=self.FREQ_ACCURACY, LOW_FREQ=self.LOW_FREQ, HIGH_FREQ=self.HIGH_FREQ,
+                 W_PIX=self.W_PIX, HOP_SPECTRO=self.HOP_SPECTRO, H_PIX=self.H_PIX)
+        try:
+            return tiles, labels_mod.merge_and_filter_labels(table, filename, self.ext, len(tiles), c)
+        except labels_mod.NoLabelsForFile:
+            print("Something went wrong with the annotation file, skipping~~")
+            return None, None
 
     def _process_long(self, plan, dev: torch.Tensor, n: int):
         """prepare_dataset.py:187-225: a recording longer than max_l = 3401 s is cut into max_l-sample pieces and every
@@ -319,4 +338,16 @@ class File_Processor:
         self.piece_spectrogram_lengths = [plan.query(cuts[k + 1] - cuts[k])[0] for k in range(len(cuts) - 1)]
         self.piece_samples = L
         self.s_min_max = minmax
-        return [tiles[tile_off[k]:tile_off[k + 1], 0] for k in range(len(cuts) - 1)], []
+        img_db = [tiles[tile_off[k]:tile_off[k + 1], 0] for k in range(len(cuts) - 1)]
+        annotations = []
+        if self.labels is not None:
+            # every piece against the annotations that start inside it, on its own time axis (:205-219); a piece
+            # without any is processed as unannotated, one whose table comes back empty answers (None, None) upstream
+            for k in range(len(img_db)):
+                rows = labels_mod.piece_labels(self.labels, self.filename, k, L / self.FREQ)
+                if rows is None:
+                    continue
+                img_db[k], ann = self._annotate(img_db[k], rows, f"temp{k}", self.piece_spectrogram_lengths[k])
+                if ann is not None:
+                    annotations.append(ann)
+        return img_db, annotations

@@ -281,6 +281,70 @@ def roipool_golden():
     print("roipool", pool.shape, np.bincount(np.asarray(lvl).ravel()))
 
 
+# ------------------------------------------------------------------------------ annotated recordings ----
+from tests.helpers import LABEL_CASES, label_table          # noqa: E402  (shared with the tests that read the fixture)
+
+
+def random_label_table(rng, filename, n, seconds):
+    import pandas as pd
+    t0 = rng.uniform(0, seconds, n)
+    dur = np.where(rng.random(n) < 0.2, rng.uniform(2.0, 8.0, n), rng.uniform(0.01, 0.8, n))
+    f0 = rng.uniform(0, 12000, n)
+    return pd.DataFrame({"filename": filename, "t_start": t0, "t_end": t0 + dur, "f_start": f0,
+                         "f_end": f0 + np.where(rng.random(n) < 0.1, 5.0, rng.uniform(100, 6000, n)),
+                         "bird_id": rng.choice([-1, 1, 2, 3, 77, 150], n)})
+
+
+def _pack_annotations(out, key, ann):
+    out[key + "/index"] = np.asarray(ann["index"].values, dtype=np.int64)
+    out[key + "/count"] = np.asarray([len(c) for c in ann["coord"]], dtype=np.int64)
+    out[key + "/coord"] = np.asarray([list(map(int, b)) for c in ann["coord"] for b in c], dtype=np.int64).reshape(-1, 4)
+    out[key + "/bird_id"] = np.asarray([int(b) for c in ann["bird_id"] for b in c], dtype=np.int64)
+
+
+def labels_golden():
+    """The reference's File_Processor WITH a label table (prepare_dataset.py:146-153, 280-292, 297-376)."""
+    pd_mod = ref_shims.ref("nbm_model.nbm_datasets.prepare_dataset")
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        for name, secs, seed, last_end in LABEL_CASES:
+            pcm = synth.synth_pcm(secs, seed)
+            path = synth.write_wav(os.path.join(d, name + ".wav"), pcm)
+            fp = pd_mod.File_Processor(path, "", label_table(name, last_end))
+            tiles, ann = fp.process_file()
+            last = np.asarray(tiles[-1])
+            out[name + "/pcm_crc"] = np.uint32(zlib.crc32(pcm.tobytes()))
+            out[name + "/n_tiles"] = np.int64(len(tiles))
+            out[name + "/spectrogram_length"] = np.int64(fp.spectrogram_length)
+            out[name + "/last_rows"] = last[[0, 187, 374], :].astype(np.float32)       # three full rows of the padded tile
+            out[name + "/last_sum"] = np.float64(last.sum())
+            _pack_annotations(out, name, ann)
+            print(name, len(tiles), fp.spectrogram_length, len(ann))
+    # merge_and_filter_labels alone on random tables (a stub instance: no audio needed), wav and mp3 naming
+    rng = np.random.default_rng(5)
+    for name, ext, n_img, n in (("rand_wav", "wav", 25, 120), ("rand_mp3", "mp3", 7, 40)):
+        fp = pd_mod.File_Processor(f"/nowhere/{name}.{ext}", "", None)
+        c = synth_consts()
+        for k, v in c.items():
+            setattr(fp, k, v)
+        table = random_label_table(rng, name, n, (n_img * 819 + 205) * c["DT"])
+        fp.labels = table
+        ann = fp.merge_and_filter_labels([None] * n_img)
+        for col in ("t_start", "t_end", "f_start", "f_end", "bird_id"):
+            out[f"{name}/table_{col}"] = table[col].to_numpy()
+        out[name + "/n_img"] = np.int64(n_img)
+        _pack_annotations(out, name, ann)
+        print(name, len(ann))
+    np.savez_compressed(os.path.join(GOLD, "labels.npz"), **out)
+
+
+def synth_consts():
+    from birdsoundclassif_b200.frontend import derive_constants
+    c = derive_constants()
+    c["H_PIX"] = 375
+    return c
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
@@ -291,6 +355,7 @@ def main():
     tail_golden()
     merge_golden()
     roipool_golden()
+    labels_golden()
 
 
 if __name__ == "__main__":

@@ -19,8 +19,8 @@ def test_png_roundtrip_and_structure():
         assert np.array_equal(dataset.decode_png_gray8(png), img)
 
 
-def test_annotations_are_out_of_scope(tmp_path):
-    with pytest.raises(NotImplementedError):
+def test_annotations_need_the_label_table(tmp_path):
+    with pytest.raises(NotImplementedError, match="labels="):
         dataset.prepare_dataset(str(tmp_path), str(tmp_path / "out"))
 
 
@@ -70,3 +70,43 @@ def test_prepare_dataset_layout_and_images(tmp_path):
             assert got.shape == (375, 1024) and d.max() <= 1 and (d != 0).mean() < 2e-3, (f, d.max(), (d != 0).mean())
     # a second call skips directories that exist (prepare_dataset.py:51-52)
     assert dataset.prepare_dataset(str(src), str(out), annotations=False) == 0
+
+
+@pytest.mark.gpu
+def test_prepare_dataset_with_annotations(tmp_path):
+    """annotations=True with the label table: annotated tiles + annotations.csv under positive_files, the other tiles
+    under negative_files, a recording the table does not know is skipped (prepare_dataset.py:33-89, 146-153)."""
+    import ast
+    import csv
+    from . import helpers as H
+    g = H.load("labels.npz")
+    src = tmp_path / "site"
+    src.mkdir()
+    synth.write_wav(str(src / "lab_tail.wav"), synth.synth_pcm(13.0, 21))
+    synth.write_wav(str(src / "lab_far.wav"), synth.synth_pcm(13.0, 23))
+    synth.write_wav(str(src / "unknown.wav"), synth.synth_pcm(2.0, 5))
+    out = tmp_path / "out"
+    import pandas as pd
+    table = pd.concat([H.label_table("lab_tail", 12.8827), H.label_table("lab_far", 6.0)], ignore_index=True)
+    n = dataset.prepare_dataset(str(src), str(out), labels=table)
+    assert n == 12
+    for name in ("lab_tail", "lab_far"):
+        want = H.annotations_from_gold(g, name)
+        pos = sorted(os.listdir(out / "positive_files" / f"site__{name}"))
+        assert pos == ["annotations.csv"] + [f"site__{name}__{i:05d}.png" for i, _, _ in want]
+        neg_dir = out / "negative_files" / f"site__{name}"
+        neg = sorted(os.listdir(neg_dir)) if neg_dir.exists() else []
+        assert neg == [f"site__{name}__{i:05d}.png" for i in range(6) if i not in {w[0] for w in want}]
+        assert len(pos) - 1 + len(neg) == 6
+    assert len(os.listdir(out / "negative_files" / "site__lab_far")) == 2
+    assert not (out / "positive_files" / "site__unknown").exists() and not (out / "negative_files" / "site__unknown").exists()
+    want = H.annotations_from_gold(g, "lab_tail")
+    with open(out / "positive_files" / "site__lab_tail" / "annotations.csv") as f:
+        rows = list(csv.reader(f, delimiter=";"))
+    assert rows[0] == ["index", "coord", "bird_id"]
+    got = [(int(r[0]), [tuple(b) for b in ast.literal_eval(r[1])], ast.literal_eval(r[2])) for r in rows[1:]]
+    assert got == want
+    # the last tile's image carries the annotated padding: compare with the reference's rows
+    last = dataset.decode_png_gray8(open(out / "positive_files" / "site__lab_tail" / "site__lab_tail__00005.png", "rb").read())
+    ref_rows = np.round(g["lab_tail/last_rows"].astype(np.float64) * 255)
+    assert np.abs(last[[0, 187, 374]].astype(np.float64) - ref_rows).max() <= 1
