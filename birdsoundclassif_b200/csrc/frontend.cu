@@ -600,11 +600,13 @@ __global__ void upload_kernel(uint4 *__restrict__ dst, const uint4 *__restrict__
 // columns past the file's end mirror numpy's iterated 'reflect' pad of the partial window.
 // (x - s_min) / (s_max - s_min) as reciprocal + one FMA Newton step: correctly rounded for these operands
 // (in particular exactly 0 and 1 at the extremes) at a third of the cost of the IEEE divide sequence.
-__device__ __forceinline__ float norm_div(float num, float den, float inv) {
+// `dz` is 0, or NaN for a recording whose band is constant (digital silence: s_max == s_min): the reference's 0 / 0 is NaN
+// in every pixel (prepare_dataset.py:250), and the clamp below would turn it into 0.
+__device__ __forceinline__ float norm_div(float num, float den, float inv, float dz) {
     const float q = num * inv;
     const float r = fmaf(-q, den, num);
     // the reference's image lies in [0, 1]; only unrefined floor pixels of digital silence can leave it by an ulp
-    return fminf(fmaxf(fmaf(r, inv, q), 0.0f), 1.0f);
+    return fminf(fmaxf(fmaf(r, inv, q), 0.0f), 1.0f) + dz;
 }
 
 __device__ __forceinline__ int reflect_src(int c, int width, int period) {
@@ -623,6 +625,7 @@ tile_block(const KParams &P, const FileDesc &fd, long long tile, int row_block, 
     const int width = (kt == fd.n_tiles - 1) ? fd.last_width : P.w_pix;
     const float range = smax - smin;
     const float inv = 1.0f / range;
+    const float dz = range > 0.0f ? 0.0f : __int_as_float(0x7fc00000);
     const int r0 = row_block * TILE_ROWS;
     const int r1 = min(r0 + TILE_ROWS, P.n_bins);
     const int period = 2 * (width - 1);
@@ -650,10 +653,10 @@ tile_block(const KParams &P, const FileDesc &fd, long long tile, int row_block, 
                     else if (S == 2) v = make_float4(a.z, a.w, b.x, b.y);
                     else v = make_float4(a.w, b.x, b.y, b.z);
                     float4 o;
-                    o.x = norm_div(v.x - smin, range, inv);
-                    o.y = norm_div(v.y - smin, range, inv);
-                    o.z = norm_div(v.z - smin, range, inv);
-                    o.w = norm_div(v.w - smin, range, inv);
+                    o.x = norm_div(v.x - smin, range, inv, dz);
+                    o.y = norm_div(v.y - smin, range, inv, dz);
+                    o.z = norm_div(v.z - smin, range, inv, dz);
+                    o.w = norm_div(v.w - smin, range, inv, dz);
                     __stcs(reinterpret_cast<float4 *>(tbase + (long long)r * P.w_pix + c), o);
                 }
             }
@@ -674,10 +677,10 @@ tile_block(const KParams &P, const FileDesc &fd, long long tile, int row_block, 
             for (int r = r0; r < r1; ++r) {
                 const float *sp = sbase + (long long)r * fd.row_stride;
                 float4 o;
-                o.x = norm_div(ld(sp + src[0]) - smin, range, inv);
-                o.y = norm_div(ld(sp + src[1]) - smin, range, inv);
-                o.z = norm_div(ld(sp + src[2]) - smin, range, inv);
-                o.w = norm_div(ld(sp + src[3]) - smin, range, inv);
+                o.x = norm_div(ld(sp + src[0]) - smin, range, inv, dz);
+                o.y = norm_div(ld(sp + src[1]) - smin, range, inv, dz);
+                o.z = norm_div(ld(sp + src[2]) - smin, range, inv, dz);
+                o.w = norm_div(ld(sp + src[3]) - smin, range, inv, dz);
                 __stcs(reinterpret_cast<float4 *>(tbase + (long long)r * P.w_pix + c), o);
             }
         }
@@ -685,7 +688,7 @@ tile_block(const KParams &P, const FileDesc &fd, long long tile, int row_block, 
         for (int c = threadIdx.x; c < P.w_pix; c += blockDim.x) {
             const int src = reflect_src(c, width, period);
             for (int r = r0; r < r1; ++r)
-                tbase[(long long)r * P.w_pix + c] = norm_div(ld(sbase + (long long)r * fd.row_stride + src) - smin, range, inv);
+                tbase[(long long)r * P.w_pix + c] = norm_div(ld(sbase + (long long)r * fd.row_stride + src) - smin, range, inv, dz);
         }
     }
 }

@@ -236,33 +236,46 @@ class GraphedDetector:
         and the dictionaries of the batches before that are built while both run."""
         lanes = self._lanes
         L = len(lanes)
-        started, pending, open_files = [], [], []        # FIFOs; open_files: [n batches, all enqueued, outputs so far]
+        started, pending, open_files = [], [], []        # FIFOs of (recording ordinal, state); open_files: [n batches, all enqueued, outputs so far]
         i = 0
+
+        def attributed(fn, item):
+            """Run one pipeline step of a batch; an exception leaves with the ordinal of the recording it belongs to
+            (``nbm_file_index``): the stream runs ahead, so the caller cannot tell from where it stands."""
+            try:
+                return (item[0], fn(item[1]))
+            except Exception as e:
+                e.nbm_file_index = item[0]
+                raise
 
         def finish_oldest():
             f = next(e for e in open_files if e[0] > len(e[2]))
-            f[2].append(self._finish(pending.pop(0)))
+            f[2].append(attributed(self._finish, pending.pop(0))[1])
+
+        def second(item):
+            pending.append(attributed(self._stage2, item))
 
         def ready():
             while open_files and open_files[0][0] == len(open_files[0][2]) and open_files[0][1]:
                 yield open_files.pop(0)[2]
 
-        for tiles in files:
+        for ordinal, tiles in enumerate(files):
             n_batches = (len(tiles) + bs - 1) // bs
             entry = [n_batches, False, []]
             open_files.append(entry)
             for s in range(0, len(tiles), bs):
-                started.append(self._stage1(tiles[s:s + bs][:, None], nms_thresh, min_score, lanes[i % L]))
+                started.append(attributed(lambda t: self._stage1(t, nms_thresh, min_score, lanes[i % L]),
+                                          (ordinal, tiles[s:s + bs][:, None])))
                 i += 1
                 if L == 1:
                     # one lane: the second graph's host copy of the class keys is free only after the previous batch's
                     # dictionaries were built from it
                     while pending:
                         finish_oldest()
-                    pending.append(self._stage2(started.pop(0)))
+                    second(started.pop(0))
                 else:
                     if len(started) == L:
-                        pending.append(self._stage2(started.pop(0)))
+                        second(started.pop(0))
                     while len(pending) > 1:
                         finish_oldest()
                 if s + bs >= len(tiles):
@@ -272,7 +285,7 @@ class GraphedDetector:
                 entry[1] = True
                 yield from ready()
         while started:
-            pending.append(self._stage2(started.pop(0)))
+            second(started.pop(0))
             while len(pending) > 1:
                 finish_oldest()
         while pending:

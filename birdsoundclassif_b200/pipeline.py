@@ -277,23 +277,38 @@ class DetectionPipeline:
                     else:
                         good.append(i)
                 # one detector stream per group: the first batches of file i+1 are already running on the detector's
-                # replay lanes while file i's boxes are merged and written
-                stream = detect_stream(self.model, (tiles_buf[slot][tile_off[i]:tile_off[i + 1], 0] for i in good),
-                                       self.min_score, self.bs)
-                t0 = time.perf_counter()
-                for i, outputs in zip(good, stream):
-                    info = g.files[i]
-                    t1 = time.perf_counter()
-                    fp = SimpleNamespace(W_PIX=self.const["W_PIX"], HOP_SPECTRO=self.const["HOP_SPECTRO"],
-                                         spectrogram_length=g.frames[i])
-                    output = postproc.merge_to_output(fp, outputs, self.config.num_classes, self.reverse_dict)
-                    t2 = time.perf_counter()
-                    c = self.counts
-                    c["files"] += 1; c["tiles"] += g.tiles[i]; c["frames"] += g.frames[i]
-                    c["detections"] += sum(len(v["scores"]) for v in output.values())
-                    c["t_model_us"] += int((t1 - t0) * 1e6); c["t_post_us"] += int((t2 - t1) * 1e6)
-                    yield info.path, output
+                # replay lanes while file i's boxes are merged and written.  A file the detector fails on (the reference
+                # crashes there, e.g. "RPN failed" on a silent recording) is reported and left out; the stream is
+                # restarted behind it.
+                while good:
+                    stream = detect_stream(self.model, (tiles_buf[slot][tile_off[i]:tile_off[i + 1], 0] for i in good),
+                                           self.min_score, self.bs)
+                    n_done = 0
                     t0 = time.perf_counter()
+                    try:
+                        for i, outputs in zip(good, stream):
+                            info = g.files[i]
+                            t1 = time.perf_counter()
+                            fp = SimpleNamespace(W_PIX=self.const["W_PIX"], HOP_SPECTRO=self.const["HOP_SPECTRO"],
+                                                 spectrogram_length=g.frames[i])
+                            output = postproc.merge_to_output(fp, outputs, self.config.num_classes, self.reverse_dict)
+                            t2 = time.perf_counter()
+                            c = self.counts
+                            c["files"] += 1; c["tiles"] += g.tiles[i]; c["frames"] += g.frames[i]
+                            c["detections"] += sum(len(v["scores"]) for v in output.values())
+                            c["t_model_us"] += int((t1 - t0) * 1e6); c["t_post_us"] += int((t2 - t1) * 1e6)
+                            n_done += 1
+                            yield info.path, output
+                            t0 = time.perf_counter()
+                        good = []
+                    except Exception as e:
+                        k = getattr(e, "nbm_file_index", None)
+                        if k is None:                               # a detector without attribution: the file it was asked for
+                            k = n_done
+                        k = max(k, n_done)                          # (merge errors surface at the file being merged)
+                        self.failed.append((g.files[good[k]].path, f"{type(e).__name__}: {e}"))
+                        torch.cuda.synchronize(dev)
+                        good = good[n_done:k] + good[k + 1:]
                 det_done[slot] = torch.cuda.Event()
                 det_done[slot].record(cur)
         finally:

@@ -321,3 +321,22 @@ def test_full_size_batch_properties(fe):
     assert checksum(tiles2) == c1
     del tiles, tiles2, t, pcm
     torch.cuda.empty_cache()
+
+
+def test_digital_silence_is_nan_like_the_reference(fe):
+    """A recording of zeros: every pixel sits on the -100 dB floor, s_max == s_min, and the reference's normalisation is
+    0 / 0 = NaN in every pixel (prepare_dataset.py:248-250) -- its detector then fails on the file.  Same here (not 0)."""
+    from oracle import frontend_oracle as fo
+    pcm = np.zeros(3 * 44100, dtype=np.int16)
+    fp, tiles = _gpu_tiles(fe, pcm)
+    with np.errstate(invalid="ignore"):
+        r = fo.process(pcm)
+    assert np.isnan(np.stack(r.tiles)).all() and r.s_min == r.s_max
+    assert tiles.shape[0] == len(r.tiles) and bool(torch.isnan(tiles).all())
+    smin, smax = fp.s_min_max.cpu().tolist()
+    assert smin == smax and abs(smin - r.s_min) <= TOL_SMIN_DB
+    # in a batch, only the silent file is affected
+    other = synth.synth_pcm(3.0, 97)
+    plan = fe.FrontendPlan()
+    both, toff, _ = plan.run_batch(torch.from_numpy(np.concatenate([pcm, other])).cuda(), [0, len(pcm), len(pcm) + len(other)])
+    assert bool(torch.isnan(both[toff[0]:toff[1]]).all()) and bool(torch.isfinite(both[toff[1]:toff[2]]).all())

@@ -170,3 +170,37 @@ def test_long_recording_detection(tmp_path, monkeypatch):
         texts[pipelined] = {os.path.basename(f): open(f).read() for f in sorted(glob.glob(str(tmp_path / "*.txt")))}
     assert texts[True] == texts[False] and set(texts[True]) == {"a_long.txt", "b_short.txt"}
     assert texts[True]["a_long.txt"] == str(out)
+
+
+def test_pipelined_driver_isolates_a_file_the_detector_fails_on(tmp_path):
+    """A recording the detector raises on (upstream: "RPN failed" and a crash, layers.py:288-290 -- digital silence
+    normalises to 0/0) is reported and has no .txt; every other file of the same front-end group is detected as if
+    it were not there."""
+    from birdsoundclassif_b200 import nbm_detect
+    d = tmp_path
+    for i, secs in enumerate([5.0, 9.0, 3.0, 12.5, 2.0]):
+        pcm = synth.synth_pcm(secs, 760 + i)
+        if i in (0, 3):
+            pcm[:] = 0
+        synth.write_wav(str(d / f"rec_{i:02d}.wav"), pcm)
+    bird = str(d / "bird_dict.json")
+    with open(bird, "w") as f:
+        json.dump({f"Species {i}": i for i in range(1, 151)}, f)
+    args = synth.default_args("cuda")
+    inner = StandInDetector(args, backend="nbm").cuda()
+
+    def model(batch, min_score=0.5):
+        if torch.isnan(batch).any():
+            raise RuntimeError("RPN produced fewer than rcnn_batch_size candidate boxes")
+        return inner(batch, min_score=min_score)
+
+    def run(pipelined):
+        for f in glob.glob(str(d / "*.txt")):
+            os.remove(f)
+        c = nbm_detect.detect_directory(model, args, str(d), bird, 0.05, 4, verbose=False, pipelined=pipelined)
+        return c, {os.path.basename(f): open(f).read() for f in sorted(glob.glob(str(d / "*.txt")))}
+
+    c_seq, t_seq = run(False)
+    c_pipe, t_pipe = run(True)
+    assert sorted(t_seq) == ["rec_01.txt", "rec_02.txt", "rec_04.txt"] and t_pipe == t_seq
+    assert c_seq["failed"] == c_pipe["failed"] == 2 and c_pipe["files"] == 3

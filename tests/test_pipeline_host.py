@@ -180,3 +180,30 @@ def test_detect_stream_schedule(n_lanes):
         inflight += ev == "s1"
         inflight -= ev == "s2"
         assert inflight <= n_lanes
+
+
+def test_detect_stream_names_the_failing_recording():
+    """The stream runs ahead of the recording the caller waits for: an exception carries the ordinal of the recording
+    whose batch raised (`nbm_file_index`), here the third one while the caller is still collecting the second."""
+    import torch
+    from birdsoundclassif_b200.graphed import GraphedDetector, _Lane
+    det = GraphedDetector.__new__(GraphedDetector)
+    det._lanes = [_Lane(), _Lane()]
+    n = {"b": 0}
+
+    def stage1(samples, nms_thresh, min_score, lane):
+        n["b"] += 1
+        return n["b"] - 1
+
+    def stage2(b):
+        if b == 3:                          # recordings of 2, 1, 2 batches: batch 3 is the first of the third
+            raise RuntimeError("RPN failed")
+        return b
+
+    det._stage1, det._stage2, det._finish = stage1, stage2, lambda b: [b]
+    files = [torch.zeros((8, 2, 2)), torch.zeros((3, 2, 2)), torch.zeros((5, 2, 2))]
+    got = []
+    with pytest.raises(RuntimeError) as ei:
+        for out in det.detect_stream(iter(files), 0.2, 4):
+            got.append(out)
+    assert ei.value.nbm_file_index == 2 and got == [[[0], [1]]]       # the second recording was still in flight: the caller re-runs it
