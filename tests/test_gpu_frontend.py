@@ -340,3 +340,28 @@ def test_digital_silence_is_nan_like_the_reference(fe):
     plan = fe.FrontendPlan()
     both, toff, _ = plan.run_batch(torch.from_numpy(np.concatenate([pcm, other])).cuda(), [0, len(pcm), len(pcm) + len(other)])
     assert bool(torch.isnan(both[toff[0]:toff[1]]).all()) and bool(torch.isfinite(both[toff[1]:toff[2]]).all())
+
+
+@pytest.mark.parametrize("kw,impl", [
+    (dict(freq_accuracy=25.0, dt=0.003, overlap_spectro=0.3, w_pix=512), "tcgen05"),       # n_fft 1764, hop 132, tiles of 512 at hop 358
+    (dict(freq_accuracy=25.0, dt=0.004, overlap_spectro=0.2, w_pix=1024), "cuda-core"),    # hop 176: six k-steps of twiddles do not fit in TMEM
+    (dict(freq_accuracy=20.0, dt=0.002, overlap_spectro=0.5, w_pix=256), "cuda-core"),     # n_fft 2205 is odd: CUDA-core kernels
+    (dict(freq_accuracy=33.3, dt=0.003, overlap_spectro=0.0, w_pix=1024), "tcgen05"),      # no overlap between tiles
+    (dict(freq_accuracy=50.0, dt=0.003, overlap_spectro=0.2, w_pix=1024), "tcgen05"),      # n_fft 882 = 4 k + 2, coarser bins
+], ids=["w512", "hop176", "w256_odd_nfft", "no_overlap", "nfft882"])
+def test_process_file_parameter_variations(fe, kw, impl):
+    """process_file's four keyword parameters away from their defaults (prepare_dataset.py:108): window and hop of the
+    STFT, tile width and tile overlap.  Against the oracle, which tests/test_oracle_frontend.py pins to the reference's
+    own File_Processor for such parameters."""
+    from oracle import frontend_oracle as fo
+    pcm = synth.synth_pcm(7.3, 88)
+    fp, tiles = _gpu_tiles(fe, pcm, **kw)
+    assert fe.get_plan(**kw).impl == impl
+    p = fo.derive_params(**kw)
+    r = fo.process(pcm, p)
+    assert (fp.W_PIX, fp.HOP_SPECTRO, fp.WIN_LENGTH, fp.HOP_LENGTH, fp.LOW_IDX, fp.HIGH_IDX) == \
+        (p.w_pix, p.hop_spectro, p.n_fft, p.hop, p.low_idx, p.high_idx)
+    assert fp.spectrogram_length == r.spectrogram_length and tiles.shape == (len(r.tiles), 375, kw["w_pix"])
+    assert_tiles_close(tiles.cpu().numpy(), np.stack(r.tiles), str(kw))
+    smin, smax = fp.s_min_max.cpu().tolist()
+    assert abs(smin - r.s_min) <= TOL_SMIN_DB and abs(smax - r.s_max) <= TOL_SMAX_DB
