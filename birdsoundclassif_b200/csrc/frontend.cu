@@ -600,13 +600,11 @@ __global__ void upload_kernel(uint4 *__restrict__ dst, const uint4 *__restrict__
 // columns past the file's end mirror numpy's iterated 'reflect' pad of the partial window.
 // (x - s_min) / (s_max - s_min) as reciprocal + one FMA Newton step: correctly rounded for these operands
 // (in particular exactly 0 and 1 at the extremes) at a third of the cost of the IEEE divide sequence.
-// `dz` is 0, or NaN for a recording whose band is constant (digital silence: s_max == s_min): the reference's 0 / 0 is NaN
-// in every pixel (prepare_dataset.py:250), and the clamp below would turn it into 0.
-__device__ __forceinline__ float norm_div(float num, float den, float inv, float dz) {
+__device__ __forceinline__ float norm_div(float num, float den, float inv) {
     const float q = num * inv;
     const float r = fmaf(-q, den, num);
     // the reference's image lies in [0, 1]; only unrefined floor pixels of digital silence can leave it by an ulp
-    return fminf(fmaxf(fmaf(r, inv, q), 0.0f), 1.0f) + dz;
+    return fminf(fmaxf(fmaf(r, inv, q), 0.0f), 1.0f);
 }
 
 __device__ __forceinline__ int reflect_src(int c, int width, int period) {
@@ -625,12 +623,20 @@ tile_block(const KParams &P, const FileDesc &fd, long long tile, int row_block, 
     const int width = (kt == fd.n_tiles - 1) ? fd.last_width : P.w_pix;
     const float range = smax - smin;
     const float inv = 1.0f / range;
-    const float dz = range > 0.0f ? 0.0f : __int_as_float(0x7fc00000);
     const int r0 = row_block * TILE_ROWS;
     const int r1 = min(r0 + TILE_ROWS, P.n_bins);
     const int period = 2 * (width - 1);
     const float *sbase = spec + fd.spec_off + start;
     float *tbase = tiles + (tile * P.n_bins) * P.w_pix;
+    if (!(range > 0.0f)) {
+        // A recording whose band is constant (digital silence: s_max == s_min): the reference's 0 / 0 is NaN in every pixel
+        // (prepare_dataset.py:250), where norm_div's clamp would give 0.  Block-uniform, so the pixel loops below stay as
+        // they are (one extra instruction per pixel there cost the pass 2.5 %).
+        const float nanv = __int_as_float(0x7fc00000);
+        for (int r = r0; r < r1; ++r)
+            for (int c = threadIdx.x; c < P.w_pix; c += blockDim.x) tbase[(long long)r * P.w_pix + c] = nanv;
+        return;
+    }
     // L2_ONLY: the band was written by other SMs during this very launch; read it from L2, never through L1
     auto ld = [](const float *p) { return L2_ONLY ? __ldcg(p) : *p; };
     if (VEC4 && width == P.w_pix) {
@@ -653,10 +659,10 @@ tile_block(const KParams &P, const FileDesc &fd, long long tile, int row_block, 
                     else if (S == 2) v = make_float4(a.z, a.w, b.x, b.y);
                     else v = make_float4(a.w, b.x, b.y, b.z);
                     float4 o;
-                    o.x = norm_div(v.x - smin, range, inv, dz);
-                    o.y = norm_div(v.y - smin, range, inv, dz);
-                    o.z = norm_div(v.z - smin, range, inv, dz);
-                    o.w = norm_div(v.w - smin, range, inv, dz);
+                    o.x = norm_div(v.x - smin, range, inv);
+                    o.y = norm_div(v.y - smin, range, inv);
+                    o.z = norm_div(v.z - smin, range, inv);
+                    o.w = norm_div(v.w - smin, range, inv);
                     __stcs(reinterpret_cast<float4 *>(tbase + (long long)r * P.w_pix + c), o);
                 }
             }
@@ -677,10 +683,10 @@ tile_block(const KParams &P, const FileDesc &fd, long long tile, int row_block, 
             for (int r = r0; r < r1; ++r) {
                 const float *sp = sbase + (long long)r * fd.row_stride;
                 float4 o;
-                o.x = norm_div(ld(sp + src[0]) - smin, range, inv, dz);
-                o.y = norm_div(ld(sp + src[1]) - smin, range, inv, dz);
-                o.z = norm_div(ld(sp + src[2]) - smin, range, inv, dz);
-                o.w = norm_div(ld(sp + src[3]) - smin, range, inv, dz);
+                o.x = norm_div(ld(sp + src[0]) - smin, range, inv);
+                o.y = norm_div(ld(sp + src[1]) - smin, range, inv);
+                o.z = norm_div(ld(sp + src[2]) - smin, range, inv);
+                o.w = norm_div(ld(sp + src[3]) - smin, range, inv);
                 __stcs(reinterpret_cast<float4 *>(tbase + (long long)r * P.w_pix + c), o);
             }
         }
@@ -688,7 +694,7 @@ tile_block(const KParams &P, const FileDesc &fd, long long tile, int row_block, 
         for (int c = threadIdx.x; c < P.w_pix; c += blockDim.x) {
             const int src = reflect_src(c, width, period);
             for (int r = r0; r < r1; ++r)
-                tbase[(long long)r * P.w_pix + c] = norm_div(ld(sbase + (long long)r * fd.row_stride + src) - smin, range, inv, dz);
+                tbase[(long long)r * P.w_pix + c] = norm_div(ld(sbase + (long long)r * fd.row_stride + src) - smin, range, inv);
         }
     }
 }
