@@ -17,9 +17,13 @@ Group g+1 is read and transformed while group g is in the detector; events hand 
 and forth.  A file is never split across groups (its normalisation is file-global), so every tile, and
 therefore every box, equals what ``run_detection.run_detection`` returns for that file alone (tested).
 
-Not done here: a CUDA graph of the detector forward.  The reference network's forward reads sizes back to
-the host (proposal counts, ``.item()`` / ``.tolist()`` in its second stage), so its launch sequence is
-data-dependent and cannot be captured unmodified; the north star keeps that network as it is.
+The detector itself is whatever ``model`` is: the reference's NbmModel, eager, or ``graphed.GraphedDetector``
+(its forward replayed from CUDA graphs on two lanes); a group's files go to it as ONE stream
+(``run_detection.detect_stream``), so a graphed detector stays busy across file boundaries.
+
+Start-up matters for short directories (BASELINE configs[0] is 16 files, 0.6 s): the pipeline's private front-end
+plan (twiddle tables, workspace) and its pinned / device buffers are taken from process-wide pools and given back
+at the end of ``run``, so a second directory in the same process does not pay for them again.
 """
 from __future__ import annotations
 
@@ -140,6 +144,41 @@ def read_into(info: WavInfo, dst: np.ndarray) -> None:
     dst[:] = a
 
 
+# --------------------------------------------------------------------- process-wide pools -----
+_POOL_LOCK = threading.Lock()
+_PLAN_POOL: dict = {}           # front-end parameters -> [idle FrontendPlan, ...]
+_PINNED_POOL: list = []         # idle pinned int16 buffers
+
+
+def _take_plan(fe_args):
+    """A front-end plan nobody else is using (a plan owns one workspace and one side stream: one caller at a time)."""
+    with _POOL_LOCK:
+        idle = _PLAN_POOL.get(tuple(fe_args))
+        if idle:
+            return idle.pop()
+    return FrontendPlan(*fe_args)
+
+
+def _give_plan(fe_args, plan):
+    with _POOL_LOCK:
+        _PLAN_POOL.setdefault(tuple(fe_args), []).append(plan)
+
+
+def _take_pinned(n_values: int) -> torch.Tensor:
+    with _POOL_LOCK:
+        for i, t in enumerate(_PINNED_POOL):
+            if t.numel() >= n_values:
+                return _PINNED_POOL.pop(i)
+    return torch.empty(max(n_values, 1), dtype=torch.int16, pin_memory=True)
+
+
+def _give_pinned(bufs):
+    with _POOL_LOCK:
+        _PINNED_POOL.extend(bufs)
+        _PINNED_POOL.sort(key=lambda t: t.numel())
+        del _PINNED_POOL[:-6]                       # keep the six largest
+
+
 # ------------------------------------------------------------------------- the pipeline -------
 class DetectionPipeline:
     """``run(paths)`` yields ``(path, output_dict)`` in input order (recordings longer than 3401 s last), the
@@ -164,6 +203,7 @@ class DetectionPipeline:
         # on a stream of its own while the caller's stream (and possibly File_Processor / run_detection calls on the
         # process-wide plan of frontend.get_plan) is busy with the detector, so it gets a private plan.
         self._plan = None
+        self._trace = None
 
     # reader side: fills pinned buffers, two groups ahead at most
     def _reader(self, groups, out_q: queue.Queue, free_q: queue.Queue, pool: ThreadPoolExecutor):
@@ -191,16 +231,26 @@ class DetectionPipeline:
         except BaseException as e:          # surfaces in run(), never a silent short result
             out_q.put(e)
 
+    def _mark(self, label):
+        if self._trace is not None:
+            self._trace.append((label, time.perf_counter()))
+
     def run(self, paths):
-        if self._plan is None:
-            self._plan = FrontendPlan(*self.fe_args)
-        plan = self._plan
+        self._trace = [] if os.environ.get("NBM_PIPE_TRACE") else None       # start-up timeline on stderr
+        self._mark("start")
         infos = [probe_wav(p) for p in paths]
         groups, rejected = plan_groups(infos, self.const, self.max_group_tiles, first_group_tiles=self.first_group_tiles)
         long_files = [info.path for info, why in rejected if why in (LONG_REASON, SOLO_REASON)]
         self.failed += [(info.path, why) for info, why in rejected if why not in (LONG_REASON, SOLO_REASON)]
+        self._mark(f"probed {len(infos)} files, {len(groups)} groups")
         if groups:
-            yield from self._run_groups(plan, groups)
+            plan = self._plan = _take_plan(self.fe_args)
+            self._mark("front-end plan")
+            try:
+                yield from self._run_groups(plan, groups)
+            finally:
+                self._plan = None
+                _give_plan(self.fe_args, plan)          # _run_groups has synchronised the device: nothing of ours is in flight
         # recordings longer than 3401 s: File_Processor cuts them into pieces that are one front-end batch already
         # (frontend.File_Processor._process_long); files at another sample rate or sample format need the host decode /
         # resample stage of File_Processor.load.  Both go through run_detection one at a time, after the groups
@@ -230,11 +280,13 @@ class DetectionPipeline:
         det_done = [None] * n_buf
         out_q: queue.Queue = queue.Queue()
         free_q: queue.Queue = queue.Queue()
-        for _ in range(n_buf + 1):                                 # one being filled, one in flight, one being consumed
-            free_q.put(torch.empty(cap_vals, dtype=torch.int16).pin_memory())
+        pinned = [_take_pinned(cap_vals) for _ in range(n_buf + 1)]        # one being filled, one in flight, one being consumed
+        for t in pinned:
+            free_q.put(t)
         pool = ThreadPoolExecutor(max_workers=self.readers)
         th = threading.Thread(target=self._reader, args=(groups, out_q, free_q, pool), daemon=True)
         th.start()
+        self._mark("buffers, reader started")
         cur = torch.cuda.current_stream(dev)
 
         def enqueue_frontend(slot, item):
@@ -268,6 +320,7 @@ class DetectionPipeline:
                 pending = None if nxt is None else ((slot + 1) % n_buf, nxt, enqueue_frontend((slot + 1) % n_buf, nxt))
                 cur.wait_event(fe_done[slot])
                 fe_done[slot].synchronize()
+                self._mark(f"group of {len(g.files)} files transformed")
                 free_q.put(host)                                    # H2D done: the pinned buffer can be refilled
                 self.counts["t_front_us"] += int(fe_start[slot].elapsed_time(fe_done[slot]) * 1e3)
                 good = []
@@ -298,6 +351,8 @@ class DetectionPipeline:
                             c["detections"] += sum(len(v["scores"]) for v in output.values())
                             c["t_model_us"] += int((t1 - t0) * 1e6); c["t_post_us"] += int((t2 - t1) * 1e6)
                             n_done += 1
+                            if self.counts["files"] <= 2:
+                                self._mark(f"file {self.counts['files']} merged")
                             yield info.path, output
                             t0 = time.perf_counter()
                         good = []
@@ -315,3 +370,11 @@ class DetectionPipeline:
             free_q.put(None)                                        # unblock the reader if we stop early
             pool.shutdown(wait=False, cancel_futures=True)
             torch.cuda.synchronize(dev)
+            th.join(timeout=10.0)                                   # the reader no longer writes into the pinned buffers
+            if not th.is_alive():
+                _give_pinned(pinned)
+            self._mark("done")
+            if self._trace:
+                import sys
+                t0 = self._trace[0][1]
+                print("[pipeline] " + "; ".join(f"{lab} +{(t - t0) * 1e3:.1f} ms" for lab, t in self._trace[1:]), file=sys.stderr)
