@@ -224,8 +224,9 @@ class GraphedDetector:
     def detect_tiles(self, tiles, min_score, bs, nms_thresh=0.3):
         """`run_detection.detect_tiles` for this detector: the reference's batching (run_detection.py:47-67) as a
         software pipeline (see `detect_stream`)."""
-        for outputs in self.detect_stream([tiles], min_score, bs, nms_thresh):
-            return outputs
+        with postproc.gc_paused():
+            for outputs in self.detect_stream([tiles], min_score, bs, nms_thresh):
+                return outputs
 
     @torch.no_grad()             # on a generator function: grad mode is switched per resume, not left off across a yield
     def detect_stream(self, files, min_score, bs, nms_thresh=0.3):

@@ -51,7 +51,7 @@ def detect_directory(model, model_args, audio_dir, bird_dict="bird_dict.json", m
             print(f"[rank {rank}] {wav_path}: FAILED: {why}")
         counts.update(pipe.counts)
     else:
-        for wav_path in files:
+        for k, wav_path in enumerate(files):
             tm = {}
             try:
                 output = rd.run_detection(model, model_args, wav_path, bird_dicts_path=bird_dict, min_score=min_score,

@@ -27,6 +27,7 @@ at the end of ``run``, so a second directory in the same process does not pay fo
 """
 from __future__ import annotations
 
+import gc
 import json
 import os
 import queue
@@ -310,6 +311,8 @@ class DetectionPipeline:
                 raise item
             return item
 
+        gc_was_on, last_gc = gc.isenabled(), time.perf_counter()
+        gc.disable()                                                # postproc.gc_paused explains; restored in `finally`
         try:
             nxt = next_group()
             pending = None if nxt is None else (0, nxt, enqueue_frontend(0, nxt))
@@ -366,7 +369,14 @@ class DetectionPipeline:
                         good = good[n_done:k] + good[k + 1:]
                 det_done[slot] = torch.cuda.Event()
                 det_done[slot].record(cur)
+                if gc_was_on and time.perf_counter() - last_gc > 120.0:
+                    # between groups the heap is small; a full collection still walks the interpreter's whole heap
+                    # (~0.1 s), so only every two minutes: cycles (tracebacks of failed files) go here
+                    gc.collect()
+                    last_gc = time.perf_counter()
         finally:
+            if gc_was_on:
+                gc.enable()
             free_q.put(None)                                        # unblock the reader if we stop early
             pool.shutdown(wait=False, cancel_futures=True)
             torch.cuda.synchronize(dev)

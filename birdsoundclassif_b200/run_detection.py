@@ -150,9 +150,9 @@ def detect_tiles(model, tiles: torch.Tensor, min_score: float, bs: int) -> list:
         return model.detect_tiles(tiles, min_score, bs)
     outputs = []
     n_img = len(tiles)
-    for s in range(0, n_img, bs):
-        batch = tiles[s:s + bs]
-        with torch.no_grad():
+    with postproc.gc_paused(), torch.no_grad():
+        for s in range(0, n_img, bs):
+            batch = tiles[s:s + bs]
             outputs.append(model(batch[:, None], min_score=min_score))
     return outputs
 
@@ -174,6 +174,11 @@ def run_detection(model, config, wav_path, bird_dicts_path, min_score=0.5, bs=10
     offered: visualise_outputs must be False)."""
     if visualise_outputs:
         raise NotImplementedError("matplotlib visualisation is out of scope")
+    with postproc.gc_paused():          # the per-tile dictionaries live until the merge below
+        return _run_detection(model, config, wav_path, bird_dicts_path, min_score, bs, timings)
+
+
+def _run_detection(model, config, wav_path, bird_dicts_path, min_score, bs, timings):
     t0 = time.perf_counter()
     fp = File_Processor(wav_path)
     img_db, _ = fp.process_file()

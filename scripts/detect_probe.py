@@ -62,11 +62,20 @@ model, _ = rd.load_model(d)
 rd.patch_reference()
 rd.accelerate_model(model)
 timed(model, "patched + accelerated, eager")
+if os.environ.get("PROBE_SKIP_SLOW"):
+    pass
 g1 = GraphedDetector(model, lanes=1)
 timed(g1, "CUDA graphs, one lane")
 g = GraphedDetector(model, lanes=2)
 timed(g, "CUDA graphs, two lanes")
 print("eager fallback:", g1._eager_only, g._eager_only)
+if os.environ.get("PROBE_NOGC"):
+    import gc
+    gc.collect()
+    gc.disable()
+    timed(g, "two lanes, cyclic GC disabled")
+    timed(model, "eager, cyclic GC disabled")
+    gc.enable()
 if os.environ.get("PROBE_LANES3"):
     timed(GraphedDetector(model, lanes=3), "CUDA graphs, three lanes")
 if not os.environ.get("PROBE_CUDNN_BENCH"):
