@@ -20,6 +20,12 @@ position embedding the reference's ``Joiner`` computes for every level (backbone
 discards it (nbm_model.py:44-46); with ``add_posenc`` it is computed once per shape outside the graph (it depends
 on the shape only).
 
+Two replay LANES (``lanes=2``): each lane has its own stream, graphs, graph memory pool, static buffers, cuBLAS and
+ProposalLayer workspaces -- the weights are shared -- and ``detect_stream`` runs consecutive batches on alternating lanes
+as a software pipeline, across recording boundaries, so that a batch's small late-stage kernels and the host's read of
+M are covered by the other batch's work (13.6 -> 11.4 ms per batch; a third lane is slower).  Each batch is still the
+same kernels on the same inputs: bit-identical to one lane.  Not thread-safe: one caller at a time.
+
 Anything the capture cannot digest (a configuration whose forward still syncs, e.g. ``pyramid_top_n_attn`` = all
 levels with its per-call ``.to(device)``, self_attention.py:27-31) raises at capture time; ``GraphedDetector`` then
 falls back to calling the eager accelerated model and says so once (still the GPU path, no CPU fallback).
@@ -54,7 +60,8 @@ class _Stage2:
 
 class GraphedDetector:
     """``GraphedDetector(model)(batch[:, None], min_score=...)`` == ``model(batch[:, None], min_score=...)`` for a
-    reference NbmModel that went through ``accelerate_model`` (inference only)."""
+    reference NbmModel that went through ``accelerate_model`` (inference only).  ``lanes``: batches kept in flight by
+    ``detect_tiles`` / ``detect_stream`` (a single ``__call__`` uses lane 0)."""
 
     def __init__(self, model, warmup: int = 2, lanes: int = 2):
         head = getattr(model, "head", None)
