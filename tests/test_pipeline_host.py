@@ -207,3 +207,39 @@ def test_detect_stream_names_the_failing_recording():
         for out in det.detect_stream(iter(files), 0.2, 4):
             got.append(out)
     assert ei.value.nbm_file_index == 2 and got == [[[0], [1]]]       # the second recording was still in flight: the caller re-runs it
+
+
+def test_gc_paused_restores_state():
+    import gc
+    from birdsoundclassif_b200 import postproc
+    assert gc.isenabled()
+    with postproc.gc_paused():
+        assert not gc.isenabled()
+        with postproc.gc_paused():          # nested: the inner exit must not switch it back on
+            assert not gc.isenabled()
+        assert not gc.isenabled()
+    assert gc.isenabled()
+    gc.disable()
+    try:
+        with postproc.gc_paused():
+            pass
+        assert not gc.isenabled()           # it was off before: stays off
+    finally:
+        gc.enable()
+    with pytest.raises(ValueError):
+        with postproc.gc_paused():
+            raise ValueError("x")
+    assert gc.isenabled()
+
+
+def test_pinned_pool_take_and_give():
+    import torch
+    from birdsoundclassif_b200 import pipeline
+    if not torch.cuda.is_available():
+        pytest.skip("pinned host memory needs the CUDA runtime")
+    a = pipeline._take_pinned(1000)
+    assert a.is_pinned() and a.numel() >= 1000 and a.dtype == torch.int16
+    pipeline._give_pinned([a])
+    b = pipeline._take_pinned(10)
+    assert b.data_ptr() == a.data_ptr()      # reused
+    pipeline._give_pinned([b])
