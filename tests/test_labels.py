@@ -135,3 +135,32 @@ def test_gpu_long_recording_with_labels(monkeypatch):
     # the call that starts at 3.9 s is clipped to the end of piece 0 (t_end 4.0 s -> the piece's last frames)
     a0 = H.annotations_from_frame(ann[0])
     assert any(b[2] == 1023 or b[2] >= 300 for _, boxes, _ in a0 for b in boxes)
+
+
+@pytest.mark.parametrize("seed,ext,n_img,n", [(101, "wav", 12, 60), (102, "mp3", 30, 200), (103, "wav", 1, 8), (104, "wav", 300, 400)])
+def test_box_table_against_the_live_reference(seed, ext, n_img, n):
+    """Container only (needs the reference checkout): random annotation tables through the reference's own
+    merge_and_filter_labels (a stub File_Processor: no audio involved) and through labels.merge_and_filter_labels."""
+    from oracle import make_golden as mg, ref_shims
+    if not ref_shims.have_reference():
+        pytest.skip("no reference checkout")
+    pd_mod = ref_shims.ref("nbm_model.nbm_datasets.prepare_dataset")
+    c = _consts()
+    rng = np.random.default_rng(seed)
+    name = f"rec_{seed}"
+    table = mg.random_label_table(rng, name, n, (n_img * 819 + 205) * c["DT"])
+    fp = pd_mod.File_Processor(f"/nowhere/{name}.{ext}", "", table)
+    for k, v in c.items():
+        setattr(fp, k, v)
+    want = fp.merge_and_filter_labels([None] * n_img)
+    got = labels.merge_and_filter_labels(table, name, ext, n_img, c)
+    assert H.annotations_from_frame(got) == H.annotations_from_frame(want)
+    # and the padding steps, against the reference's split_power_spec on an index image (its reflect of a row of column
+    # numbers IS the source map)
+    T = (n_img - 1) * 819 + int(rng.integers(1, 1024))
+    fp.spectrogram_length = T
+    img = np.arange(T, dtype=np.float64)[None, :].repeat(2, axis=0)
+    tiles = fp.split_power_spec([img])
+    w_last = T - (len(tiles) - 1) * 819
+    src = labels.labelled_pad_map(w_last, 1024, labels.empty_width_of(labels.file_rows(table, name), T, c["DT"]))
+    np.testing.assert_array_equal(np.asarray(tiles[-1])[0], src + (len(tiles) - 1) * 819)
