@@ -61,3 +61,26 @@ def test_product_code_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"
+
+
+def test_ctypes_argument_counts_match_the_header():
+    """Every declaration of include/nbm_b200.h against the ctypes table: same number of parameters, pointer parameters
+    bound as pointers (a drifted binding would pass garbage without any error at the call)."""
+    header = open(os.path.join(ROOT, "include", "nbm_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    header = re.sub(r"//[^\n]*", "", header)
+    decls = re.findall(r"\b(nbm_[a-z_0-9]+)\s*\(([^;{}]*?)\)\s*;", header, flags=re.S)
+    seen = 0
+    for name, args in decls:
+        if name not in _lib.SIGNATURES:
+            continue
+        params = [a.strip() for a in args.split(",")] if args.strip() not in ("", "void") else []
+        _, argtypes = _lib.SIGNATURES[name]
+        assert len(params) == len(argtypes), f"{name}: header has {len(params)} parameters, ctypes table {len(argtypes)}"
+        for p, t in zip(params, argtypes):
+            is_ptr = "*" in p or "cudaStream_t" in p
+            bound_ptr = t in (C.c_void_p, C.c_char_p) or hasattr(t, "contents") or getattr(t, "_type_", None) == "P"
+            if is_ptr:
+                assert bound_ptr or issubclass(t, C._Pointer) or t is C.c_void_p, f"{name}: `{p}` bound as {t}"
+        seen += 1
+    assert seen == len(_lib.SIGNATURES)
