@@ -22,8 +22,8 @@ The detector itself is whatever ``model`` is: the reference's NbmModel, eager, o
 (``run_detection.detect_stream``), so a graphed detector stays busy across file boundaries.
 
 Start-up matters for short directories (BASELINE configs[0] is 16 files, 0.6 s): the pipeline's private front-end
-plan (twiddle tables, workspace) and its pinned / device buffers are taken from process-wide pools and given back
-at the end of ``run``, so a second directory in the same process does not pay for them again.
+plan (twiddle tables, workspace) and its pinned host buffers are taken from process-wide pools and given back
+at the end of ``run`` (the device buffers come from torch's caching allocator), so a second directory in the same process does not pay for them again.
 """
 from __future__ import annotations
 
@@ -152,17 +152,20 @@ _PINNED_POOL: list = []         # idle pinned int16 buffers
 
 
 def _take_plan(fe_args):
-    """A front-end plan nobody else is using (a plan owns one workspace and one side stream: one caller at a time)."""
+    """A front-end plan nobody else is using (a plan owns one workspace and one side stream: one caller at a time), on the
+    current device."""
+    key = (torch.cuda.current_device(),) + tuple(fe_args)
     with _POOL_LOCK:
-        idle = _PLAN_POOL.get(tuple(fe_args))
+        idle = _PLAN_POOL.get(key)
         if idle:
             return idle.pop()
     return FrontendPlan(*fe_args)
 
 
 def _give_plan(fe_args, plan):
+    key = (plan.device.index if plan.device.index is not None else torch.cuda.current_device(),) + tuple(fe_args)
     with _POOL_LOCK:
-        _PLAN_POOL.setdefault(tuple(fe_args), []).append(plan)
+        _PLAN_POOL.setdefault(key, []).append(plan)
 
 
 def _take_pinned(n_values: int) -> torch.Tensor:
