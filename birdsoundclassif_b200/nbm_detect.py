@@ -20,14 +20,29 @@ from . import run_detection as rd
 from . import sharding
 
 
+def _size(path: str) -> int:
+    try:
+        return os.path.getsize(path)
+    except OSError:
+        return 0
+
+
 def detect_directory(model, model_args, audio_dir, bird_dict="bird_dict.json", min_score=0.2, bs=4,
                      rank=0, world=1, skip_done=False, verbose=True, pipelined=True, group_tiles=1024,
-                     json_sidecar=False) -> dict:
+                     json_sidecar=False, balance="duration") -> dict:
     """This rank's share of ``audio_dir/*.wav`` -> sibling ``.txt`` files (nbm_detect.py:23-29).  ``pipelined``: wav
     decoding, the batched front-end and the detector overlap across files (pipeline.DetectionPipeline); otherwise the
     reference's one-file-at-a-time loop through ``run_detection``.  Same outputs either way.  ``json_sidecar``: also
-    write ``<wav>.json`` (the same dictionary as JSON; the ``.txt`` is ``str(dict)``, readable only by ``ast.literal_eval``)."""
-    files = sharding.shard_files(glob.glob(os.path.join(audio_dir, "*.wav")), rank, world)
+    write ``<wav>.json`` (the same dictionary as JSON; the ``.txt`` is ``str(dict)``, readable only by ``ast.literal_eval``).
+    ``balance``: how the directory is split over ``world`` ranks -- "duration" (longest file first onto the least loaded
+    rank, SURVEY 8e) or "name" (``sorted(files)[rank::world]``); the union over the ranks is the directory either way."""
+    paths = glob.glob(os.path.join(audio_dir, "*.wav"))
+    if world > 1 and balance == "duration":
+        # longest first onto the least loaded rank, by file size (PCM: bytes ~ duration); every rank computes the same
+        # partition from the same directory listing.  Equal-sized files fall back to the name-order round robin.
+        files = sharding.shard_by_duration([(p, _size(p)) for p in paths], rank, world)
+    else:
+        files = sharding.shard_files(paths, rank, world)
     if skip_done:
         files = [f for f in files if not os.path.exists(f.replace(".wav", ".txt"))]
     counts = dict.fromkeys(sharding.COUNT_FIELDS, 0)
@@ -84,6 +99,8 @@ def main(argv=None):
     parser.add_argument("--no_pipeline", action="store_true", help="one file at a time, as the reference loops")
     parser.add_argument("--no_graphs", action="store_true", help="run the detector eagerly instead of replaying CUDA graphs")
     parser.add_argument("--group_tiles", type=int, default=1024, help="detector tiles per front-end batch (pipelined)")
+    parser.add_argument("--balance", choices=["duration", "name"], default="duration",
+                        help="multi-GPU split of the directory: longest file first onto the least loaded rank, or name order round robin")
     args = parser.parse_args(argv)
     assert os.path.isfile(args.bird_dict), "Missing dictionary of bird species names --> bird_dict.json."
 
@@ -103,7 +120,7 @@ def main(argv=None):
         model = GraphedDetector(model)
     counts = detect_directory(model, model_args, args.audio_dirp, args.bird_dict, args.min_score, args.bs,
                               rank, world, args.skip_done, pipelined=not args.no_pipeline, group_tiles=args.group_tiles,
-                              json_sidecar=args.json)
+                              json_sidecar=args.json, balance=args.balance)
     per_rank = sharding.gather_counts(counts, device=torch.device("cuda", local))
     if rank == 0:
         print(json.dumps({"per_rank": per_rank, "totals": sharding.totals(per_rank)}))

@@ -57,3 +57,43 @@ def test_count_gather_gloo_world2():
 def test_single_process_gather_is_identity():
     out = sharding.gather_counts(dict(files=3, tiles=7))
     assert out[0]["files"] == 3 and out[0]["tiles"] == 7 and out[0]["frames"] == 0
+
+
+def test_duration_balance_quality_and_equal_sizes():
+    # equal sizes: exactly the name-order round robin (the bench's 16 x 30 s directory keeps its partition)
+    files = [(f"rec_{i:04d}.wav", 2646044) for i in range(16)]
+    for world in (1, 2, 4, 8):
+        for r in range(world):
+            assert sharding.shard_by_duration(files, r, world) == sharding.shard_files([f for f, _ in files], r, world)
+    # a night of mixed lengths: one long recording does not pile up with others on the same rank
+    mixed = [("long.wav", 3000)] + [(f"s{i:02d}.wav", 100) for i in range(30)]
+    loads = [sum(dict(mixed)[p] for p in sharding.shard_by_duration(mixed, r, 4)) for r in range(4)]
+    assert max(loads) == 3000 and sorted(loads)[:3] == [1000, 1000, 1000]
+    rr = [sum(dict(mixed)[p] for p in sharding.shard_files([f for f, _ in mixed], r, 4)) for r in range(4)]
+    assert max(rr) > max(loads)
+
+
+def test_detect_directory_partitions_by_duration(tmp_path, monkeypatch):
+    """nbm_detect.detect_directory's file selection (no GPU: the loop body is stubbed): the ranks' shares are disjoint,
+    cover the directory, and follow the duration balance unless balance='name'."""
+    from birdsoundclassif_b200 import nbm_detect
+    sizes = {"a.wav": 5000, "b.wav": 100, "c.wav": 100, "d.wav": 100, "e.wav": 4000}
+    for name, n in sizes.items():
+        (tmp_path / name).write_bytes(b"\\0" * n)
+    seen = {}
+
+    def fake_run_detection(model, args, wav_path, **kw):
+        seen.setdefault(kw["_rank"], []).append(os.path.basename(wav_path))
+        raise RuntimeError("stub")                       # counted as failed, no output written
+
+    for balance, want in (("duration", [["a.wav"], ["b.wav", "c.wav", "d.wav", "e.wav"]]),
+                          ("name", [["a.wav", "c.wav", "e.wav"], ["b.wav", "d.wav"]])):
+        seen.clear()
+        for rank in range(2):
+            monkeypatch.setattr(nbm_detect.rd, "run_detection",
+                                lambda *a, _r=rank, **kw: fake_run_detection(*a, _rank=_r, **kw))
+            monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+            c = nbm_detect.detect_directory(None, None, str(tmp_path), rank=rank, world=2, verbose=False,
+                                            pipelined=False, balance=balance)
+            assert c["files"] == 0 and c["failed"] == len(want[rank])
+        assert [sorted(seen[r]) for r in range(2)] == want
