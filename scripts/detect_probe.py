@@ -62,8 +62,6 @@ model, _ = rd.load_model(d)
 rd.patch_reference()
 rd.accelerate_model(model)
 timed(model, "patched + accelerated, eager")
-if os.environ.get("PROBE_SKIP_SLOW"):
-    pass
 g1 = GraphedDetector(model, lanes=1)
 timed(g1, "CUDA graphs, one lane")
 g = GraphedDetector(model, lanes=2)
